@@ -1,0 +1,149 @@
+// TEST INFRASTRUCTURE ONLY -- C entry points of the CPU oracle (loaded with ctypes from
+// oracle/oracle.py by tests/, __graft_entry__.smoke() and bench.py's CPU legs).
+// The product (libctdirect_b200.so) never links or loads this file.
+#include <cstdio>
+#include <memory>
+#include <string>
+
+#include "docp_oracle.hpp"
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+using namespace oracle;
+
+namespace {
+
+struct ModelBase {
+    virtual ~ModelBase() {}
+    virtual void dims(int64_t* out) = 0;  // nvar, ncon, nnzj, nnzh, nx, nu, nv, np, nb, N, step_block, cblock
+    virtual void flags(int* out) = 0;     // free_t0, free_tf, lagrange, mayer, max
+    virtual void structure(int which, int64_t* rows, int64_t* cols) = 0;
+    virtual void bounds(double* lvar, double* uvar, double* lcon, double* ucon) = 0;
+    virtual void x0(double* x) = 0;
+    virtual void time_grid(const double* x, double* t) = 0;
+    virtual double obj(const double* x) = 0;
+    virtual void cons(const double* x, double* c) = 0;
+    virtual void derivs(const double* x, const double* y, double sigma, double* grad, double* jvals,
+                        double* hvals, int64_t* dropped) = 0;
+};
+
+template <class P, int SCH>
+struct Model : ModelBase {
+    Docp<P, SCH> d;
+    Pattern jp, hp;
+    Model(int N, const double* tg, int ntg, const double* par, int npar, int pmode)
+        : d(N, tg, ntg, par, npar, pmode) {
+        jp = d.jacobian_pattern();
+        hp = d.hessian_pattern();
+    }
+    void dims(int64_t* o) override {
+        o[0] = d.nvar; o[1] = d.ncon; o[2] = jp.nnz(); o[3] = hp.nnz();
+        o[4] = P::nx; o[5] = P::nu; o[6] = P::nv; o[7] = P::np; o[8] = P::nb; o[9] = d.N;
+        o[10] = d.step_block; o[11] = d.cblock;
+    }
+    void flags(int* o) override {
+        o[0] = P::free_t0; o[1] = P::free_tf; o[2] = P::has_lagrange; o[3] = P::has_mayer; o[4] = P::is_max;
+    }
+    void structure(int which, int64_t* rows, int64_t* cols) override {
+        const Pattern& p = which == 0 ? jp : hp;
+        std::copy(p.rows.begin(), p.rows.end(), rows);
+        std::copy(p.cols.begin(), p.cols.end(), cols);
+    }
+    void bounds(double* lvar, double* uvar, double* lcon, double* ucon) override {
+        d.variable_bounds(lvar, uvar);
+        d.constraint_bounds(lcon, ucon);
+    }
+    void x0(double* x) override { d.initial_guess(x); }
+    void time_grid(const double* x, double* t) override {
+        PlainAcc a{x};
+        for (int i = 1; i <= d.N + 1; ++i) t[i - 1] = d.time_at(a, i);
+    }
+    double obj(const double* x) override { return d.objective(x); }
+    void cons(const double* x, double* c) override { d.constraints(x, c); }
+    void derivs(const double* x, const double* y, double sigma, double* grad, double* jvals, double* hvals,
+                int64_t* dropped) override {
+        typename Docp<P, SCH>::DerivOut o;
+        o.jp = &jp; o.jvals = jvals;
+        o.hp = &hp; o.hvals = hvals;
+        o.grad = grad;
+        d.derivatives(x, y, sigma, o);
+        if (dropped) { dropped[0] = o.dropped_j; dropped[1] = o.dropped_h; }
+    }
+};
+
+template <class P>
+ModelBase* make_for_problem(int sch, int N, const double* tg, int ntg, const double* par, int npar, int pm) {
+    switch (sch) {
+        case TRAPEZE: return new Model<P, TRAPEZE>(N, tg, ntg, par, npar, pm);
+        case MIDPOINT: return new Model<P, MIDPOINT>(N, tg, ntg, par, npar, pm);
+        case GL1_CONST: return new Model<P, GL1_CONST>(N, tg, ntg, par, npar, pm);
+        case GL2_CONST: return new Model<P, GL2_CONST>(N, tg, ntg, par, npar, pm);
+        case GL3_CONST: return new Model<P, GL3_CONST>(N, tg, ntg, par, npar, pm);
+        case GL2_STAGEWISE: return new Model<P, GL2_STAGEWISE>(N, tg, ntg, par, npar, pm);
+        case GL3_STAGEWISE: return new Model<P, GL3_STAGEWISE>(N, tg, ntg, par, npar, pm);
+    }
+    return nullptr;
+}
+
+thread_local std::string g_err;
+
+}  // namespace
+
+extern "C" {
+
+const char* orc_last_error() { return g_err.c_str(); }
+
+void* orc_create(const char* problem, const char* scheme, int grid_size, const double* time_grid, int n_time_grid,
+                 const double* params, int nparams, int pattern_mode) {
+    try {
+        int sch = scheme_from_name(scheme);
+        if (sch < 0) { g_err = std::string("Unknown discretization method: ") + scheme; return nullptr; }
+        std::string p = problem;
+        ModelBase* m = nullptr;
+#define ORC_P(T) if (p == T::name) m = make_for_problem<T>(sch, grid_size, time_grid, n_time_grid, params, nparams, pattern_mode);
+        ORC_P(Goddard)
+        ORC_P(GoddardAll)
+        ORC_P(DoubleIntegratorMinEnergy)
+        ORC_P(DoubleIntegratorMinTf)
+        ORC_P(StagewiseScalar)
+        ORC_P(BolzaFreeTf)
+        ORC_P(VanDerPol)
+        ORC_P(RobotArm)
+#undef ORC_P
+        if (!m) g_err = std::string("unknown problem: ") + problem;
+        return m;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+void orc_destroy(void* h) { delete static_cast<ModelBase*>(h); }
+void orc_dims(void* h, int64_t* out12) { static_cast<ModelBase*>(h)->dims(out12); }
+void orc_flags(void* h, int* out5) { static_cast<ModelBase*>(h)->flags(out5); }
+void orc_jac_structure(void* h, int64_t* rows, int64_t* cols) { static_cast<ModelBase*>(h)->structure(0, rows, cols); }
+void orc_hess_structure(void* h, int64_t* rows, int64_t* cols) { static_cast<ModelBase*>(h)->structure(1, rows, cols); }
+void orc_bounds(void* h, double* lvar, double* uvar, double* lcon, double* ucon) {
+    static_cast<ModelBase*>(h)->bounds(lvar, uvar, lcon, ucon);
+}
+void orc_x0(void* h, double* x) { static_cast<ModelBase*>(h)->x0(x); }
+void orc_time_grid(void* h, const double* x, double* t) { static_cast<ModelBase*>(h)->time_grid(x, t); }
+double orc_obj(void* h, const double* x) { return static_cast<ModelBase*>(h)->obj(x); }
+void orc_cons(void* h, const double* x, double* c) { static_cast<ModelBase*>(h)->cons(x, c); }
+// any of grad / jvals / hvals may be NULL; y may be NULL (treated as 0)
+void orc_derivs(void* h, const double* x, const double* y, double sigma, double* grad, double* jvals,
+                double* hvals, int64_t* dropped2) {
+    static_cast<ModelBase*>(h)->derivs(x, y, sigma, grad, jvals, hvals, dropped2);
+}
+int orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
+}  // extern "C"
