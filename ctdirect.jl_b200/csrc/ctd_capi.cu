@@ -1,0 +1,202 @@
+// extern "C" entry points declared in include/ctdirect_b200.h.
+#include <cstring>
+#include <exception>
+#include <string>
+
+#include "../../include/ctdirect_b200.h"
+#include "ctd_model.hpp"
+
+using namespace ctd;
+
+struct ctd_model_s {
+    Model* m;
+};
+
+namespace {
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code == 0 ? -1 : code;
+}
+
+template <class Fn>
+int guarded(Fn&& fn) {
+    try {
+        fn();
+        return 0;
+    } catch (const CtdError& e) {
+        return fail(e.code, e.msg);
+    } catch (const std::exception& e) {
+        return fail(-1, e.what());
+    } catch (...) {
+        return fail(-1, "unknown error");
+    }
+}
+
+int check(ctd_handle h) {
+    if (!h || !h->m) return fail(-2, "invalid handle");
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
+const char* ctd_last_error(void) { return g_err.c_str(); }
+
+int64_t ctd_list_models(char* buf, int64_t buflen) {
+    std::string s;
+    for (const Registration& r : registry())
+        s += r.info.problem + " " + r.info.scheme + " " + (r.info.pattern_mode ? "corrected" : "reference") + "\n";
+    if (buf && buflen > 0) {
+        const size_t n = std::min<size_t>(s.size(), (size_t)buflen - 1);
+        std::memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return (int64_t)s.size() + 1;
+}
+
+int ctd_create(const ctd_desc* d, ctd_handle* out) {
+    if (!d || !out || !d->problem || !d->scheme) return fail(-2, "ctd_create: NULL argument");
+    *out = nullptr;
+    return guarded([&] {
+        const Registration* reg = nullptr;
+        bool scheme_known = false, problem_known = false;
+        for (const Registration& r : registry()) {
+            if (r.info.scheme == d->scheme) scheme_known = true;
+            if (r.info.problem == d->problem) problem_known = true;
+            if (r.info.problem == d->problem && r.info.scheme == d->scheme) {
+                if (r.info.pattern_mode == d->pattern_mode) reg = &r;
+                // a pair without quirks is only compiled in reference mode: both modes coincide
+                else if (!reg && r.info.pattern_mode == 0) reg = &r;
+            }
+        }
+        if (!reg) {
+            if (!scheme_known)  // same wording as the reference's error, DOCP_data.jl:343-348
+                throw CtdError{-4, std::string("Unknown discretization method: ") + d->scheme};
+            if (!problem_known) throw CtdError{-5, std::string("unknown problem: ") + d->problem};
+            throw CtdError{-5, "this (problem, scheme) pair is not compiled in"};
+        }
+        if (d->pattern_mode != 0 && d->pattern_mode != 1) throw CtdError{-2, "pattern_mode must be 0 or 1"};
+        Model* m = new Model(*reg, d->grid_size, d->time_grid, d->n_time_grid, d->params, d->n_params,
+                             d->batch < 1 ? 1 : d->batch, d->device);
+        *out = new ctd_model_s{m};
+    });
+}
+
+int ctd_destroy(ctd_handle h) {
+    if (!h) return 0;
+    delete h->m;
+    delete h;
+    return 0;
+}
+
+int ctd_dims(ctd_handle h, int64_t* nvar, int64_t* ncon, int64_t* nnzj, int64_t* nnzh) {
+    if (int e = check(h)) return e;
+    if (nvar) *nvar = h->m->nvar();
+    if (ncon) *ncon = h->m->ncon();
+    if (nnzj) *nnzj = h->m->nnzj();
+    if (nnzh) *nnzh = h->m->nnzh();
+    return 0;
+}
+
+int ctd_info(ctd_handle h, int64_t out[16]) {
+    if (int e = check(h)) return e;
+    const ElemInfo& f = h->m->info();
+    const int64_t v[16] = {f.nx, f.nu, f.nv, f.np, f.nb, h->m->N(), f.blk, f.cb, h->m->batch(),
+                           f.free_t0, f.free_tf, f.lagrange, f.mayer, f.is_max, f.npar, f.stage};
+    std::memcpy(out, v, sizeof(v));
+    return 0;
+}
+
+int ctd_bounds(ctd_handle h, double* lvar, double* uvar, double* lcon, double* ucon) {
+    if (int e = check(h)) return e;
+    return guarded([&] {
+        if (lvar && uvar) h->m->variable_bounds(lvar, uvar);
+        if (lcon && ucon) h->m->constraint_bounds(lcon, ucon);
+    });
+}
+
+int ctd_x0(ctd_handle h, double* x0) {
+    if (int e = check(h)) return e;
+    return guarded([&] { h->m->initial_guess(x0); });
+}
+
+int ctd_time_grid(ctd_handle h, double* s) {
+    if (int e = check(h)) return e;
+    const std::vector<double>& g = h->m->sgrid();
+    std::memcpy(s, g.data(), sizeof(double) * g.size());
+    return 0;
+}
+
+int ctd_jac_structure(ctd_handle h, int64_t* rows, int64_t* cols) {
+    if (int e = check(h)) return e;
+    return guarded([&] { h->m->structure(h->m->jac(), rows, cols); });
+}
+
+int ctd_hess_structure(ctd_handle h, int64_t* rows, int64_t* cols) {
+    if (int e = check(h)) return e;
+    return guarded([&] { h->m->structure(h->m->hess(), rows, cols); });
+}
+
+int ctd_eval(ctd_handle h, int what, const double* x, const double* y, double obj_weight, double* f, double* g,
+             double* c, double* jvals, double* hvals) {
+    if (int e = check(h)) return e;
+    return guarded([&] { h->m->eval_host(what, x, y, obj_weight, f, g, c, jvals, hvals); });
+}
+
+int ctd_eval_dev(ctd_handle h, int what, const double* x, const double* y, double obj_weight, double* f,
+                 double* g, double* c, double* jvals, double* hvals) {
+    if (int e = check(h)) return e;
+    return guarded([&] { h->m->eval_dev(what, x, y, obj_weight, f, g, c, jvals, hvals); });
+}
+
+int ctd_obj(ctd_handle h, const double* x, double* f) {
+    return ctd_eval(h, CTD_OBJ, x, nullptr, 1.0, f, nullptr, nullptr, nullptr, nullptr);
+}
+int ctd_grad(ctd_handle h, const double* x, double* g) {
+    return ctd_eval(h, CTD_GRAD | CTD_OBJ, x, nullptr, 1.0, nullptr, g, nullptr, nullptr, nullptr);
+}
+int ctd_cons(ctd_handle h, const double* x, double* c) {
+    return ctd_eval(h, CTD_CONS, x, nullptr, 1.0, nullptr, nullptr, c, nullptr, nullptr);
+}
+int ctd_jac_coord(ctd_handle h, const double* x, double* vals) {
+    return ctd_eval(h, CTD_JAC, x, nullptr, 1.0, nullptr, nullptr, nullptr, vals, nullptr);
+}
+int ctd_hess_coord(ctd_handle h, const double* x, const double* y, double obj_weight, double* vals) {
+    return ctd_eval(h, CTD_HESS, x, y, obj_weight, nullptr, nullptr, nullptr, nullptr, vals);
+}
+
+int ctd_norms_dev(ctd_handle h, const double* x, double* obj, double* viol) {
+    if (int e = check(h)) return e;
+    return guarded([&] { h->m->norms_dev(x, obj, viol); });
+}
+
+int ctd_norms(ctd_handle h, const double* x, double* obj, double* viol) {
+    if (int e = check(h)) return e;
+    return guarded([&] { h->m->norms_host(x, obj, viol); });
+}
+
+int ctd_set_params(ctd_handle h, const double* params, int32_t n) {
+    if (int e = check(h)) return e;
+    return guarded([&] { h->m->set_params(params, n); });
+}
+
+int ctd_sync(ctd_handle h) {
+    if (int e = check(h)) return e;
+    return guarded([&] { h->m->sync(); });
+}
+
+void* ctd_stream(ctd_handle h) {
+    if (check(h)) return nullptr;
+    void* s = nullptr;
+    guarded([&] { s = (void*)h->m->stream(); });
+    return s;
+}
+
+int64_t ctd_launch_count(ctd_handle h) {
+    if (check(h)) return -1;
+    return h->m->launches();
+}
+
+}  // extern "C"

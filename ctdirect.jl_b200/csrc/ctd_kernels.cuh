@@ -1,0 +1,493 @@
+// Fused DOCP evaluation kernels for sm_100a (FP64), templated on a generated element struct E
+// (csrc/generated/*.cuh) and on the set F of requested outputs:
+//   constraints c(x)            __constraints!      DOCP_functions.jl:80-115
+//   Jacobian values             jac_coord!  on the :manual pattern, CSC order
+//   Lagrangian-Hessian values   hess_coord! on the tril :manual pattern, CSC order
+//   objective / gradient        __objective         DOCP_functions.jl:23-54
+//
+// Work decomposition:
+//   * one thread evaluates one time step (all rows of the step and their analytic derivatives,
+//     straight-line generated code);
+//   * a CTA of T threads owns the T-1 consecutive *column blocks* i0..i0+T-2 of the value arrays
+//     (the columns of the variables (x_i,u_i[,k_i]) of those steps).  Thread 0 re-evaluates the halo
+//     step i0-1, whose derivatives w.r.t. x_{i0} land in block i0;
+//   * every value is written into shared memory at its final CSC position relative to the tile, so
+//     the tile leaves the SM as a handful of contiguous ranges written with 16-byte coalesced stores;
+//   * the irregular ends (column blocks 1, N, N+1, boundary / final-path rows) are handled by one
+//     extra CTA through host-built position tables;
+//   * (v,v) Hessian entries, d/dv of the cost and the Lagrange sum are block-reduced with warp
+//     shuffles into per-CTA partials and summed in a fixed order by the last CTA to finish
+//     (deterministic, no floating-point atomics on global memory).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "ctd_elem_common.cuh"
+
+namespace ctd {
+
+constexpr int MAX_NV = 4;
+constexpr int MAX_NVV = MAX_NV * (MAX_NV + 1) / 2;
+constexpr int MAX_TASKS = 3;
+
+enum : int { F_CONS = 1, F_JAC = 2, F_HESS = 4, F_GRAD = 8, F_OBJ = 16 };
+
+struct EdgeTask {
+    int step;      // 1-based step index
+    int own;       // writes its own column block, its constraint rows and its v-column rows
+    int map_off;   // offset of this task's map inside edge_map
+};
+
+struct EvalArgs {
+    // per-instance arrays: instance b starts at pointer + b * stride
+    const double* x;
+    const double* y;
+    double* c;
+    double* jvals;
+    double* hvals;
+    double* grad;
+    double* obj;
+    const double* params;
+    long long x_stride, y_stride, c_stride, j_stride, h_stride, g_stride;
+    double sigma;
+    const double* sgrid;   // normalized time grid (N+1), or nullptr for the uniform grid j/N
+    int N;
+    int tiles;             // tile CTAs per instance; CTA index `tiles` is the edge CTA
+    long long nvar, ncon;
+    long long jv_base[MAX_NV];    // position of the first value of column v_k in jvals
+    long long hvv_pos[MAX_NVV];   // positions of the (v_a, v_b) entries in hvals (packed lower triangle)
+    double* partials;             // [batch][tiles+1][NRED]
+    unsigned int* counters;       // [batch]
+    // edge tables (identical for every instance)
+    const int* edge_map;
+    const long long* edge_pos;    // destination position of every edge-buffer entry
+    int ne_j, ne_h, ne_g;         // edge-buffer sections: J values, H values, gradient entries
+    int ntask;
+    EdgeTask task[MAX_TASKS];
+    int fp_map_off, bc_map_off;
+};
+
+// ---------------------------------------------------------------------------------------------
+template <class E, int F>
+struct Cfg {
+    static constexpr bool WC = (F & F_CONS) != 0, WJ = (F & F_JAC) != 0, WH = (F & F_HESS) != 0,
+                          WG = (F & F_GRAD) != 0, WO = (F & F_OBJ) != 0;
+    static constexpr int NV = E::NV;
+    static constexpr int NVV = NV * (NV + 1) / 2;
+    static constexpr int R_H = 0, R_G = R_H + (WH ? NVV : 0), R_O = R_G + (WG ? NV : 0);
+    static constexpr int NRED = R_O + (WO ? 1 : 0);
+    static constexpr int NJV = NV * E::JV_STRIDE;
+    // doubles staged in shared memory per owned step
+    static constexpr int PER_STEP = (WC ? E::CB : 0) + (WJ ? E::J_BLOCK + NJV : 0) + (WH ? E::H_BLOCK : 0) +
+                                    (WG ? E::BLK : 0);
+    static constexpr int SMEM_BUDGET = 72 * 1024;
+    static constexpr int T = (PER_STEP * 8 * 127 + 256 <= SMEM_BUDGET) ? 128
+                             : (PER_STEP * 8 * 63 + 256 <= SMEM_BUDGET) ? 64 : 32;
+    static constexpr int OWN = T - 1;  // owned steps per tile
+    // shared-memory sub-buffers (each with 2 doubles of slack so that the staged range can be given
+    // the same 16-byte phase as its destination in global memory)
+    static constexpr int even(int n) { return (n + 3) & ~1; }
+    static constexpr int S_C = 0;
+    static constexpr int S_J = S_C + (WC ? even(OWN * E::CB) : 0);
+    static constexpr int S_JV = S_J + (WJ ? even(OWN * E::J_BLOCK) : 0);
+    static constexpr int JV_ONE = even(OWN * E::JV_STRIDE);
+    static constexpr int S_H = S_JV + (WJ ? NV * JV_ONE : 0);
+    static constexpr int S_G = S_H + (WH ? even(OWN * E::H_BLOCK) : 0);
+    static constexpr int S_RED = S_G + (WG ? even(OWN * E::BLK) : 0);
+    static constexpr int S_END = S_RED + 32 * (NRED > 0 ? NRED : 1) + 2;
+    static constexpr size_t TILE_SMEM = (size_t)S_END * sizeof(double);
+    // edge map layout of one step task
+    static constexpr int M_JO = 0, M_JN = M_JO + E::NJ_OWN, M_JV = M_JN + E::NJ_NEXT, M_HO = M_JV + E::NJ_V,
+                         M_HN = M_HO + E::NH_OWN, M_GO = M_HN + E::NH_NEXT, M_GN = M_GO + E::NG_OWN,
+                         M_STEP = M_GN + E::NG_NEXT;
+    static constexpr int M_FP_J = 0, M_FP_H = M_FP_J + E::NFP_J, M_FP = M_FP_H + E::NFP_H;
+    static constexpr int M_BC_J = 0, M_BC_H = M_BC_J + E::NBC_J, M_BC_G = M_BC_H + E::NBC_H, M_BC = M_BC_G + E::NBC_G;
+};
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double grid_point(const EvalArgs& a, long long j /*0-based node*/) {
+    // DOCP_data.jl:176-214: collect(LinRange(0,1,N+1))[j+1] == fl(j/N) for the default grid
+    return a.sgrid ? a.sgrid[j] : (double)j / (double)a.N;
+}
+
+template <class E>
+__device__ __forceinline__ void time_args(const EvalArgs& a, const double* v, const double* p, long long i,
+                                          TimeArgs<E::NV>& T) {
+    // get_time_grid: DOCP_data.jl:437-458, t_i = t0 + s_i * (tf - t0)
+    const double t0 = E::T0_KIND == 0 ? E::T0_CONST : (E::T0_KIND == 1 ? v[E::T0_IDX > 0 ? E::T0_IDX : 0] : p[E::T0_IDX > 0 ? E::T0_IDX : 0]);
+    const double tf = E::TF_KIND == 0 ? E::TF_CONST : (E::TF_KIND == 1 ? v[E::TF_IDX > 0 ? E::TF_IDX : 0] : p[E::TF_IDX > 0 ? E::TF_IDX : 0]);
+    const double si = grid_point(a, i - 1);
+    const double sp = (i <= a.N) ? grid_point(a, i) : si;
+    T.ti = t0 + si * (tf - t0);
+    T.tp = t0 + sp * (tf - t0);
+    T.hh = T.tp - T.ti;
+#pragma unroll
+    for (int k = 0; k < E::NV; ++k) {
+        double di = 0.0, dp = 0.0;
+        if (E::TF_KIND == 1 && k == E::TF_IDX) { di += si; dp += sp; }
+        if (E::T0_KIND == 1 && k == E::T0_IDX) { di += 1.0 - si; dp += 1.0 - sp; }
+        T.dti[k] = di;
+        T.dtp[k] = dp;
+        T.dh[k] = dp - di;
+    }
+}
+
+// contiguous shared -> global copy; s and g have the same 16-byte phase
+__device__ __forceinline__ void store_range(double* __restrict__ g, const double* __restrict__ s, int n, int tid,
+                                            int nthreads) {
+    const int head = (int)((reinterpret_cast<unsigned long long>(g) >> 3) & 1ull) < n
+                         ? (int)((reinterpret_cast<unsigned long long>(g) >> 3) & 1ull) : n;
+    if (tid == 0 && head) g[0] = s[0];
+    const int n2 = (n - head) >> 1;
+    const double2* __restrict__ s2 = reinterpret_cast<const double2*>(s + head);
+    double2* __restrict__ g2 = reinterpret_cast<double2*>(g + head);
+    for (int k = tid; k < n2; k += nthreads) g2[k] = s2[k];
+    const int done = head + 2 * n2;
+    if (done < n && tid == nthreads - 1) g[done] = s[done];
+}
+
+__device__ __forceinline__ int phase_of(const double* g) {
+    return (int)((reinterpret_cast<unsigned long long>(g) >> 3) & 1ull);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sink of a tile thread: derivative values go to their CSC slot inside the staged tile.
+template <class E, int F>
+struct TileSink {
+    using C = Cfg<E, F>;
+    double* c_;       // own constraint rows
+    double* jo_;      // own column block (Jacobian)
+    double* jn_;      // next column block (Jacobian)
+    double* jv_[E::NV > 0 ? E::NV : 1];  // v columns, this step's rows
+    double* ho_;      // own column block (Hessian)
+    double* go_;      // own gradient block
+    bool owner, giver;
+    double hn_[E::NH_NEXT > 0 ? E::NH_NEXT : 1];
+    double gn_[E::NG_NEXT > 0 ? E::NG_NEXT : 1];
+    double red[C::NRED > 0 ? C::NRED : 1];
+
+    template <int R> __device__ __forceinline__ void c(double v) { if (owner) c_[R] = v; }
+    template <int N> __device__ __forceinline__ void jo(double v) { if (owner) jo_[E::J_OWN(N, 2)] = v; }
+    template <int N> __device__ __forceinline__ void jn(double v) { if (giver) jn_[E::J_NEXT(N, 2)] = v; }
+    template <int N> __device__ __forceinline__ void jv(double v) {
+        if (owner) jv_[E::J_V(N, 1)][E::J_V(N, 2)] = v;
+    }
+    template <int N> __device__ __forceinline__ void ho(double v) { if (owner) ho_[E::H_OWN(N, 2)] = v; }
+    template <int N> __device__ __forceinline__ void hn(double v) { hn_[N] = v; }
+    template <int K> __device__ __forceinline__ void hv(double v) { if (owner) red[C::R_H + K] += v; }
+    template <int N> __device__ __forceinline__ void go(double v) { if (owner) go_[E::G_OWN(N, 2)] = v; }
+    template <int N> __device__ __forceinline__ void gn(double v) { gn_[N] = v; }
+    template <int N> __device__ __forceinline__ void gv(double v) { if (owner) red[C::R_G + E::G_V(N, 2)] += v; }
+};
+
+// Sink of an edge task: values are accumulated into the edge buffer through the host-built map.
+template <class E, int F>
+struct EdgeSink {
+    using C = Cfg<E, F>;
+    double* buf;
+    const int* map;
+    double* crow;     // destination of the constraint rows (global) or nullptr
+    double* red;
+    __device__ __forceinline__ void put(int m, double v) {
+        if (m >= 0) atomicAdd(&buf[m], v);
+    }
+    template <int R> __device__ __forceinline__ void c(double v) { if (crow) crow[R] = v; }
+    template <int N> __device__ __forceinline__ void jo(double v) { put(map[C::M_JO + N], v); }
+    template <int N> __device__ __forceinline__ void jn(double v) { put(map[C::M_JN + N], v); }
+    template <int N> __device__ __forceinline__ void jv(double v) { put(map[C::M_JV + N], v); }
+    template <int N> __device__ __forceinline__ void ho(double v) { put(map[C::M_HO + N], v); }
+    template <int N> __device__ __forceinline__ void hn(double v) { put(map[C::M_HN + N], v); }
+    template <int K> __device__ __forceinline__ void hv(double v) { if (map[C::M_STEP]) red[C::R_H + K] += v; }
+    template <int N> __device__ __forceinline__ void go(double v) { put(map[C::M_GO + N], v); }
+    template <int N> __device__ __forceinline__ void gn(double v) { put(map[C::M_GN + N], v); }
+    template <int N> __device__ __forceinline__ void gv(double v) { if (map[C::M_STEP]) red[C::R_G + E::G_V(N, 2)] += v; }
+};
+
+// final path / boundary elements (edge CTA only): c<R>, j<N>, h<N>, g<N>
+template <class E, int F, int MJ, int MH, int MG>
+struct EdgeElemSink {
+    using C = Cfg<E, F>;
+    double* buf;
+    const int* map;
+    double* crow;
+    double* red;
+    // map codes: >= 0 edge-buffer index, -1 not in the pattern (dropped), <= -2 reduction slot -(m+2)
+    // ((v,v) Hessian entry for h<>, d/dv_k of the cost for g<>)
+    template <int R> __device__ __forceinline__ void c(double v) { if (crow) crow[R] = v; }
+    template <int N> __device__ __forceinline__ void j(double v) {
+        const int m = map[MJ + N];
+        if (m >= 0) atomicAdd(&buf[m], v);
+    }
+    template <int N> __device__ __forceinline__ void h(double v) {
+        const int m = map[MH + N];
+        if (m >= 0) atomicAdd(&buf[m], v);
+        else if (m <= -2) red[C::R_H + (-m - 2)] += v;
+    }
+    template <int N> __device__ __forceinline__ void g(double v) {
+        const int m = map[MG + N];
+        if (m >= 0) atomicAdd(&buf[m], v);
+        else if (m <= -2) red[C::R_G + (-m - 2)] += v;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+template <class E>
+__device__ __forceinline__ void load_step(const double* __restrict__ x, long long nvar, long long i,
+                                          double* __restrict__ z) {
+    const double* xo = x + (i - 1) * E::BLK;
+#pragma unroll
+    for (int k = 0; k < E::NOWN + E::NNEXT; ++k) z[k] = xo[k];
+#pragma unroll
+    for (int k = 0; k < E::NV; ++k) z[E::NOWN + E::NNEXT + k] = x[nvar - E::NV + k];
+}
+
+template <class E, int F>
+__device__ void edge_cta(const EvalArgs& a, const double* __restrict__ x, const double* __restrict__ y,
+                         const double* __restrict__ p, double* c, double* jvals, double* hvals, double* grad,
+                         double* buf, double* red) {
+    using C = Cfg<E, F>;
+    const int tid = threadIdx.x;
+    constexpr int T = C::T;
+    constexpr int NW = T / 32;
+    const int ne = a.ne_j + a.ne_h + a.ne_g;
+    for (int k = tid; k < ne; k += T) buf[k] = 0.0;
+    __syncthreads();
+    // ---- phase 1: the step elements that touch column blocks 1, N and N+1 (one warp each if possible)
+    {
+        const int task = (tid % 32 == 0) ? tid / 32 : -1;
+        for (int k = task; k >= 0 && k < a.ntask; k += NW) {
+            const EdgeTask tk = a.task[k];
+            double z[E::NZ], lam[E::CB];
+            load_step<E>(x, a.nvar, tk.step, z);
+#pragma unroll
+            for (int r = 0; r < E::CB; ++r) lam[r] = (C::WH && y) ? y[(long long)(tk.step - 1) * E::CB + r] : 0.0;
+            TimeArgs<E::NV> Tm;
+            time_args<E>(a, z + E::NOWN + E::NNEXT, p, tk.step, Tm);
+            EdgeSink<E, F> s;
+            s.buf = buf;
+            s.map = a.edge_map + tk.map_off;
+            s.crow = (C::WC && tk.own) ? c + (long long)(tk.step - 1) * E::CB : nullptr;
+            s.red = red;
+            if constexpr (C::WC || C::WJ || C::WH) E::template step<C::WC, C::WJ, C::WH>(z, Tm, p, lam, a.sigma, s);
+            if constexpr (C::WG) E::grad_step(z, Tm, p, s);
+            if constexpr (C::WO) { if (tk.own) red[C::R_O] += E::cost_step(z, Tm, p); }
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: final path constraints g(t_f, x_f, u_f, v)  (DOCP_functions.jl:100)
+    if constexpr (E::NP > 0 && (C::WC || C::WJ || C::WH)) {
+        if (tid == 0) {
+            double z[E::FP_NLOC], lam[E::NP];
+            const long long N = a.N;
+            if (E::FINAL_CONTROL) {
+#pragma unroll
+                for (int k = 0; k < E::NX + E::NU; ++k) z[k] = x[N * E::BLK + k];
+            } else {
+#pragma unroll
+                for (int k = 0; k < E::CTRL_BLK; ++k) z[k] = x[(N - 1) * E::BLK + E::NX + k];
+#pragma unroll
+                for (int k = 0; k < E::NX; ++k) z[E::CTRL_BLK + k] = x[N * E::BLK + k];
+            }
+#pragma unroll
+            for (int k = 0; k < E::NV; ++k) z[E::FP_NLOC - E::NV + k] = x[a.nvar - E::NV + k];
+#pragma unroll
+            for (int r = 0; r < E::NP; ++r) lam[r] = (C::WH && y) ? y[N * E::CB + r] : 0.0;
+            TimeArgs<E::NV> Tm;
+            time_args<E>(a, z + E::FP_NLOC - E::NV, p, N + 1, Tm);
+            EdgeElemSink<E, F, C::M_FP_J, C::M_FP_H, 0> s;
+            s.buf = buf;
+            s.map = a.edge_map + a.fp_map_off;
+            s.crow = C::WC ? c + N * E::CB : nullptr;
+            s.red = red;
+            E::template fpath<C::WC, C::WJ, C::WH>(z, Tm, p, lam, s);
+        }
+        __syncthreads();
+    }
+    // ---- phase 3: boundary constraints + Mayer cost  (DOCP_functions.jl:103-111, 35-39)
+    if (tid == 0) {
+        double z[E::BC_NLOC], lam[E::NB > 0 ? E::NB : 1];
+        const long long N = a.N;
+#pragma unroll
+        for (int k = 0; k < E::NX; ++k) { z[k] = x[k]; z[E::NX + k] = x[N * E::BLK + k]; }
+#pragma unroll
+        for (int k = 0; k < E::NV; ++k) z[2 * E::NX + k] = x[a.nvar - E::NV + k];
+#pragma unroll
+        for (int r = 0; r < E::NB; ++r) lam[r] = (C::WH && y) ? y[a.ncon - E::NB + r] : 0.0;
+        EdgeElemSink<E, F, C::M_BC_J, C::M_BC_H, C::M_BC_G> s;
+        s.buf = buf;
+        s.map = a.edge_map + a.bc_map_off;
+        s.crow = (C::WC && E::NB > 0) ? c + (a.ncon - E::NB) : nullptr;
+        s.red = red;
+        if constexpr (C::WC || C::WJ || C::WH) E::template bc<C::WC, C::WJ, C::WH>(z, p, lam, a.sigma, s);
+        if constexpr (C::WG) E::grad_bc(z, p, s);
+        if constexpr (C::WO) red[C::R_O] += E::mayer(z, p);
+    }
+    __syncthreads();
+    // ---- scatter the edge buffer
+    if constexpr (C::WJ)
+        for (int k = tid; k < a.ne_j; k += T) jvals[a.edge_pos[k]] = buf[k];
+    if constexpr (C::WH)
+        for (int k = tid; k < a.ne_h; k += T) hvals[a.edge_pos[a.ne_j + k]] = buf[a.ne_j + k];
+    if constexpr (C::WG)
+        for (int k = tid; k < a.ne_g; k += T) grad[a.edge_pos[a.ne_j + a.ne_h + k]] = buf[a.ne_j + a.ne_h + k];
+}
+
+template <class E, int F>
+__global__ void __launch_bounds__(Cfg<E, F>::T) ctd_eval_kernel(const EvalArgs a) {
+    using C = Cfg<E, F>;
+    constexpr int T = C::T;
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
+    const long long inst = blockIdx.y;
+
+    const double* __restrict__ x = a.x + inst * a.x_stride;
+    const double* __restrict__ y = a.y ? a.y + inst * a.y_stride : nullptr;
+    const double* __restrict__ p = a.params + inst * (E::NPAR > 0 ? E::NPAR : 1);
+    double* c = C::WC ? a.c + inst * a.c_stride : nullptr;
+    double* jvals = C::WJ ? a.jvals + inst * a.j_stride : nullptr;
+    double* hvals = C::WH ? a.hvals + inst * a.h_stride : nullptr;
+    double* grad = C::WG ? a.grad + inst * a.g_stride : nullptr;
+
+    double red[C::NRED > 0 ? C::NRED : 1];
+#pragma unroll
+    for (int k = 0; k < (C::NRED > 0 ? C::NRED : 1); ++k) red[k] = 0.0;
+
+    if (tile == a.tiles) {
+        edge_cta<E, F>(a, x, y, p, c, jvals, hvals, grad, smem, red);
+    } else {
+        const long long i0 = 2 + (long long)tile * C::OWN;            // first owned step / column block
+        const long long last = (long long)a.N - 1;                    // last regular column block
+        const int nown = (int)((last - i0 + 1) < C::OWN ? (last - i0 + 1) : C::OWN);
+        const long long i = i0 - 1 + tid;                             // this thread's step
+        const bool active = tid <= nown;
+
+        // global destinations of this tile and the matching shared-memory phases
+        double* gC = C::WC ? c + (i0 - 1) * E::CB : nullptr;
+        double* gJ = C::WJ ? jvals + E::J_FIRST + (i0 - 2) * E::J_BLOCK : nullptr;
+        double* gH = C::WH ? hvals + E::H_FIRST + (i0 - 2) * E::H_BLOCK : nullptr;
+        double* gG = C::WG ? grad + (i0 - 1) * E::BLK : nullptr;
+        double* sC = smem + C::S_C + (C::WC ? phase_of(gC) : 0);
+        double* sJ = smem + C::S_J + (C::WJ ? phase_of(gJ) : 0);
+        double* sH = smem + C::S_H + (C::WH ? phase_of(gH) : 0);
+        double* sG = smem + C::S_G + (C::WG ? phase_of(gG) : 0);
+        double* gJV[C::NV > 0 ? C::NV : 1];
+        double* sJV[C::NV > 0 ? C::NV : 1];
+        if constexpr (C::WJ && C::NV > 0) {
+#pragma unroll
+            for (int k = 0; k < C::NV; ++k) {
+                gJV[k] = jvals + a.jv_base[k] + (i0 - 1) * E::JV_STRIDE;
+                sJV[k] = smem + C::S_JV + k * C::JV_ONE + phase_of(gJV[k]);
+            }
+        }
+
+        TileSink<E, F> s;
+#pragma unroll
+        for (int k = 0; k < (C::NRED > 0 ? C::NRED : 1); ++k) s.red[k] = 0.0;
+        s.owner = active && tid >= 1;
+        s.giver = active && tid < nown;
+        s.c_ = sC + (tid - 1) * E::CB;
+        s.jo_ = sJ + (tid - 1) * E::J_BLOCK;
+        s.jn_ = sJ + tid * E::J_BLOCK;
+        s.ho_ = sH + (tid - 1) * E::H_BLOCK;
+        s.go_ = sG + (tid - 1) * E::BLK;
+        if constexpr (C::WJ && C::NV > 0) {
+#pragma unroll
+            for (int k = 0; k < C::NV; ++k) s.jv_[k] = sJV[k] + (tid - 1) * E::JV_STRIDE;
+        }
+
+        if (active) {
+            double z[E::NZ], lam[E::CB];
+            load_step<E>(x, a.nvar, i, z);
+#pragma unroll
+            for (int r = 0; r < E::CB; ++r) lam[r] = (C::WH && y) ? y[(i - 1) * E::CB + r] : 0.0;
+            TimeArgs<E::NV> Tm;
+            time_args<E>(a, z + E::NOWN + E::NNEXT, p, i, Tm);
+            if constexpr (C::WG) {
+                if (s.owner) {
+#pragma unroll
+                    for (int k = 0; k < E::BLK; ++k) s.go_[k] = 0.0;
+                }
+            }
+            if constexpr (C::WC || C::WJ || C::WH) E::template step<C::WC, C::WJ, C::WH>(z, Tm, p, lam, a.sigma, s);
+            if constexpr (C::WG) E::grad_step(z, Tm, p, s);
+            if constexpr (C::WO) { if (s.owner) s.red[C::R_O] += E::cost_step(z, Tm, p); }
+        }
+        if constexpr ((C::WH && E::NH_NEXT > 0) || (C::WG && E::NG_NEXT > 0)) {
+            __syncthreads();
+            if (s.giver) {
+                if constexpr (C::WH) {
+#pragma unroll
+                    for (int n = 0; n < E::NH_NEXT; ++n) sH[tid * E::H_BLOCK + E::H_NEXT(n, 2)] += s.hn_[n];
+                }
+                if constexpr (C::WG) {
+#pragma unroll
+                    for (int n = 0; n < E::NG_NEXT; ++n) sG[tid * E::BLK + E::G_NEXT(n, 2)] += s.gn_[n];
+                }
+            }
+        }
+        __syncthreads();
+        if (nown > 0) {
+            if constexpr (C::WC) store_range(gC, sC, nown * E::CB, tid, T);
+            if constexpr (C::WJ) {
+                store_range(gJ, sJ, nown * E::J_BLOCK, tid, T);
+                if constexpr (C::NV > 0) {
+#pragma unroll
+                    for (int k = 0; k < C::NV; ++k) store_range(gJV[k], sJV[k], nown * E::JV_STRIDE, tid, T);
+                }
+            }
+            if constexpr (C::WH) store_range(gH, sH, nown * E::H_BLOCK, tid, T);
+            if constexpr (C::WG) store_range(gG, sG, nown * E::BLK, tid, T);
+        }
+#pragma unroll
+        for (int k = 0; k < (C::NRED > 0 ? C::NRED : 1); ++k) red[k] = s.red[k];
+    }
+
+    // ---- deterministic reduction of the global sums: (v,v) Hessian entries, d cost / d v, cost
+    if constexpr (C::NRED > 0) {
+        double* sred = smem + C::S_RED;
+        __shared__ int is_last;
+        const int nblk = a.tiles + 1;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < C::NRED; ++k) {
+            double v = red[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((tid & 31) == 0) sred[(tid >> 5) * C::NRED + k] = v;
+        }
+        __syncthreads();
+        double* part = a.partials + (inst * nblk) * C::NRED;
+        if (tid < C::NRED) {
+            double v = 0.0;
+            for (int w = 0; w < T / 32; ++w) v += sred[w * C::NRED + tid];
+            part[(long long)tile * C::NRED + tid] = v;
+            __threadfence();
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned int ticket = atomicAdd(&a.counters[inst], 1u);
+            is_last = (ticket == (unsigned int)(nblk - 1));
+        }
+        __syncthreads();
+        if (is_last) {
+            __threadfence();
+            if (tid < 32) {
+#pragma unroll
+                for (int k = 0; k < C::NRED; ++k) {
+                    double v = 0.0;
+                    for (int b = tid; b < nblk; b += 32) v += __ldcg(&part[(long long)b * C::NRED + k]);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (tid == 0) {
+                        if (C::WH && k < C::R_G) hvals[a.hvv_pos[k - C::R_H]] = v;
+                        else if (C::WG && k < C::R_O) grad[a.nvar - E::NV + (k - C::R_G)] = v;
+                        else if (C::WO && a.obj) a.obj[inst] = v;
+                    }
+                }
+                if (tid == 0) a.counters[inst] = 0u;
+            }
+        }
+    }
+}
+
+}  // namespace ctd

@@ -1,0 +1,73 @@
+// Included by every generated translation unit (csrc/generated/<element>.cu): instantiates the
+// evaluation kernels for one element struct and registers them with the model registry.
+#pragma once
+#include "ctd_kernels.cuh"
+#include "ctd_model.hpp"
+
+namespace ctd {
+
+// the output combinations that are compiled (one kernel each):
+//   cons | jac | hess | obj | cons+obj | grad+obj | cons+jac+hess | everything
+#define CTD_FOR_EACH_FLAGSET(X) X(1) X(2) X(4) X(16) X(17) X(24) X(7) X(31)
+
+template <class E>
+struct ElementLauncher {
+    template <int F>
+    static LaunchCfg cfg_of() {
+        using C = Cfg<E, F>;
+        LaunchCfg c;
+        c.threads = C::T;
+        c.own = C::OWN;
+        c.nred = C::NRED;
+        c.tile_smem = C::TILE_SMEM;
+        c.map_step = C::M_STEP + 1;
+        c.map_fp = C::M_FP;
+        c.map_bc = C::M_BC;
+        return c;
+    }
+    static LaunchCfg cfg(int flags) {
+        switch (flags) {
+#define CTD_X(F) case F: return cfg_of<F>();
+            CTD_FOR_EACH_FLAGSET(CTD_X)
+#undef CTD_X
+        }
+        return LaunchCfg();
+    }
+    static int prepare(int flags, size_t smem) {
+        switch (flags) {
+#define CTD_X(F) \
+    case F: return (int)cudaFuncSetAttribute(ctd_eval_kernel<E, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            CTD_FOR_EACH_FLAGSET(CTD_X)
+#undef CTD_X
+        }
+        return (int)cudaErrorInvalidValue;
+    }
+    static int launch(const EvalArgs& a, int flags, int batch, size_t smem, cudaStream_t st) {
+        dim3 grid((unsigned)(a.tiles + 1), (unsigned)batch, 1);
+        switch (flags) {
+#define CTD_X(F) \
+    case F: ctd_eval_kernel<E, F><<<grid, Cfg<E, F>::T, smem, st>>>(a); break;
+            CTD_FOR_EACH_FLAGSET(CTD_X)
+#undef CTD_X
+            default: return (int)cudaErrorInvalidValue;
+        }
+        return (int)cudaGetLastError();
+    }
+};
+
+template <class E>
+struct ElementRegistrar {
+    ElementRegistrar() {
+        Registration r;
+        r.info = make_elem_info<E>();
+        r.launcher.launch = &ElementLauncher<E>::launch;
+        r.launcher.cfg = &ElementLauncher<E>::cfg;
+        r.launcher.prepare = &ElementLauncher<E>::prepare;
+        register_element(r);
+    }
+};
+
+}  // namespace ctd
+
+#define CTD_REGISTER_ELEMENT(E) \
+    namespace { ctd::ElementRegistrar<E> ctd_registrar_instance; }

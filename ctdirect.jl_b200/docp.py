@@ -1,0 +1,310 @@
+"""Host-side mirror of the reference's interface for the DOCP evaluation path.
+
+Names follow CTDirect.jl (paths relative to the reference tree):
+  Collocation(grid_size, scheme, time_grid)     src/collocation.jl:8-48   (defaults 250 / :midpoint / nothing)
+  discretize(ocp, discretizer) -> DOCP          src/CTDirect.jl:31-50, src/collocation.jl:57-73
+  DOCP.nlp_model() / adnlp_model_builder(...)   src/collocation.jl:90-153 (returns the NLPModels-style model)
+  direct_transcription / nlp_model / DOCP_*     legacy spellings (test/tmp/percival.jl:24, test/benchmark.jl:81-125)
+and, for the model, the NLPModels API [3P] that Ipopt / MadNLP drive:
+  obj, grad, cons, jac_structure, jac_coord, hess_structure, hess_coord(x, y; obj_weight), meta.
+
+Arrays may be numpy arrays (host; copied through the handle, synchronous) or torch CUDA tensors
+(device; no copies, enqueued on the handle's stream).  All compute happens in libctdirect_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+
+CONS, JAC, HESS, GRAD, OBJ = 1, 2, 4, 8, 16
+
+SCHEMES = (
+    "trapeze", "midpoint", "gauss_legendre_2", "gauss_legendre_3",
+    "gauss_legendre_1_constant_control", "gauss_legendre_2_constant_control", "gauss_legendre_3_constant_control",
+)
+
+
+@dataclass
+class Collocation:
+    """Collocation discretizer options (src/collocation.jl:20-42; alias disc_method for scheme)."""
+    grid_size: int = 250
+    scheme: str = "midpoint"
+    time_grid: Optional[np.ndarray] = None
+
+    def __post_init__(self):
+        self.scheme = str(self.scheme).lstrip(":")
+        if self.time_grid is not None:
+            self.time_grid = np.ascontiguousarray(self.time_grid, dtype=np.float64)
+
+
+@dataclass
+class Meta:
+    """Subset of NLPModels' NLPModelMeta that CTDirect's builders fill (src/collocation.jl:137-149)."""
+    nvar: int
+    ncon: int
+    nnzj: int
+    nnzh: int
+    x0: np.ndarray
+    lvar: np.ndarray
+    uvar: np.ndarray
+    lcon: np.ndarray
+    ucon: np.ndarray
+    minimize: bool
+    name: str
+
+
+def _is_torch(a):
+    return type(a).__module__.startswith("torch")
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if _is_torch(a):
+        return C.c_void_p(a.data_ptr())
+    return C.c_void_p(a.ctypes.data)
+
+
+class DOCP:
+    """Discretised optimal control problem bound to one GPU (DOCP struct, src/DOCP_data.jl:265-366)."""
+
+    def __init__(self, ocp, grid_size: int = 250, scheme: str = "midpoint", time_grid=None, params=None,
+                 pattern_mode: str = "reference", batch: int = 1, device: int = 0, disc_method: Optional[str] = None):
+        lib = _lib.load()
+        name = ocp if isinstance(ocp, str) else ocp.name
+        scheme = str(disc_method if disc_method is not None else scheme).lstrip(":")
+        tg = None if time_grid is None else np.ascontiguousarray(time_grid, dtype=np.float64)
+        par = None if params is None else np.ascontiguousarray(params, dtype=np.float64).ravel()
+        d = _lib.Desc()
+        self._keep = (name.encode(), scheme.encode(), tg, par)
+        d.problem, d.scheme = self._keep[0], self._keep[1]
+        d.grid_size = int(grid_size)
+        d.time_grid = None if tg is None else tg.ctypes.data_as(_lib._dp)
+        d.n_time_grid = 0 if tg is None else len(tg)
+        d.params = None if par is None else par.ctypes.data_as(_lib._dp)
+        d.n_params = 0 if par is None else len(par)
+        d.pattern_mode = {"reference": 0, "corrected": 1}[pattern_mode]
+        d.batch = int(batch)
+        d.device = int(device)
+        h = C.c_void_p()
+        _lib.check(lib.ctd_create(C.byref(d), C.byref(h)))
+        self._h = h
+        self._lib = lib
+        self.problem, self.scheme, self.pattern_mode, self.device = name, scheme, pattern_mode, int(device)
+        v = [C.c_int64() for _ in range(4)]
+        _lib.check(lib.ctd_dims(h, *[C.byref(q) for q in v]))
+        self.dim_NLP_variables, self.dim_NLP_constraints, self.nnzj, self.nnzh = (int(q.value) for q in v)
+        info = np.zeros(16, dtype=np.int64)
+        _lib.check(lib.ctd_info(h, info.ctypes.data_as(_lib._ip)))
+        (self.NLP_x, self.NLP_u, self.NLP_v, self.path_cons, self.boundary_cons, self.steps, self.step_variables_block,
+         self.step_constraints_block, self.batch) = (int(q) for q in info[:9])
+        self.free_t0, self.free_tf, self.lagrange, self.mayer, self.max = (bool(q) for q in info[9:14])
+        self.npar, self.stage = int(info[14]), int(info[15])
+        self._nlp = None
+
+    # convenient aliases
+    nvar = property(lambda self: self.dim_NLP_variables)
+    ncon = property(lambda self: self.dim_NLP_constraints)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._lib.ctd_destroy(h)
+            self._h = None
+
+    # ---- host-only structural queries ------------------------------------------------------------
+    def bounds(self):
+        lvar, uvar = np.empty(self.nvar), np.empty(self.nvar)
+        lcon, ucon = np.empty(self.ncon), np.empty(self.ncon)
+        _lib.check(self._lib.ctd_bounds(self._h, *[a.ctypes.data_as(_lib._dp) for a in (lvar, uvar, lcon, ucon)]))
+        return lvar, uvar, lcon, ucon
+
+    def initial_guess(self):
+        x0 = np.empty(self.nvar)
+        _lib.check(self._lib.ctd_x0(self._h, x0.ctypes.data_as(_lib._dp)))
+        return x0
+
+    def normalized_time_grid(self):
+        s = np.empty(self.steps + 1)
+        _lib.check(self._lib.ctd_time_grid(self._h, s.ctypes.data_as(_lib._dp)))
+        return s
+
+    def jacobian_structure(self):
+        r, c = np.empty(self.nnzj, dtype=np.int64), np.empty(self.nnzj, dtype=np.int64)
+        _lib.check(self._lib.ctd_jac_structure(self._h, r.ctypes.data_as(_lib._ip), c.ctypes.data_as(_lib._ip)))
+        return r, c
+
+    def hessian_structure(self):
+        r, c = np.empty(self.nnzh, dtype=np.int64), np.empty(self.nnzh, dtype=np.int64)
+        _lib.check(self._lib.ctd_hess_structure(self._h, r.ctypes.data_as(_lib._ip), c.ctypes.data_as(_lib._ip)))
+        return r, c
+
+    # ---- evaluation --------------------------------------------------------------------------------
+    def _shape(self, n):
+        return (n,) if self.batch == 1 else (self.batch, n)
+
+    def _empty_like(self, x, n):
+        if _is_torch(x):
+            import torch
+            return torch.empty(self._shape(n), dtype=torch.float64, device=x.device)
+        return np.empty(self._shape(n))
+
+    def _check_in(self, a, n, what):
+        if a is None:
+            return None
+        if _is_torch(a):
+            import torch
+            if a.dtype != torch.float64 or not a.is_cuda or not a.is_contiguous():
+                raise TypeError(f"{what}: expected a contiguous float64 CUDA tensor")
+            if a.device.index != self.device:
+                raise ValueError(f"{what}: tensor is on cuda:{a.device.index}, handle on cuda:{self.device}")
+        else:
+            a = np.ascontiguousarray(a, dtype=np.float64)
+        if a.size if not _is_torch(a) else a.numel():
+            pass
+        size = a.numel() if _is_torch(a) else a.size
+        if size != self.batch * n:
+            raise ValueError(f"{what}: expected {self.batch}x{n} values, got {size}")
+        return a
+
+    def evaluate(self, what: int, x, y=None, obj_weight: float = 1.0, out=None):
+        """One fused kernel launch for the outputs selected by `what` (CONS|JAC|HESS|GRAD|OBJ subset).
+        Returns a dict with keys among 'obj', 'grad', 'cons', 'jac', 'hess'."""
+        x = self._check_in(x, self.nvar, "x")
+        y = self._check_in(y, self.ncon, "y")
+        dev = _is_torch(x)
+        if dev and y is not None and not _is_torch(y):
+            raise TypeError("x and y must both be host arrays or both CUDA tensors")
+        out = dict(out or {})
+        res = {}
+        for bit, key, n in ((OBJ, "obj", 1), (GRAD, "grad", self.nvar), (CONS, "cons", self.ncon),
+                            (JAC, "jac", self.nnzj), (HESS, "hess", self.nnzh)):
+            if what & bit:
+                buf = out.get(key)
+                res[key] = self._check_in(buf, n, key) if buf is not None else self._empty_like(x, n)
+        fn = self._lib.ctd_eval_dev if dev else self._lib.ctd_eval
+        _lib.check(fn(self._h, int(what), _ptr(x), _ptr(y), float(obj_weight), _ptr(res.get("obj")),
+                      _ptr(res.get("grad")), _ptr(res.get("cons")), _ptr(res.get("jac")), _ptr(res.get("hess"))))
+        return res
+
+    def norms(self, x):
+        """Per-instance (objective, max constraint violation): what a batched MPC driver gathers."""
+        x = self._check_in(x, self.nvar, "x")
+        if _is_torch(x):
+            import torch
+            obj = torch.empty(self.batch, dtype=torch.float64, device=x.device)
+            viol = torch.empty(self.batch, dtype=torch.float64, device=x.device)
+            _lib.check(self._lib.ctd_norms_dev(self._h, _ptr(x), _ptr(obj), _ptr(viol)))
+        else:
+            obj, viol = np.empty(self.batch), np.empty(self.batch)
+            _lib.check(self._lib.ctd_norms(self._h, _ptr(x), _ptr(obj), _ptr(viol)))
+        return obj, viol
+
+    def set_params(self, params):
+        par = np.ascontiguousarray(params, dtype=np.float64).ravel()
+        _lib.check(self._lib.ctd_set_params(self._h, par.ctypes.data_as(_lib._dp), len(par)))
+
+    def synchronize(self):
+        _lib.check(self._lib.ctd_sync(self._h))
+
+    @property
+    def cuda_stream(self) -> int:
+        return int(self._lib.ctd_stream(self._h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.ctd_launch_count(self._h))
+
+    # ---- the reference's builder seam ---------------------------------------------------------------
+    def nlp_model(self, initial_guess=None):
+        if self._nlp is None or initial_guess is not None:
+            self._nlp = B200NLPModel(self, initial_guess)
+        return self._nlp
+
+    def adnlp_model_builder(self, initial_guess=None, backend: str = "b200", **kwargs):
+        """Same slot as build_adnlp_model(initial_guess; backend, kwargs...) (src/collocation.jl:90-153)."""
+        if backend not in ("b200", "manual"):
+            raise ValueError("this backend evaluates the :manual pattern on the GPU; backend must be 'b200'")
+        return self.nlp_model(initial_guess)
+
+
+class B200NLPModel:
+    """NLPModels-style model [3P API] whose callbacks run on the B200 (drop-in for the ADNLPModel built at
+    src/collocation.jl:137-149)."""
+
+    def __init__(self, docp: DOCP, initial_guess=None):
+        self.docp = docp
+        lvar, uvar, lcon, ucon = docp.bounds()
+        x0 = docp.initial_guess() if initial_guess is None else np.ascontiguousarray(initial_guess, dtype=np.float64)
+        self.meta = Meta(docp.nvar, docp.ncon, docp.nnzj, docp.nnzh, x0, lvar, uvar, lcon, ucon,
+                         minimize=not docp.max, name=f"{docp.problem}:{docp.scheme}")
+        self.counters = {"neval_obj": 0, "neval_grad": 0, "neval_cons": 0, "neval_jac": 0, "neval_hess": 0}
+
+    def obj(self, x):
+        self.counters["neval_obj"] += 1
+        f = self.docp.evaluate(OBJ, x)["obj"]
+        if _is_torch(f):
+            return f if self.docp.batch > 1 else f.reshape(())
+        return f if self.docp.batch > 1 else float(f[0])
+
+    def grad(self, x, g=None):
+        self.counters["neval_grad"] += 1
+        return self.docp.evaluate(GRAD | OBJ, x, out={"grad": g})["grad"]
+
+    def cons(self, x, c=None):
+        self.counters["neval_cons"] += 1
+        return self.docp.evaluate(CONS, x, out={"cons": c})["cons"]
+
+    def jac_structure(self):
+        return self.docp.jacobian_structure()
+
+    def jac_coord(self, x, vals=None):
+        self.counters["neval_jac"] += 1
+        return self.docp.evaluate(JAC, x, out={"jac": vals})["jac"]
+
+    def hess_structure(self):
+        return self.docp.hessian_structure()
+
+    def hess_coord(self, x, y, vals=None, obj_weight: float = 1.0):
+        self.counters["neval_hess"] += 1
+        return self.docp.evaluate(HESS, x, y, obj_weight, out={"hess": vals})["hess"]
+
+    def eval_all(self, x, y, obj_weight: float = 1.0, out=None):
+        """obj, grad, cons, jac_coord and hess_coord in one launch."""
+        for k in self.counters:
+            self.counters[k] += 1
+        return self.docp.evaluate(CONS | JAC | HESS | GRAD | OBJ, x, y, obj_weight, out=out)
+
+
+# ---- reference entry points ------------------------------------------------------------------------
+def discretize(ocp, discretizer: Optional[Collocation] = None, **kwargs) -> DOCP:
+    """CTDirect.discretize(ocp, Collocation(...)) (src/CTDirect.jl:31-50)."""
+    d = discretizer or Collocation()
+    return DOCP(ocp, grid_size=d.grid_size, scheme=d.scheme, time_grid=d.time_grid, **kwargs)
+
+
+def direct_transcription(ocp, grid_size: int = 250, disc_method: str = "midpoint", time_grid=None, init=None, **kwargs):
+    """Legacy spelling (test/tmp/percival.jl:24): returns (docp, nlp)."""
+    docp = DOCP(ocp, grid_size=grid_size, scheme=disc_method, time_grid=time_grid, **kwargs)
+    return docp, docp.nlp_model(init)
+
+
+def nlp_model(docp: DOCP):
+    return docp.nlp_model()
+
+
+def DOCP_objective(x, docp: DOCP):       # test/benchmark.jl:112
+    return docp.nlp_model().obj(x)
+
+
+def DOCP_constraints(c, x, docp: DOCP):  # DOCP_constraints! test/benchmark.jl:125
+    return docp.nlp_model().cons(x, c)
+
+
+def DOCP_initial_guess(docp: DOCP):      # test/benchmark.jl:81-86
+    return docp.initial_guess()

@@ -1,0 +1,391 @@
+"""Symbolic per-step "elements" of a discretised OCP and their value-slot tables.
+
+For one (OCP, scheme) pair this module builds, with sympy,
+  * the constraint rows of one time step (state equation, stage equations, path constraints) --
+    stepStateConstraints! / stepPathConstraints! of the reference (src/ode/midpoint.jl:124-156,
+    trapeze.jl:118-142, irk.jl:236-308, irk_stagewise.jl:394-460, DOCP_functions.jl:122-140),
+  * the running-cost term of the step (integral(): midpoint.jl:79-116, trapeze.jl:78-110,
+    irk.jl:179-228, irk_stagewise.jl:344-384),
+  * their analytic first and second derivatives with respect to the step's local variables
+    z = (x_i, u_i[, k_i], x_{i+1}[, u_{i+1}], v),
+and, by probing the reference-faithful patterns (gen/patterns.py) on a tiny grid, the offset of
+every derivative value inside the CSC value arrays of an interior column block.
+
+Time enters through t_i, t_{i+1} and h_i = t_{i+1} - t_i, which the kernels compute exactly like
+the reference (t = t0 + s*(tf - t0), DOCP_data.jl:456); they are kept as opaque symbols whose
+derivatives with respect to free t0 / tf are supplied as seeds (s_i, 1 - s_i, and their
+differences), mirroring what forward-mode AD of the reference code produces.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Tuple
+
+import sympy as sp
+
+from . import patterns as pat
+from .ocps import OCP
+
+PROBE_N = 6
+PROBE_I = 3
+
+
+def butcher_symbols(s: int):
+    """Opaque symbols for the tableau (values are defined in the emitted code from the reference's
+    own expressions, irk.jl:41-43,78-80,116-122)."""
+    a = [[sp.Symbol(f"BA{j}{l}") for l in range(s)] for j in range(s)]
+    b = [sp.Symbol(f"BB{j}") for j in range(s)]
+    c = [sp.Symbol(f"BC{j}") for j in range(s)]
+    return a, b, c
+
+
+@dataclass
+class TimeSyms:
+    ti: sp.Symbol
+    tp: sp.Symbol
+    h: sp.Symbol
+    # seeds: d ti / d v_k etc.; zero when v_k is not a free time
+    dti: Dict[int, sp.Symbol]
+    dtp: Dict[int, sp.Symbol]
+    dh: Dict[int, sp.Symbol]
+
+
+class Differ:
+    """Total derivatives with respect to local variables, time symbols folded in by the chain rule."""
+
+    def __init__(self, z, nv_off, nv, ts: TimeSyms):
+        self.z = z
+        self.nv_off = nv_off
+        self.nv = nv
+        self.ts = ts
+
+    def d(self, e, a):
+        e = sp.sympify(e)
+        r = sp.diff(e, self.z[a])
+        k = a - self.nv_off
+        if 0 <= k < self.nv:
+            if k in self.ts.dti:
+                r = r + sp.diff(e, self.ts.ti) * self.ts.dti[k]
+            if k in self.ts.dtp:
+                r = r + sp.diff(e, self.ts.tp) * self.ts.dtp[k]
+            if k in self.ts.dh:
+                r = r + sp.diff(e, self.ts.h) * self.ts.dh[k]
+        return r
+
+
+@dataclass
+class StepElement:
+    ocp: OCP
+    scheme: str
+    L: pat.Layout                      # probe layout (dims + block sizes)
+    pattern_mode: str
+    z: List[sp.Symbol] = field(default_factory=list)
+    lam: List[sp.Symbol] = field(default_factory=list)
+    p: List[sp.Symbol] = field(default_factory=list)
+    sg: sp.Symbol = None
+    ts: TimeSyms = None
+    rows: List[sp.Expr] = field(default_factory=list)        # constraint rows (for derivatives)
+    cost: sp.Expr = sp.Integer(0)                            # running cost of the step
+    # value tables: lists of (local row / a, local col / b, offset, expr)
+    j_own: list = field(default_factory=list)
+    j_next: list = field(default_factory=list)
+    j_v: list = field(default_factory=list)
+    h_own: list = field(default_factory=list)
+    h_next: list = field(default_factory=list)
+    h_vv: list = field(default_factory=list)
+    g_own: list = field(default_factory=list)
+    g_next: list = field(default_factory=list)
+    g_v: list = field(default_factory=list)
+    j_block: int = 0
+    h_block: int = 0
+    j_first: int = 0      # base offset of column block 2 (= size of column block 1)
+    h_first: int = 0
+    jv_stride: int = 0    # values per step inside one v column
+    dropped: list = field(default_factory=list)
+    # c-value code pieces (dynamics evaluations kept apart so that the scheme formula can be
+    # emitted in the reference's association order)
+    cons_code: dict = field(default_factory=dict)
+
+
+def _time_syms(ocp: OCP, prefix=""):
+    ts = TimeSyms(sp.Symbol(prefix + "ti"), sp.Symbol(prefix + "tp"), sp.Symbol(prefix + "hh"), {}, {}, {})
+    for which, spec in ((0, ocp.t0), (1, ocp.tf)):
+        if spec[0] == "var":
+            k = spec[1]
+            ts.dti[k] = sp.Symbol(f"{prefix}dti{k}")
+            ts.dtp[k] = sp.Symbol(f"{prefix}dtp{k}")
+            ts.dh[k] = sp.Symbol(f"{prefix}dh{k}")
+    return ts
+
+
+def dims_of(ocp: OCP) -> pat.Dims:
+    return pat.Dims(ocp.nx, ocp.nu, ocp.nv, ocp.np, ocp.nb, ocp.lagrange is not None, ocp.mayer is not None)
+
+
+def build_step_element(ocp: OCP, scheme: str, pattern_mode: str = "reference") -> StepElement:
+    d = dims_of(ocp)
+    L = pat.Layout(scheme, d, PROBE_N)
+    nx, nu, nv, npc = d.nx, d.nu, d.nv, d.np
+    s = L.stage
+    E = StepElement(ocp, scheme, L, pattern_mode)
+    E.z = [sp.Symbol(f"z{a}") for a in range(L.nz)]
+    E.lam = [sp.Symbol(f"lam{r}") for r in range(L.cblock)]
+    E.p = [sp.Symbol(f"p{k}") for k in range(ocp.npar)]
+    E.sg = sp.Symbol("sg")
+    E.ts = _time_syms(ocp)
+    z, p, ts = E.z, E.p, E.ts
+    v = z[L.n_own + L.n_next:]
+    xi = z[0:nx]
+    xn = z[L.n_own:L.n_own + nx]
+    ti, tp, h = ts.ti, ts.tp, ts.h
+    half = sp.Rational(1, 2)
+
+    def dyn(t, x, u):
+        return [sp.sympify(e) for e in ocp.dynamics(t, x, u, v, p)]
+
+    def lag(t, x, u):
+        return sp.sympify(ocp.lagrange(t, x, u, v, p)) if ocp.lagrange else sp.Integer(0)
+
+    rows = []
+    cost = sp.Integer(0)
+    if scheme == "midpoint":
+        ui = z[nx:nx + nu]
+        tsm = half * (ti + tp)
+        xs = [half * (xi[k] + xn[k]) for k in range(nx)]
+        f = dyn(tsm, xs, ui)
+        rows = [xn[k] - (xi[k] + h * f[k]) for k in range(nx)]
+        cost = h * lag(tsm, xs, ui)
+        u_node = ui
+    elif scheme == "trapeze":
+        ui = z[nx:nx + nu]
+        un = z[L.n_own + nx:L.n_own + nx + nu]
+        fi = dyn(ti, xi, ui)
+        fn = dyn(tp, xn, un)
+        rows = [xn[k] - (xi[k] + half * h * (fi[k] + fn[k])) for k in range(nx)]
+        cost = half * h * (lag(ti, xi, ui) + lag(tp, xn, un))
+        u_node = ui
+    else:
+        A, Bw, Cw = butcher_symbols(s)
+        cb = L.control_block
+        ks = [z[nx + cb + j * nx: nx + cb + (j + 1) * nx] for j in range(s)]
+        if L.stagewise:
+            us = [z[nx + j * nu: nx + (j + 1) * nu] for j in range(s)]
+            u_node = [sum(Bw[j] * us[j][k] for j in range(s)) for k in range(nu)]  # irk_stagewise.jl:197-205
+        else:
+            us = [z[nx:nx + nu]] * s
+            u_node = z[nx:nx + nu]
+        stage_rows = []
+        lsum = sp.Integer(0)
+        for j in range(s):
+            tij = ti + Cw[j] * h
+            xij = [xi[k] + sum(h * A[j][l] * ks[l][k] for l in range(s)) for k in range(nx)]
+            f = dyn(tij, xij, us[j])
+            stage_rows += [ks[j][k] - f[k] for k in range(nx)]
+            lsum = lsum + Bw[j] * lag(tij, xij, us[j])
+        state_rows = [xn[k] - (xi[k] + h * sum(Bw[j] * ks[j][k] for j in range(s))) for k in range(nx)]
+        rows = state_rows + stage_rows
+        cost = h * lsum
+    if npc:
+        rows += [sp.sympify(e) for e in ocp.path(ti, xi, u_node, v, p)]
+    assert len(rows) == L.cblock
+    E.rows = rows
+    E.cost = sp.sympify(cost)
+
+    # ------------------------------------------------------------------ value slots from the probe
+    jr, jc, jptr = pat.jacobian_pattern(L, pattern_mode)
+    hr, hc, hptr = pat.hessian_pattern(L, pattern_mode)
+    B, CB = L.step_block, L.cblock
+    nvar = L.nvar
+
+    def jbase(i):  # 0-based position of the first value of column block i
+        return int(jptr[(i - 1) * B])
+
+    def hbase(i):
+        return int(hptr[(i - 1) * B])
+
+    E.j_block = jbase(PROBE_I + 1) - jbase(PROBE_I)
+    E.h_block = hbase(PROBE_I + 1) - hbase(PROBE_I)
+    E.j_first = jbase(2)
+    E.h_first = hbase(2)
+    for i in range(2, PROBE_N - 1):
+        assert jbase(i + 1) - jbase(i) == E.j_block and hbase(i + 1) - hbase(i) == E.h_block
+
+    def gcol(i, a):  # global 1-based column of local variable a at step i
+        if a < L.n_own + L.n_next:
+            return (i - 1) * B + a + 1
+        return nvar - nv + (a - L.n_own - L.n_next) + 1
+
+    def which(a):
+        return "own" if a < L.n_own else ("next" if a < L.n_own + L.n_next else "v")
+
+    D = Differ(z, L.n_own + L.n_next, nv, ts)
+    jv_stride = None
+    if nv > 0:
+        c0 = int(jptr[nvar - nv])
+        # values per step inside a v column (CB for midpoint/IRK; NP for reference-mode trapeze)
+        cnt = [int(((jr[c0:jptr[nvar - nv + 1]] > (i - 1) * CB) & (jr[c0:jptr[nvar - nv + 1]] <= i * CB)).sum())
+               for i in (PROBE_I, PROBE_I + 1)]
+        assert cnt[0] == cnt[1]
+        jv_stride = cnt[0]
+    E.jv_stride = jv_stride or 0
+
+    for r in range(CB):
+        for a in range(L.nz):
+            expr = sp.simplify(D.d(rows[r], a)) if False else D.d(rows[r], a)
+            offs = []
+            for i in (PROBE_I, PROBE_I + 1):
+                pos = pat.find_pos(jr, jptr, (i - 1) * CB + r + 1, gcol(i, a))
+                if pos < 0:
+                    offs.append(None)
+                    continue
+                w = which(a)
+                if w == "own":
+                    offs.append(pos - jbase(i))
+                elif w == "next":
+                    offs.append(pos - jbase(i + 1))
+                else:
+                    kv = a - L.n_own - L.n_next
+                    offs.append(pos - int(jptr[nvar - nv + kv]) - (i - 1) * jv_stride)
+            assert offs[0] == offs[1], (scheme, r, a, offs)
+            if offs[0] is None:
+                if expr != 0:
+                    E.dropped.append(("J", r, a))
+                continue
+            w = which(a)
+            entry = (r, a, offs[0], expr)
+            (E.j_own if w == "own" else E.j_next if w == "next" else E.j_v).append(entry)
+
+    # Lagrangian of the step and its derivatives
+    lagr = sum(E.lam[r] * rows[r] for r in range(CB)) + E.sg * E.cost
+    grad = [D.d(lagr, a) for a in range(L.nz)]
+    for b in range(L.nz):
+        for a in range(b, L.nz):
+            expr = D.d(grad[a], b)
+            wa, wb = which(a), which(b)
+            if wb == "v":
+                kv1, kv2 = a - L.n_own - L.n_next, b - L.n_own - L.n_next
+                if expr != 0:
+                    E.h_vv.append((kv1, kv2, kv1 * (kv1 + 1) // 2 + kv2, expr))
+                continue
+            offs = []
+            for i in (PROBE_I, PROBE_I + 1):
+                pos = pat.find_pos(hr, hptr, gcol(i, a), gcol(i, b))
+                if pos < 0:
+                    offs.append(None)
+                else:
+                    offs.append(pos - (hbase(i) if wb == "own" else hbase(i + 1)))
+            assert offs[0] == offs[1], (scheme, a, b, offs)
+            if offs[0] is None:
+                if expr != 0:
+                    E.dropped.append(("H", a, b))
+                continue
+            if wb == "own":
+                E.h_own.append((a, b, offs[0], expr))       # owner writes every slot, zeros included
+            elif expr != 0:
+                E.h_next.append((a, b, offs[0], expr))      # accumulated into the next block
+    # coverage: every slot of an interior column block must be written by its owner / the previous step
+    jslots = sorted([e[2] for e in E.j_own] + [e[2] for e in E.j_next])
+    assert jslots == list(range(E.j_block)), (scheme, jslots, E.j_block)
+    hslots = sorted(e[2] for e in E.h_own)
+    assert hslots == list(range(E.h_block)), (scheme, hslots, E.h_block)
+    if nv > 0:
+        for kv in range(nv):
+            sl = sorted(e[2] for e in E.j_v if e[1] - L.n_own - L.n_next == kv)
+            assert sl == list(range(E.jv_stride)), (scheme, sl, E.jv_stride)
+
+    # objective gradient of the running cost
+    if ocp.lagrange is not None:
+        for a in range(L.nz):
+            expr = D.d(E.cost, a)
+            w = which(a)
+            if w == "own":
+                E.g_own.append((a, a, a, expr))
+            elif expr != 0:
+                if w == "next":
+                    E.g_next.append((a, a, a - L.n_own, expr))
+                else:
+                    E.g_v.append((a, a, a - L.n_own - L.n_next, expr))
+    return E
+
+
+@dataclass
+class EdgeElement:
+    """Final-path or boundary(+Mayer) element: dense local Jacobian / packed lower-triangular Hessian."""
+    kind: str
+    nloc: int
+    nrows: int
+    z: List[sp.Symbol]
+    lam: List[sp.Symbol]
+    rows: List[sp.Expr]
+    cost: sp.Expr
+    jac: list   # (r, a, r*nloc+a, expr) nonzero only
+    hess: list  # (a, b, a*(a+1)/2+b, expr) nonzero only
+    grad: list  # (a, a, a, expr) nonzero only (objective part)
+
+
+def build_final_path(ocp: OCP, scheme: str, E: StepElement) -> EdgeElement:
+    """g(t_{N+1}, x_{N+1}, u_f, v): DOCP_functions.jl:100,122-140.  Local order follows the global
+    variable order: (u_f, x_f, v) when u(tf) aliases U_N (common.jl:144-146), (x_f, u_f, v) for trapeze."""
+    L = E.L
+    d = L.dims
+    nx, nu, nv = d.nx, d.nu, d.nv
+    cb = L.control_block
+    nloc = cb + nx + nv
+    z = [sp.Symbol(f"z{a}") for a in range(nloc)]
+    lam = [sp.Symbol(f"lam{r}") for r in range(d.np)]
+    v = z[cb + nx:]
+    if scheme == "trapeze":
+        x, ublk = z[0:nx], z[nx:nx + nu]
+    else:
+        ublk, x = z[0:cb], z[cb:cb + nx]
+    if L.stagewise:
+        _, Bw, _ = butcher_symbols(L.stage)
+        u = [sum(Bw[j] * ublk[j * nu + k] for j in range(L.stage)) for k in range(nu)]
+    else:
+        u = ublk
+    ts = E.ts
+    rows = [sp.sympify(e) for e in ocp.path(ts.ti, x, u, v, E.p)] if d.np else []
+    D = Differ(z, cb + nx, nv, TimeSyms(ts.ti, ts.tp, ts.h, ts.dti, {}, {}))
+    jac, hess = [], []
+    for r, e in enumerate(rows):
+        for a in range(nloc):
+            ex = D.d(e, a)
+            if ex != 0:
+                jac.append((r, a, r * nloc + a, ex))
+    lagr = sum(lam[r] * rows[r] for r in range(len(rows)))
+    g = [D.d(lagr, a) for a in range(nloc)]
+    for a in range(nloc):
+        for b in range(a + 1):
+            ex = D.d(g[a], b)
+            if ex != 0:
+                hess.append((a, b, a * (a + 1) // 2 + b, ex))
+    return EdgeElement("fpath", nloc, len(rows), z, lam, rows, sp.Integer(0), jac, hess, [])
+
+
+def build_boundary(ocp: OCP, E: StepElement) -> EdgeElement:
+    """b(x_1, x_{N+1}, v) rows (DOCP_functions.jl:103-111) + sigma * mayer(x_1, x_{N+1}, v) (l.35-39)."""
+    d = E.L.dims
+    nx, nv = d.nx, d.nv
+    nloc = 2 * nx + nv
+    z = [sp.Symbol(f"z{a}") for a in range(nloc)]
+    lam = [sp.Symbol(f"lam{r}") for r in range(d.nb)]
+    x0, xf, v = z[0:nx], z[nx:2 * nx], z[2 * nx:]
+    rows = [sp.sympify(e) for e in ocp.boundary(x0, xf, v, E.p)] if d.nb else []
+    cost = sp.sympify(ocp.mayer(x0, xf, v, E.p)) if ocp.mayer else sp.Integer(0)
+    jac, hess, grad = [], [], []
+    for r, e in enumerate(rows):
+        for a in range(nloc):
+            ex = sp.diff(e, z[a])
+            if ex != 0:
+                jac.append((r, a, r * nloc + a, ex))
+    lagr = sum(lam[r] * rows[r] for r in range(len(rows))) + E.sg * cost
+    g = [sp.diff(lagr, z[a]) for a in range(nloc)]
+    for a in range(nloc):
+        for b in range(a + 1):
+            ex = sp.diff(g[a], z[b])
+            if ex != 0:
+                hess.append((a, b, a * (a + 1) // 2 + b, ex))
+        ex = sp.diff(cost, z[a])
+        if ex != 0:
+            grad.append((a, a, a, ex))
+    return EdgeElement("bc", nloc, len(rows), z, lam, rows, cost, jac, hess, grad)

@@ -1,0 +1,127 @@
+/* ctdirect_b200.h -- C ABI of the B200-native NLP-evaluation engine for CTDirect.jl's discretised
+ * optimal control problem (DOCP).
+ *
+ * The library (libctdirect_b200.so) replaces, for one discretised OCP, what CTDirect.jl obtains from
+ * ADNLPModels on the CPU: the NLPModels callbacks that Ipopt / MadNLP call every iteration.  Each entry
+ * point names the reference interface it stands for (paths relative to the CTDirect.jl tree; [3P] marks
+ * the NLPModels API implemented by the un-vendored ADNLPModels package that CTDirect wires up in
+ * src/collocation.jl:90-153).
+ *
+ * Conventions
+ *  - return value: 0 = ok, < 0 = usage error, > 0 = CUDA error code; ctd_last_error() gives the message
+ *    (thread-local).  Nothing is thrown across the boundary.  NaN/Inf in results are passed through.
+ *  - all floating-point data are IEEE double; all indices are int64 and 1-BASED, in the order of
+ *    Julia's CSC storage (column by column, rows ascending); the Hessian is the lower triangle.
+ *  - buffers are owned by the caller and never retained after the call returns.
+ *  - functions without suffix take HOST pointers (copied through device buffers owned by the handle,
+ *    and synchronous); the `_dev` twins take DEVICE pointers, enqueue on the handle's stream and return
+ *    without synchronising (ctd_sync waits).
+ *  - batched handles (desc.batch = B > 1) evaluate B independent instances of the same DOCP that
+ *    differ by their parameters (MPC scenarios); every array then holds B consecutive instances.
+ *  - there is no CPU fallback: evaluation entry points fail with a CUDA error without a GPU.  The
+ *    structural queries (dims, bounds, x0, structures) are host-only and work anywhere.
+ */
+#ifndef CTDIRECT_B200_H
+#define CTDIRECT_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define CTD_API __attribute__((visibility("default")))
+#else
+#define CTD_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ctd_model_s* ctd_handle;
+
+/* pattern_mode */
+#define CTD_PATTERN_REFERENCE 0 /* bit-exact `:manual` patterns of the reference, quirks included */
+#define CTD_PATTERN_CORRECTED 1 /* adds the entries the reference omits        */
+
+/* output selection bits of ctd_eval / ctd_eval_dev */
+#define CTD_CONS 1
+#define CTD_JAC 2
+#define CTD_HESS 4
+#define CTD_GRAD 8
+#define CTD_OBJ 16
+
+typedef struct ctd_desc {
+    const char* problem;      /* name of a compiled-in OCP ("goddard", "double_integrator_minenergy", ...)   */
+    const char* scheme;       /* "trapeze" | "midpoint" | "gauss_legendre_{2,3}" |
+                                 "gauss_legendre_{1,2,3}_constant_control"      (src/DOCP_data.jl:307-349)  */
+    int32_t grid_size;        /* number of time steps N (Collocation option grid_size, collocation.jl:20-42) */
+    const double* time_grid;  /* optional explicit grid (n_time_grid points, increasing) or NULL             */
+    int32_t n_time_grid;
+    const double* params;     /* optional problem parameters: n_params = npar (shared) or batch*npar         */
+    int32_t n_params;
+    int32_t pattern_mode;     /* CTD_PATTERN_*                                                               */
+    int32_t batch;            /* number of independent instances (>= 1)                                      */
+    int32_t device;           /* CUDA device ordinal                                                         */
+} ctd_desc;
+
+/* DOCP(ocp, grid_size, control_steps, scheme, time_grid) + __variables_bounds! + __constraints_bounds!
+ * + the :manual pattern providers: src/DOCP_data.jl:293-365, src/collocation.jl:57-73,116-125.          */
+CTD_API int ctd_create(const ctd_desc* desc, ctd_handle* out);
+CTD_API int ctd_destroy(ctd_handle h);
+CTD_API const char* ctd_last_error(void);
+/* names of the compiled-in (problem, scheme, pattern_mode) combinations, one "problem scheme mode" per
+ * line; returns the number of bytes needed (including the terminating NUL). */
+CTD_API int64_t ctd_list_models(char* buf, int64_t buflen);
+
+/* nlp.meta.{nvar, ncon, nnzj, nnzh}  [3P NLPModels meta]; dim_NLP_variables / dim_NLP_constraints of
+ * src/DOCP_data.jl:276-277.  Per instance. */
+CTD_API int ctd_dims(ctd_handle h, int64_t* nvar, int64_t* ncon, int64_t* nnzj, int64_t* nnzh);
+/* out[0..15]: nx, nu, nv, path_cons, boundary_cons, N, step_variables_block, step constraint block,
+ * batch, free_t0, free_tf, lagrange, mayer, max (1 => minimize=false, collocation.jl:145), npar, stage  */
+CTD_API int ctd_info(ctd_handle h, int64_t out[16]);
+/* nlp.meta.{lvar, uvar, lcon, ucon}: src/DOCP_variables.jl:21-63, src/DOCP_functions.jl:163-191 */
+CTD_API int ctd_bounds(ctd_handle h, double* lvar, double* uvar, double* lcon, double* ucon);
+/* nlp.meta.x0 for the default initial guess: __initial_guess, src/DOCP_variables.jl:122-145 */
+CTD_API int ctd_x0(ctd_handle h, double* x0);
+/* normalized time grid (N+1 values in [0,1]): DOCPtime, src/DOCP_data.jl:176-214 */
+CTD_API int ctd_time_grid(ctd_handle h, double* s);
+/* jac_structure!(nlp, rows, cols) [3P] for DOCP_Jacobian_pattern (src/ode/{trapeze,midpoint,irk,
+ * irk_stagewise}.jl); nnzj entries, per instance */
+CTD_API int ctd_jac_structure(ctd_handle h, int64_t* rows, int64_t* cols);
+/* hess_structure!(nlp, rows, cols) [3P] for tril(DOCP_Hessian_pattern); nnzh entries */
+CTD_API int ctd_hess_structure(ctd_handle h, int64_t* rows, int64_t* cols);
+
+/* obj(nlp, x) [3P] -> __objective(x, docp), src/DOCP_functions.jl:23-54.  f has `batch` entries. */
+CTD_API int ctd_obj(ctd_handle h, const double* x, double* f);
+/* grad!(nlp, x, g) [3P] (ReverseDiffADGradient of __objective in the reference, collocation.jl:126-130) */
+CTD_API int ctd_grad(ctd_handle h, const double* x, double* g);
+/* cons!(nlp, x, c) [3P] -> __constraints!(c, x, docp), src/DOCP_functions.jl:80-115 */
+CTD_API int ctd_cons(ctd_handle h, const double* x, double* c);
+/* jac_coord!(nlp, x, vals) [3P] (SparseADJacobian in the reference, collocation.jl:116-120) */
+CTD_API int ctd_jac_coord(ctd_handle h, const double* x, double* vals);
+/* hess_coord!(nlp, x, y, vals; obj_weight) [3P]: Hessian of obj_weight*f(x) + y'c(x)
+ * (SparseReverseADHessian in the reference, collocation.jl:121-125) */
+CTD_API int ctd_hess_coord(ctd_handle h, const double* x, const double* y, double obj_weight, double* vals);
+/* any subset of the above in ONE kernel launch; `what` is an OR of CTD_* bits out of
+ * {CONS, JAC, HESS, OBJ, GRAD|OBJ, CONS|JAC|HESS, all five}; unused outputs may be NULL */
+CTD_API int ctd_eval(ctd_handle h, int what, const double* x, const double* y, double obj_weight, double* f, double* g,
+             double* c, double* jvals, double* hvals);
+
+/* device-pointer twins (asynchronous on the handle's stream) */
+CTD_API int ctd_eval_dev(ctd_handle h, int what, const double* x, const double* y, double obj_weight, double* f,
+                 double* g, double* c, double* jvals, double* hvals);
+/* per-instance objective and constraint violation  max_k max(lcon_k - c_k, c_k - ucon_k, 0)  (the two
+ * numbers a batched MPC driver gathers across GPUs); obj and viol have `batch` entries (device) */
+CTD_API int ctd_norms_dev(ctd_handle h, const double* x, double* obj, double* viol);
+CTD_API int ctd_norms(ctd_handle h, const double* x, double* obj, double* viol);
+/* replace the problem parameters (n = npar or batch*npar), e.g. new MPC scenarios */
+CTD_API int ctd_set_params(ctd_handle h, const double* params, int32_t n);
+CTD_API int ctd_sync(ctd_handle h);
+/* cudaStream_t of the handle (for callers that enqueue their own work around the _dev calls) */
+CTD_API void* ctd_stream(ctd_handle h);
+/* number of kernel launches issued through this handle so far */
+CTD_API int64_t ctd_launch_count(ctd_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTDIRECT_B200_H */

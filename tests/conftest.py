@@ -1,0 +1,63 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def oracle_mod():
+    """CPU oracle (test infrastructure): built on demand with g++."""
+    from oracle import oracle as orc
+    orc.build()
+    return orc
+
+
+@pytest.fixture(scope="session")
+def ctd():
+    """The product package; the CUDA library must exist (no fallback)."""
+    import ctdirect_b200
+    if not os.path.exists(ctdirect_b200.LIB_PATH):
+        from ctdirect_b200 import build
+        build.build()
+    return ctdirect_b200
+
+
+def synthetic_point(model, seed=20261018, batch=1):
+    """Synthetic evaluation point of SURVEY.md §8d: the reference initial guess perturbed by
+    1 + 1e-3*U(-1,1), multipliers ~ N(0,1).  `model` needs nvar, ncon and x0()/initial_guess()."""
+    rng = np.random.default_rng(seed)
+    x0 = model.x0() if hasattr(model, "x0") else model.initial_guess()
+    x = x0[None, :] * (1.0 + 1e-3 * rng.uniform(-1.0, 1.0, size=(batch, x0.size)))
+    y = rng.standard_normal((batch, model.ncon))
+    if batch == 1:
+        return x[0].copy(), y[0].copy()
+    return np.ascontiguousarray(x), np.ascontiguousarray(y)
+
+
+def assert_close(a, b, scale=None, rtol=1e-12, what=""):
+    """|a-b| <= rtol * max(|a|, |b|, scale): relative 1e-12 with a floor at the natural scale of the
+    quantities that were combined (entries of the :manual pattern can be structurally present but
+    numerically zero or the result of cancellation)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    if a.size == 0:
+        return
+    s = np.maximum(np.abs(a), np.abs(b))
+    if scale is not None:
+        s = np.maximum(s, scale)
+    err = np.abs(a - b)
+    bad = ~(err <= rtol * s)
+    if bad.any():
+        k = int(np.argmax(np.where(bad, err / np.maximum(s, 1e-300), 0)))
+        raise AssertionError(f"{what}: {int(bad.sum())} of {a.size} entries differ; worst at {k}: "
+                             f"{a.flat[k]!r} vs {b.flat[k]!r} (scale {s.flat[k] if np.ndim(s) else s})")
