@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""Benchmark of the DOCP evaluation path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one fused cons + Jacobian + Hessian evaluation (ctd_eval_dev, flags CONS|JAC|HESS) of the
+Goddard / midpoint / grid_size=1e5 DOCP on synthetic inputs resident in HBM.  With N > 1 ranks (torchrun)
+every rank evaluates its own instance (independent scenarios, no data-path collective): weak scaling,
+`value` = evaluations of all ranks / max-over-ranks device time.  The same JSON line carries
+  e2e           the same evaluation through the host-pointer C ABI call (ctd_eval) with pinned host buffers,
+                H2D of x,y and D2H of c, J values, H values inside the timed region;
+  roofline      algorithmic bytes / measured launch time against the measured HBM copy bandwidth;
+  cpu_baseline  the CPU oracle port (oracle/, test infrastructure) timed on the host cores;
+  batched       the 4096-instance Goddard MPC-scenario batch (grid_size=1000) sharded over the ranks with
+                one NCCL all-gather of (objective, violation) per evaluation.
+`--impl reference` times the CPU port of the reference's algorithm instead (the reference itself is Julia
+and cannot run in this image).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PROBLEM, SCHEME, GRID = "goddard", "midpoint", 100_000
+B_TOTAL, B_GRID = 4096, 1000
+SEED = 20261018
+METRIC = "cons+Jacobian+Hessian evals/s @ grid 1e5"
+
+
+def synthetic_point(x0, ncon, seed, batch=1):
+    """reference initial guess perturbed by 1 + 1e-3*U(-1,1); y ~ N(0,1)."""
+    rng = np.random.default_rng(seed)
+    x = x0[None, :] * (1.0 + 1e-3 * rng.uniform(-1.0, 1.0, size=(batch, x0.size)))
+    y = rng.standard_normal((batch, ncon))
+    return np.ascontiguousarray(x), np.ascontiguousarray(y)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons with NVML while a timed region runs."""
+    REASONS = {
+        0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+        0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
+        0x100: "display_clock_setting",
+    }
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.005)
+
+    def start(self):
+        if self.nv:
+            self._stop.clear()
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr:
+            self._stop.set()
+            self._thr.join()
+            self._thr = None
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_fused_eval_time(orc_mod, n_threads, budget_s, min_reps=2):
+    """Time one fused cons + Jacobian + Hessian evaluation of the CPU oracle at the bench workload."""
+    o = orc_mod.OracleModel(PROBLEM, SCHEME, GRID)
+    x, y = synthetic_point(o.x0(), o.ncon, SEED)
+    x, y = x[0], y[0]
+    used = orc_mod.set_threads(n_threads)
+    o.cons(x)
+    o.derivs(x, y, 1.0, want=("jac", "hess"))
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        o.cons(x)
+        o.derivs(x, y, 1.0, want=("jac", "hess"))
+        reps += 1
+        el = time.perf_counter() - t0
+        if reps >= min_reps and el >= budget_s:
+            break
+        if reps >= 200:
+            break
+    return el / reps, reps, used
+
+
+def run_reference(args, rank):
+    """--impl reference: the CPU port of the reference's algorithm on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    orc.build()
+    ncores = os.cpu_count() or 1
+    o = orc.OracleModel(PROBLEM, SCHEME, GRID)
+    x, y = synthetic_point(o.x0(), o.ncon, SEED)
+    x, y = x[0], y[0]
+    used = orc.set_threads(ncores)
+    for _ in range(max(args.warmup, 1)):
+        o.cons(x)
+        o.derivs(x, y, 1.0, want=("jac", "hess"))
+    steps = max(1, min(args.steps, 50))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.cons(x)
+        o.derivs(x, y, 1.0, want=("jac", "hess"))
+    el = time.perf_counter() - t0
+    val = steps / el
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "evals/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * el / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{PROBLEM}/{SCHEME}/grid_size={GRID} fused cons+jac+hess, :manual pattern",
+                   "note": "CPU port of the reference algorithm (oracle/): the reference is Julia + ADNLPModels and "
+                           "cannot run in this image; derivatives by element-wise second-order forward AD, OpenMP"},
+        "cpu_baseline": {"value": val, "unit": "evals/s", "cores": used, "kind": "port",
+                         "sample": f"{steps} fused evaluations of the full workload"},
+        "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-batched", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return 0
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+    import ctdirect_b200 as ctd
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU port")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    FLAGS = ctd.CONS | ctd.JAC | ctd.HESS
+    docp = ctd.DOCP(PROBLEM, GRID, SCHEME, device=local_rank)
+    nlp = docp.nlp_model()
+    nvar, ncon, nnzj, nnzh = docp.nvar, docp.ncon, docp.nnzj, docp.nnzh
+    alg_bytes = 8 * (nvar + 2 * ncon + nnzj + nnzh)
+    stream = torch.cuda.ExternalStream(docp.cuda_stream, device=dev)
+    # rotating buffer sets so that consecutive evaluations do not find their lines in the 126 MB L2
+    nsets = max(3, int(np.ceil(1.5 * 126e6 / alg_bytes)))
+    xh, yh = synthetic_point(nlp.meta.x0, ncon, SEED + rank)
+    sets = []
+    for s in range(nsets):
+        xs, ys = synthetic_point(nlp.meta.x0, ncon, SEED + 1000 * s + rank)
+        sets.append({
+            "x": torch.from_numpy(xs[0]).to(dev), "y": torch.from_numpy(ys[0]).to(dev),
+            "out": {"cons": torch.empty(ncon, dtype=torch.float64, device=dev),
+                    "jac": torch.empty(nnzj, dtype=torch.float64, device=dev),
+                    "hess": torch.empty(nnzh, dtype=torch.float64, device=dev)},
+        })
+    torch.cuda.synchronize()
+
+    calls = [docp.bind(FLAGS, s["x"], s["y"], 1.0, out=s["out"])[0] for s in sets]
+
+    def step(i):
+        calls[i % nsets]()
+
+    sampler = ClockSampler(local_rank)
+    with torch.cuda.stream(stream):
+        for i in range(args.warmup):
+            step(i)
+        barrier()
+        l0 = docp.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.start()
+        e0.record(stream)
+        for i in range(args.steps):
+            step(i)
+        e1.record(stream)
+        barrier()
+        launches = docp.launch_count - l0
+        ms_local = e0.elapsed_time(e1)
+    ms = max_over_ranks(ms_local)
+    value = world * args.steps / (ms * 1e-3)
+    peak, peak_src = measured_peak()
+    launch_s = ms_local * 1e-3 / args.steps
+    achieved = alg_bytes / launch_s / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "ctd_eval_kernel<E_goddard__midpoint, CONS|JAC|HESS>",
+                "algorithmic_bytes_per_launch": alg_bytes, "launch_us": launch_s * 1e6, "peak_source": peak_src}
+
+    # ---- e2e: host buffers through the host-pointer C ABI call (H2D + kernel + D2H every step)
+    e2e = None
+    if not args.no_e2e:
+        pin = lambda n: torch.empty(n, dtype=torch.float64).pin_memory()
+        hx, hy = pin(nvar), pin(ncon)
+        hx.numpy()[:] = xh[0]
+        hy.numpy()[:] = yh[0]
+        hout = {"cons": pin(ncon).numpy(), "jac": pin(nnzj).numpy(), "hess": pin(nnzh).numpy()}
+        nx_, ny_ = hx.numpy(), hy.numpy()
+        e2e_steps = max(3, min(args.steps, 200))
+        host_call = docp.bind(FLAGS, nx_, ny_, 1.0, out=hout)[0]
+        for _ in range(3):
+            host_call()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            host_call()   # synchronous: returns with results on the host
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        el = max_over_ranks(el * 1e3) * 1e-3
+        launches_e2e = e2e_steps
+        e2e = {"value": world * e2e_steps / el, "unit": "evals/s", "h2d_bytes_per_step": 8 * (nvar + ncon),
+               "d2h_bytes_per_step": 8 * (ncon + nnzj + nnzh), "steps": e2e_steps, "ms_per_step": 1e3 * el / e2e_steps,
+               "api": "ctd_eval (host pointers, pinned buffers), wall clock around synchronous calls"}
+    sampler.stop()
+
+    # ---- batched MPC scenarios: 4096 instances of grid 1000 sharded over the ranks
+    batched = None
+    if not args.no_batched:
+        bl = B_TOTAL // world
+        rng = np.random.default_rng(SEED + 17)
+        tmax = rng.uniform(1.0, 3.5, size=B_TOTAL)          # continuation range test_initial_guess.jl:242
+        par = np.tile(np.array([310.0, 500.0, 2.0, 3.5]), (B_TOTAL, 1))
+        par[:, 3] = tmax
+        par = par[rank * bl:(rank + 1) * bl]
+        bd = ctd.DOCP(PROBLEM, B_GRID, SCHEME, params=par, batch=bl, device=local_rank)
+        bx, by = synthetic_point(bd.initial_guess(), bd.ncon, SEED + 99 + rank, batch=bl)
+        tx, ty = torch.from_numpy(bx).to(dev), torch.from_numpy(by).to(dev)
+        bout = {"cons": torch.empty((bl, bd.ncon), dtype=torch.float64, device=dev),
+                "jac": torch.empty((bl, bd.nnzj), dtype=torch.float64, device=dev),
+                "hess": torch.empty((bl, bd.nnzh), dtype=torch.float64, device=dev),
+                "grad": torch.empty((bl, bd.nvar), dtype=torch.float64, device=dev),
+                "obj": torch.empty(bl, dtype=torch.float64, device=dev)}
+        norms = torch.empty((2, bl), dtype=torch.float64, device=dev)
+        gathered = torch.empty((world, 2, bl), dtype=torch.float64, device=dev)
+        ALL = ctd.CONS | ctd.JAC | ctd.HESS | ctd.GRAD | ctd.OBJ
+        bstream = torch.cuda.ExternalStream(bd.cuda_stream, device=dev)
+        bsteps = max(3, min(args.steps, 50))
+
+        def bstep():
+            bd.evaluate(ALL, tx, ty, 1.0, out=bout)
+            bd.violation(bout["cons"], norms[1])
+            norms[0].copy_(bout["obj"])
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, norms)
+
+        with torch.cuda.stream(bstream):
+            for _ in range(3):
+                bstep()
+            barrier()
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record(bstream)
+            for _ in range(bsteps):
+                bstep()
+            b1.record(bstream)
+            barrier()
+            bms = max_over_ranks(b0.elapsed_time(b1))
+        bbytes = 8 * bl * (2 * bd.nvar + 2 * bd.ncon + bd.nnzj + bd.nnzh)
+        bach = bbytes / (bms * 1e-3 / bsteps) / 1e9
+        batched = {"workload": f"{B_TOTAL} Goddard/midpoint instances, grid_size={B_GRID}, Tmax in [1,3.5], "
+                               f"{bl} per GPU; obj+grad+cons+jac+hess + violation norm + NCCL all-gather",
+                   "batched_evals_per_s": bsteps / (bms * 1e-3), "instance_evals_per_s": B_TOTAL * bsteps / (bms * 1e-3),
+                   "ms_per_batched_eval": bms / bsteps, "steps": bsteps, "scaling": "strong",
+                   "hbm_gbs_per_gpu": bach, "hbm_frac_per_gpu": bach / peak}
+
+    # ---- CPU baseline on the host cores (rank 0, bounded sample)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            from oracle import oracle as orc
+            orc.build()
+            ncores = os.cpu_count() or 1
+            t1, r1, _ = cpu_fused_eval_time(orc, 1, 4.0)
+            tn, rn, used = cpu_fused_eval_time(orc, ncores, 8.0)
+            cpu = {"value": 1.0 / tn, "unit": "evals/s", "cores": used, "kind": "port",
+                   "sample": f"{rn} fused cons+jac+hess evaluations of the full workload on {used} threads "
+                             f"(OpenMP over steps); single thread: {1.0 / t1:.3f} evals/s over {r1} evaluations",
+                   "single_thread_value": 1.0 / t1}
+        except Exception as ex:  # the oracle is only a reported baseline
+            cpu = {"value": None, "unit": "evals/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{PROBLEM}/{SCHEME}/grid_size={GRID}: fused cons+jac+hess (one launch), :manual "
+                                   f"pattern, nvar={nvar} ncon={ncon} nnzj={nnzj} nnzh={nnzh}; one instance per GPU",
+                       "l2": f"rotating {nsets} input/output buffer sets ({nsets * alg_bytes / 1e6:.0f} MB > 126 MB L2)",
+                       "timing": "CUDA events on the handle's stream, max over ranks"},
+            "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "batched": batched,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

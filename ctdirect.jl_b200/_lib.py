@@ -51,6 +51,7 @@ SIGNATURES = {
     "ctd_eval": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_double] + [C.c_void_p] * 5),
     "ctd_eval_dev": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_double] + [C.c_void_p] * 5),
     "ctd_norms_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ctd_violation_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "ctd_norms": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ctd_set_params": (C.c_int, [_H, _dp, C.c_int32]),
     "ctd_sync": (C.c_int, [_H]),

@@ -172,6 +172,11 @@ int ctd_norms_dev(ctd_handle h, const double* x, double* obj, double* viol) {
     return guarded([&] { h->m->norms_dev(x, obj, viol); });
 }
 
+int ctd_violation_dev(ctd_handle h, const double* c, double* viol) {
+    if (int e = check(h)) return e;
+    return guarded([&] { h->m->violation_dev(c, viol); });
+}
+
 int ctd_norms(ctd_handle h, const double* x, double* obj, double* viol) {
     if (int e = check(h)) return e;
     return guarded([&] { h->m->norms_host(x, obj, viol); });

@@ -7,6 +7,20 @@
 
 #define CTD_INF (__builtin_huge_val())
 
+// Non-contracting arithmetic for the scheme formulas (time grid, midpoint / stage points, defects):
+// the reference's Julia code rounds every product and sum separately, whereas nvcc would fuse a*b+c
+// into one FMA.  Feeding the nonlinear OCP functions bit-identical arguments keeps ill-conditioned
+// derivative entries (e.g. Goddard's exp(-500 (r-1)) terms that cancel between stages) within 1e-12.
+#ifdef __CUDA_ARCH__
+#define CTD_MUL(a, b) __dmul_rn((a), (b))
+#define CTD_ADD(a, b) __dadd_rn((a), (b))
+#define CTD_SUB(a, b) __dsub_rn((a), (b))
+#else
+#define CTD_MUL(a, b) ((a) * (b))
+#define CTD_ADD(a, b) ((a) + (b))
+#define CTD_SUB(a, b) ((a) - (b))
+#endif
+
 namespace ctd {
 
 // Times of one step, computed like the reference (t = t0 + s*(tf - t0), DOCP_data.jl:456;

@@ -8,16 +8,20 @@
 // Work decomposition:
 //   * one thread evaluates one time step (all rows of the step and their analytic derivatives,
 //     straight-line generated code);
-//   * a CTA of T threads owns the T-1 consecutive *column blocks* i0..i0+T-2 of the value arrays
-//     (the columns of the variables (x_i,u_i[,k_i]) of those steps).  Thread 0 re-evaluates the halo
-//     step i0-1, whose derivatives w.r.t. x_{i0} land in block i0;
-//   * every value is written into shared memory at its final CSC position relative to the tile, so
-//     the tile leaves the SM as a handful of contiguous ranges written with 16-byte coalesced stores;
-//   * the irregular ends (column blocks 1, N, N+1, boundary / final-path rows) are handled by one
-//     extra CTA through host-built position tables;
-//   * (v,v) Hessian entries, d/dv of the cost and the Lagrange sum are block-reduced with warp
-//     shuffles into per-CTA partials and summed in a fixed order by the last CTA to finish
-//     (deterministic, no floating-point atomics on global memory).
+//   * a WARP is an autonomous tile: lanes 1..31 own 31 consecutive *column blocks* i0..i0+30 of the
+//     value arrays (the columns of the variables (x_i,u_i[,k_i]) of those steps) and lane 0
+//     re-evaluates the halo step i0-1, whose derivatives w.r.t. x_{i0} land in block i0.  Warps only
+//     synchronise with __syncwarp, so the load / compute / store phases of the warps resident on an SM
+//     overlap each other;
+//   * every value is written into the warp's shared-memory region at its final CSC position relative
+//     to the tile, so the tile leaves the SM as a handful of contiguous ranges written with 16-byte
+//     coalesced stores.  The region is used twice (phase A: constraints, Jacobian, gradient;
+//     phase B: Hessian), which halves the shared memory per resident warp;
+//   * the irregular ends (column blocks 1, N, N+1, boundary / final-path rows) are handled by CTA 0
+//     through host-built position tables;
+//   * (v,v) Hessian entries, d/dv of the cost and the Lagrange sum are reduced with warp shuffles into
+//     per-CTA partials and summed in a fixed order by the last CTA to finish (deterministic, no
+//     floating-point atomics on global memory).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -51,11 +55,12 @@ struct EvalArgs {
     double sigma;
     const double* sgrid;   // normalized time grid (N+1), or nullptr for the uniform grid j/N
     int N;
-    int tiles;             // tile CTAs per instance; CTA index `tiles` is the edge CTA
+    int tiles;             // warp tiles per instance
+    int ctas;              // CTAs per instance: CTA 0 is the edge CTA, CTAs 1.. hold WPC warp tiles each
     long long nvar, ncon;
     long long jv_base[MAX_NV];    // position of the first value of column v_k in jvals
     long long hvv_pos[MAX_NVV];   // positions of the (v_a, v_b) entries in hvals (packed lower triangle)
-    double* partials;             // [batch][tiles+1][NRED]
+    double* partials;             // [batch][ctas][NRED]
     unsigned int* counters;       // [batch]
     // edge tables (identical for every instance)
     const int* edge_map;
@@ -76,24 +81,33 @@ struct Cfg {
     static constexpr int R_H = 0, R_G = R_H + (WH ? NVV : 0), R_O = R_G + (WG ? NV : 0);
     static constexpr int NRED = R_O + (WO ? 1 : 0);
     static constexpr int NJV = NV * E::JV_STRIDE;
-    // doubles staged in shared memory per owned step
-    static constexpr int PER_STEP = (WC ? E::CB : 0) + (WJ ? E::J_BLOCK + NJV : 0) + (WH ? E::H_BLOCK : 0) +
-                                    (WG ? E::BLK : 0);
-    static constexpr int SMEM_BUDGET = 72 * 1024;
-    static constexpr int T = (PER_STEP * 8 * 127 + 256 <= SMEM_BUDGET) ? 128
-                             : (PER_STEP * 8 * 63 + 256 <= SMEM_BUDGET) ? 64 : 32;
-    static constexpr int OWN = T - 1;  // owned steps per tile
-    // shared-memory sub-buffers (each with 2 doubles of slack so that the staged range can be given
-    // the same 16-byte phase as its destination in global memory)
+    // phase A stages constraints, Jacobian and gradient; phase B the Hessian (same shared memory)
+    static constexpr bool PHASE_A = WC || WJ || WG || WO, PHASE_B = WH;
+    static constexpr int PER_STEP_A = (WC ? E::CB : 0) + (WJ ? E::J_BLOCK + NJV : 0) + (WG ? E::BLK : 0);
+    static constexpr int PER_STEP_B = WH ? E::H_BLOCK : 0;
+    static constexpr int PER_STEP = PER_STEP_A > PER_STEP_B ? PER_STEP_A : PER_STEP_B;
+    // warps per CTA: 4 when a CTA's staged tiles stay small (many CTAs per SM), fewer for wide
+    // elements (e.g. 3-stage IRK of a 6-state problem)
+    static constexpr int SMEM_MAX = 200 * 1024;
+    static constexpr int WPC = (PER_STEP * 8 * 31 * 4 <= 96 * 1024) ? 4 : (PER_STEP * 8 * 31 * 2 <= 128 * 1024) ? 2 : 1;
+    static constexpr int T = WPC * 32;
+    static constexpr int FIT = PER_STEP > 0 ? (SMEM_MAX / WPC - 512) / (PER_STEP * 8) : 31;
+    static constexpr int OWN = (31 < FIT) ? 31 : FIT;  // owned steps per warp tile
+    static_assert(OWN >= 1, "element too wide for one SM's shared memory");
+    // sub-buffers of a warp's region (each with 2 doubles of slack so that the staged range can be
+    // given the same 16-byte phase as its destination in global memory)
     static constexpr int even(int n) { return (n + 3) & ~1; }
     static constexpr int S_C = 0;
     static constexpr int S_J = S_C + (WC ? even(OWN * E::CB) : 0);
     static constexpr int S_JV = S_J + (WJ ? even(OWN * E::J_BLOCK) : 0);
     static constexpr int JV_ONE = even(OWN * E::JV_STRIDE);
-    static constexpr int S_H = S_JV + (WJ ? NV * JV_ONE : 0);
-    static constexpr int S_G = S_H + (WH ? even(OWN * E::H_BLOCK) : 0);
-    static constexpr int S_RED = S_G + (WG ? even(OWN * E::BLK) : 0);
-    static constexpr int S_END = S_RED + 32 * (NRED > 0 ? NRED : 1) + 2;
+    static constexpr int S_G = S_JV + (WJ ? NV * JV_ONE : 0);
+    static constexpr int A_END = S_G + (WG ? even(OWN * E::BLK) : 0);
+    static constexpr int S_H = 0;
+    static constexpr int B_END = WH ? even(OWN * E::H_BLOCK) : 0;
+    static constexpr int WARP_DOUBLES = ((A_END > B_END ? A_END : B_END) + 1) & ~1;
+    static constexpr int S_RED = WPC * WARP_DOUBLES;
+    static constexpr int S_END = S_RED + WPC * (NRED > 0 ? NRED : 1) + 2;
     static constexpr size_t TILE_SMEM = (size_t)S_END * sizeof(double);
     // edge map layout of one step task
     static constexpr int M_JO = 0, M_JN = M_JO + E::NJ_OWN, M_JV = M_JN + E::NJ_NEXT, M_HO = M_JV + E::NJ_V,
@@ -117,9 +131,9 @@ __device__ __forceinline__ void time_args(const EvalArgs& a, const double* v, co
     const double tf = E::TF_KIND == 0 ? E::TF_CONST : (E::TF_KIND == 1 ? v[E::TF_IDX > 0 ? E::TF_IDX : 0] : p[E::TF_IDX > 0 ? E::TF_IDX : 0]);
     const double si = grid_point(a, i - 1);
     const double sp = (i <= a.N) ? grid_point(a, i) : si;
-    T.ti = t0 + si * (tf - t0);
-    T.tp = t0 + sp * (tf - t0);
-    T.hh = T.tp - T.ti;
+    T.ti = CTD_ADD(t0, CTD_MUL(si, CTD_SUB(tf, t0)));
+    T.tp = CTD_ADD(t0, CTD_MUL(sp, CTD_SUB(tf, t0)));
+    T.hh = CTD_SUB(T.tp, T.ti);
 #pragma unroll
     for (int k = 0; k < E::NV; ++k) {
         double di = 0.0, dp = 0.0;
@@ -150,8 +164,9 @@ __device__ __forceinline__ int phase_of(const double* g) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Sink of a tile thread: derivative values go to their CSC slot inside the staged tile.
-template <class E, int F>
+// Sink of a tile thread for one phase (PC/PJ/PH/PG select what this phase keeps): derivative values go
+// to their CSC slot inside the warp's staged tile.
+template <class E, int F, bool PC, bool PJ, bool PH, bool PG>
 struct TileSink {
     using C = Cfg<E, F>;
     double* c_;       // own constraint rows
@@ -163,20 +178,20 @@ struct TileSink {
     bool owner, giver;
     double hn_[E::NH_NEXT > 0 ? E::NH_NEXT : 1];
     double gn_[E::NG_NEXT > 0 ? E::NG_NEXT : 1];
-    double red[C::NRED > 0 ? C::NRED : 1];
+    double* red;
 
-    template <int R> __device__ __forceinline__ void c(double v) { if (owner) c_[R] = v; }
-    template <int N> __device__ __forceinline__ void jo(double v) { if (owner) jo_[E::J_OWN(N, 2)] = v; }
-    template <int N> __device__ __forceinline__ void jn(double v) { if (giver) jn_[E::J_NEXT(N, 2)] = v; }
+    template <int R> __device__ __forceinline__ void c(double v) { if (PC && owner) c_[R] = v; }
+    template <int N> __device__ __forceinline__ void jo(double v) { if (PJ && owner) jo_[E::J_OWN(N, 2)] = v; }
+    template <int N> __device__ __forceinline__ void jn(double v) { if (PJ && giver) jn_[E::J_NEXT(N, 2)] = v; }
     template <int N> __device__ __forceinline__ void jv(double v) {
-        if (owner) jv_[E::J_V(N, 1)][E::J_V(N, 2)] = v;
+        if (PJ && owner) jv_[E::J_V(N, 1)][E::J_V(N, 2)] = v;
     }
-    template <int N> __device__ __forceinline__ void ho(double v) { if (owner) ho_[E::H_OWN(N, 2)] = v; }
-    template <int N> __device__ __forceinline__ void hn(double v) { hn_[N] = v; }
-    template <int K> __device__ __forceinline__ void hv(double v) { if (owner) red[C::R_H + K] += v; }
-    template <int N> __device__ __forceinline__ void go(double v) { if (owner) go_[E::G_OWN(N, 2)] = v; }
-    template <int N> __device__ __forceinline__ void gn(double v) { gn_[N] = v; }
-    template <int N> __device__ __forceinline__ void gv(double v) { if (owner) red[C::R_G + E::G_V(N, 2)] += v; }
+    template <int N> __device__ __forceinline__ void ho(double v) { if (PH && owner) ho_[E::H_OWN(N, 2)] = v; }
+    template <int N> __device__ __forceinline__ void hn(double v) { if (PH) hn_[N] = v; }
+    template <int K> __device__ __forceinline__ void hv(double v) { if (PH && owner) red[C::R_H + K] += v; }
+    template <int N> __device__ __forceinline__ void go(double v) { if (PG && owner) go_[E::G_OWN(N, 2)] = v; }
+    template <int N> __device__ __forceinline__ void gn(double v) { if (PG) gn_[N] = v; }
+    template <int N> __device__ __forceinline__ void gv(double v) { if (PG && owner) red[C::R_G + E::G_V(N, 2)] += v; }
 };
 
 // Sink of an edge task: values are accumulated into the edge buffer through the host-built map.
@@ -240,6 +255,10 @@ __device__ __forceinline__ void load_step(const double* __restrict__ x, long lon
     for (int k = 0; k < E::NV; ++k) z[E::NOWN + E::NNEXT + k] = x[nvar - E::NV + k];
 }
 
+// Edge CTA: the elements that touch column blocks 1, N, N+1 and the boundary / final-path rows.  Every
+// job (a step element, the final-path element, the boundary+Mayer element) is run by lane 0 of a warp;
+// jobs of different kinds accumulate into different layers of the edge buffer, which are summed in a
+// fixed order when the buffer is scattered (deterministic whatever the warp interleaving).
 template <class E, int F>
 __device__ void edge_cta(const EvalArgs& a, const double* __restrict__ x, const double* __restrict__ y,
                          const double* __restrict__ p, double* c, double* jvals, double* hvals, double* grad,
@@ -247,88 +266,164 @@ __device__ void edge_cta(const EvalArgs& a, const double* __restrict__ x, const 
     using C = Cfg<E, F>;
     const int tid = threadIdx.x;
     constexpr int T = C::T;
-    constexpr int NW = T / 32;
+    constexpr int NW = C::WPC;
     const int ne = a.ne_j + a.ne_h + a.ne_g;
-    for (int k = tid; k < ne; k += T) buf[k] = 0.0;
+    for (int k = tid; k < 3 * ne; k += T) buf[k] = 0.0;
     __syncthreads();
-    // ---- phase 1: the step elements that touch column blocks 1, N and N+1 (one warp each if possible)
-    {
-        const int task = (tid % 32 == 0) ? tid / 32 : -1;
-        for (int k = task; k >= 0 && k < a.ntask; k += NW) {
-            const EdgeTask tk = a.task[k];
-            double z[E::NZ], lam[E::CB];
-            load_step<E>(x, a.nvar, tk.step, z);
+    if ((tid & 31) == 0) {
+        const int njobs = a.ntask + 2;
+        for (int job = tid >> 5; job < njobs; job += NW) {
+            if (job < a.ntask) {
+                // step elements: stepStateConstraints! / stepPathConstraints! of steps 1, N-1, N
+                const EdgeTask tk = a.task[job];
+                double z[E::NZ], lam[E::CB];
+                load_step<E>(x, a.nvar, tk.step, z);
 #pragma unroll
-            for (int r = 0; r < E::CB; ++r) lam[r] = (C::WH && y) ? y[(long long)(tk.step - 1) * E::CB + r] : 0.0;
-            TimeArgs<E::NV> Tm;
-            time_args<E>(a, z + E::NOWN + E::NNEXT, p, tk.step, Tm);
-            EdgeSink<E, F> s;
-            s.buf = buf;
-            s.map = a.edge_map + tk.map_off;
-            s.crow = (C::WC && tk.own) ? c + (long long)(tk.step - 1) * E::CB : nullptr;
-            s.red = red;
-            if constexpr (C::WC || C::WJ || C::WH) E::template step<C::WC, C::WJ, C::WH>(z, Tm, p, lam, a.sigma, s);
-            if constexpr (C::WG) E::grad_step(z, Tm, p, s);
-            if constexpr (C::WO) { if (tk.own) red[C::R_O] += E::cost_step(z, Tm, p); }
-        }
-    }
-    __syncthreads();
-    // ---- phase 2: final path constraints g(t_f, x_f, u_f, v)  (DOCP_functions.jl:100)
-    if constexpr (E::NP > 0 && (C::WC || C::WJ || C::WH)) {
-        if (tid == 0) {
-            double z[E::FP_NLOC], lam[E::NP];
-            const long long N = a.N;
-            if (E::FINAL_CONTROL) {
+                for (int r = 0; r < E::CB; ++r) lam[r] = (C::WH && y) ? y[(long long)(tk.step - 1) * E::CB + r] : 0.0;
+                TimeArgs<E::NV> Tm;
+                time_args<E>(a, z + E::NOWN + E::NNEXT, p, tk.step, Tm);
+                EdgeSink<E, F> s;
+                s.buf = buf;
+                s.map = a.edge_map + tk.map_off;
+                s.crow = (C::WC && tk.own) ? c + (long long)(tk.step - 1) * E::CB : nullptr;
+                s.red = red;
+                if constexpr (C::WC || C::WJ || C::WH) E::template step<C::WC, C::WJ, C::WH>(z, Tm, p, lam, a.sigma, s);
+                if constexpr (C::WG) E::grad_step(z, Tm, p, s);
+                if constexpr (C::WO) { if (tk.own) red[C::R_O] += E::cost_step(z, Tm, p); }
+            } else if (job == a.ntask) {
+                // final path constraints g(t_f, x_f, u_f, v)  (DOCP_functions.jl:100)
+                if constexpr (E::NP > 0 && (C::WC || C::WJ || C::WH)) {
+                    double z[E::FP_NLOC], lam[E::NP];
+                    const long long N = a.N;
+                    if (E::FINAL_CONTROL) {
 #pragma unroll
-                for (int k = 0; k < E::NX + E::NU; ++k) z[k] = x[N * E::BLK + k];
+                        for (int k = 0; k < E::NX + E::NU; ++k) z[k] = x[N * E::BLK + k];
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < E::CTRL_BLK; ++k) z[k] = x[(N - 1) * E::BLK + E::NX + k];
+#pragma unroll
+                        for (int k = 0; k < E::NX; ++k) z[E::CTRL_BLK + k] = x[N * E::BLK + k];
+                    }
+#pragma unroll
+                    for (int k = 0; k < E::NV; ++k) z[E::FP_NLOC - E::NV + k] = x[a.nvar - E::NV + k];
+#pragma unroll
+                    for (int r = 0; r < E::NP; ++r) lam[r] = (C::WH && y) ? y[N * E::CB + r] : 0.0;
+                    TimeArgs<E::NV> Tm;
+                    time_args<E>(a, z + E::FP_NLOC - E::NV, p, N + 1, Tm);
+                    EdgeElemSink<E, F, C::M_FP_J, C::M_FP_H, 0> s;
+                    s.buf = buf + ne;
+                    s.map = a.edge_map + a.fp_map_off;
+                    s.crow = C::WC ? c + N * E::CB : nullptr;
+                    s.red = red;
+                    E::template fpath<C::WC, C::WJ, C::WH>(z, Tm, p, lam, s);
+                }
             } else {
+                // boundary constraints + Mayer cost  (DOCP_functions.jl:103-111, 35-39)
+                double z[E::BC_NLOC], lam[E::NB > 0 ? E::NB : 1];
+                const long long N = a.N;
 #pragma unroll
-                for (int k = 0; k < E::CTRL_BLK; ++k) z[k] = x[(N - 1) * E::BLK + E::NX + k];
+                for (int k = 0; k < E::NX; ++k) { z[k] = x[k]; z[E::NX + k] = x[N * E::BLK + k]; }
 #pragma unroll
-                for (int k = 0; k < E::NX; ++k) z[E::CTRL_BLK + k] = x[N * E::BLK + k];
+                for (int k = 0; k < E::NV; ++k) z[2 * E::NX + k] = x[a.nvar - E::NV + k];
+#pragma unroll
+                for (int r = 0; r < E::NB; ++r) lam[r] = (C::WH && y) ? y[a.ncon - E::NB + r] : 0.0;
+                EdgeElemSink<E, F, C::M_BC_J, C::M_BC_H, C::M_BC_G> s;
+                s.buf = buf + 2 * ne;
+                s.map = a.edge_map + a.bc_map_off;
+                s.crow = (C::WC && E::NB > 0) ? c + (a.ncon - E::NB) : nullptr;
+                s.red = red;
+                if constexpr (C::WC || C::WJ || C::WH) E::template bc<C::WC, C::WJ, C::WH>(z, p, lam, a.sigma, s);
+                if constexpr (C::WG) E::grad_bc(z, p, s);
+                if constexpr (C::WO) red[C::R_O] += E::mayer(z, p);
             }
-#pragma unroll
-            for (int k = 0; k < E::NV; ++k) z[E::FP_NLOC - E::NV + k] = x[a.nvar - E::NV + k];
-#pragma unroll
-            for (int r = 0; r < E::NP; ++r) lam[r] = (C::WH && y) ? y[N * E::CB + r] : 0.0;
-            TimeArgs<E::NV> Tm;
-            time_args<E>(a, z + E::FP_NLOC - E::NV, p, N + 1, Tm);
-            EdgeElemSink<E, F, C::M_FP_J, C::M_FP_H, 0> s;
-            s.buf = buf;
-            s.map = a.edge_map + a.fp_map_off;
-            s.crow = C::WC ? c + N * E::CB : nullptr;
-            s.red = red;
-            E::template fpath<C::WC, C::WJ, C::WH>(z, Tm, p, lam, s);
         }
-        __syncthreads();
-    }
-    // ---- phase 3: boundary constraints + Mayer cost  (DOCP_functions.jl:103-111, 35-39)
-    if (tid == 0) {
-        double z[E::BC_NLOC], lam[E::NB > 0 ? E::NB : 1];
-        const long long N = a.N;
-#pragma unroll
-        for (int k = 0; k < E::NX; ++k) { z[k] = x[k]; z[E::NX + k] = x[N * E::BLK + k]; }
-#pragma unroll
-        for (int k = 0; k < E::NV; ++k) z[2 * E::NX + k] = x[a.nvar - E::NV + k];
-#pragma unroll
-        for (int r = 0; r < E::NB; ++r) lam[r] = (C::WH && y) ? y[a.ncon - E::NB + r] : 0.0;
-        EdgeElemSink<E, F, C::M_BC_J, C::M_BC_H, C::M_BC_G> s;
-        s.buf = buf;
-        s.map = a.edge_map + a.bc_map_off;
-        s.crow = (C::WC && E::NB > 0) ? c + (a.ncon - E::NB) : nullptr;
-        s.red = red;
-        if constexpr (C::WC || C::WJ || C::WH) E::template bc<C::WC, C::WJ, C::WH>(z, p, lam, a.sigma, s);
-        if constexpr (C::WG) E::grad_bc(z, p, s);
-        if constexpr (C::WO) red[C::R_O] += E::mayer(z, p);
     }
     __syncthreads();
-    // ---- scatter the edge buffer
+    // ---- scatter the edge buffer (layers summed in a fixed order)
     if constexpr (C::WJ)
-        for (int k = tid; k < a.ne_j; k += T) jvals[a.edge_pos[k]] = buf[k];
+        for (int k = tid; k < a.ne_j; k += T) jvals[a.edge_pos[k]] = (buf[k] + buf[ne + k]) + buf[2 * ne + k];
     if constexpr (C::WH)
-        for (int k = tid; k < a.ne_h; k += T) hvals[a.edge_pos[a.ne_j + k]] = buf[a.ne_j + k];
+        for (int k = a.ne_j + tid; k < a.ne_j + a.ne_h; k += T) hvals[a.edge_pos[k]] = (buf[k] + buf[ne + k]) + buf[2 * ne + k];
     if constexpr (C::WG)
-        for (int k = tid; k < a.ne_g; k += T) grad[a.edge_pos[a.ne_j + a.ne_h + k]] = buf[a.ne_j + a.ne_h + k];
+        for (int k = a.ne_j + a.ne_h + tid; k < ne; k += T) grad[a.edge_pos[k]] = (buf[k] + buf[ne + k]) + buf[2 * ne + k];
+}
+
+// One phase of a warp tile: evaluate, stage, add the halo contributions, copy out.
+template <class E, int F, bool PC, bool PJ, bool PH, bool PG, bool PO>
+__device__ __forceinline__ void tile_phase(const EvalArgs& a, double* __restrict__ ws, const double* __restrict__ z,
+                                           const double* __restrict__ lam, const TimeArgs<E::NV>& Tm,
+                                           const double* __restrict__ p, double* red, int lane, int nown, long long i0,
+                                           bool active, double* c, double* jvals, double* hvals, double* grad) {
+    using C = Cfg<E, F>;
+    // global destinations of this tile and the matching shared-memory phases
+    double* gC = PC ? c + (i0 - 1) * E::CB : nullptr;
+    double* gJ = PJ ? jvals + E::J_FIRST + (i0 - 2) * E::J_BLOCK : nullptr;
+    double* gH = PH ? hvals + E::H_FIRST + (i0 - 2) * E::H_BLOCK : nullptr;
+    double* gG = PG ? grad + (i0 - 1) * E::BLK : nullptr;
+    double* sC = ws + C::S_C + (PC ? phase_of(gC) : 0);
+    double* sJ = ws + C::S_J + (PJ ? phase_of(gJ) : 0);
+    double* sH = ws + C::S_H + (PH ? phase_of(gH) : 0);
+    double* sG = ws + C::S_G + (PG ? phase_of(gG) : 0);
+    double* gJV[C::NV > 0 ? C::NV : 1];
+    double* sJV[C::NV > 0 ? C::NV : 1];
+    if constexpr (PJ && C::NV > 0) {
+#pragma unroll
+        for (int k = 0; k < C::NV; ++k) {
+            gJV[k] = jvals + a.jv_base[k] + (i0 - 1) * E::JV_STRIDE;
+            sJV[k] = ws + C::S_JV + k * C::JV_ONE + phase_of(gJV[k]);
+        }
+    }
+    TileSink<E, F, PC, PJ, PH, PG> s;
+    s.red = red;
+    s.owner = active && lane >= 1;
+    s.giver = active && lane < nown;
+    s.c_ = sC + (lane - 1) * E::CB;
+    s.jo_ = sJ + (lane - 1) * E::J_BLOCK;
+    s.jn_ = sJ + lane * E::J_BLOCK;
+    s.ho_ = sH + (lane - 1) * E::H_BLOCK;
+    s.go_ = sG + (lane - 1) * E::BLK;
+    if constexpr (PJ && C::NV > 0) {
+#pragma unroll
+        for (int k = 0; k < C::NV; ++k) s.jv_[k] = sJV[k] + (lane - 1) * E::JV_STRIDE;
+    }
+    if (active) {
+        if constexpr (PG) {
+            if (s.owner) {
+#pragma unroll
+                for (int k = 0; k < E::BLK; ++k) s.go_[k] = 0.0;
+            }
+        }
+        if constexpr (PC || PJ || PH) E::template step<PC, PJ, PH>(z, Tm, p, lam, a.sigma, s);
+        if constexpr (PG) E::grad_step(z, Tm, p, s);
+        if constexpr (PO) { if (s.owner) red[C::R_O] += E::cost_step(z, Tm, p); }
+    }
+    __syncwarp();
+    if constexpr ((PH && E::NH_NEXT > 0) || (PG && E::NG_NEXT > 0)) {
+        if (s.giver) {
+            if constexpr (PH) {
+#pragma unroll
+                for (int n = 0; n < E::NH_NEXT; ++n) sH[lane * E::H_BLOCK + E::H_NEXT(n, 2)] += s.hn_[n];
+            }
+            if constexpr (PG) {
+#pragma unroll
+                for (int n = 0; n < E::NG_NEXT; ++n) sG[lane * E::BLK + E::G_NEXT(n, 2)] += s.gn_[n];
+            }
+        }
+        __syncwarp();
+    }
+    if (nown > 0) {
+        if constexpr (PC) store_range(gC, sC, nown * E::CB, lane, 32);
+        if constexpr (PJ) {
+            store_range(gJ, sJ, nown * E::J_BLOCK, lane, 32);
+            if constexpr (C::NV > 0) {
+#pragma unroll
+                for (int k = 0; k < C::NV; ++k) store_range(gJV[k], sJV[k], nown * E::JV_STRIDE, lane, 32);
+            }
+        }
+        if constexpr (PH) store_range(gH, sH, nown * E::H_BLOCK, lane, 32);
+        if constexpr (PG) store_range(gG, sG, nown * E::BLK, lane, 32);
+    }
+    __syncwarp();
 }
 
 template <class E, int F>
@@ -337,7 +432,8 @@ __global__ void __launch_bounds__(Cfg<E, F>::T) ctd_eval_kernel(const EvalArgs a
     constexpr int T = C::T;
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x;
-    const int tile = blockIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int cta = blockIdx.x;
     const long long inst = blockIdx.y;
 
     const double* __restrict__ x = a.x + inst * a.x_stride;
@@ -352,115 +448,52 @@ __global__ void __launch_bounds__(Cfg<E, F>::T) ctd_eval_kernel(const EvalArgs a
 #pragma unroll
     for (int k = 0; k < (C::NRED > 0 ? C::NRED : 1); ++k) red[k] = 0.0;
 
-    if (tile == a.tiles) {
+    if (cta == 0) {
         edge_cta<E, F>(a, x, y, p, c, jvals, hvals, grad, smem, red);
     } else {
-        const long long i0 = 2 + (long long)tile * C::OWN;            // first owned step / column block
+        const long long tile = (long long)(cta - 1) * C::WPC + warp;
+        const long long i0 = 2 + tile * C::OWN;                       // first owned step / column block
         const long long last = (long long)a.N - 1;                    // last regular column block
-        const int nown = (int)((last - i0 + 1) < C::OWN ? (last - i0 + 1) : C::OWN);
-        const long long i = i0 - 1 + tid;                             // this thread's step
-        const bool active = tid <= nown;
-
-        // global destinations of this tile and the matching shared-memory phases
-        double* gC = C::WC ? c + (i0 - 1) * E::CB : nullptr;
-        double* gJ = C::WJ ? jvals + E::J_FIRST + (i0 - 2) * E::J_BLOCK : nullptr;
-        double* gH = C::WH ? hvals + E::H_FIRST + (i0 - 2) * E::H_BLOCK : nullptr;
-        double* gG = C::WG ? grad + (i0 - 1) * E::BLK : nullptr;
-        double* sC = smem + C::S_C + (C::WC ? phase_of(gC) : 0);
-        double* sJ = smem + C::S_J + (C::WJ ? phase_of(gJ) : 0);
-        double* sH = smem + C::S_H + (C::WH ? phase_of(gH) : 0);
-        double* sG = smem + C::S_G + (C::WG ? phase_of(gG) : 0);
-        double* gJV[C::NV > 0 ? C::NV : 1];
-        double* sJV[C::NV > 0 ? C::NV : 1];
-        if constexpr (C::WJ && C::NV > 0) {
-#pragma unroll
-            for (int k = 0; k < C::NV; ++k) {
-                gJV[k] = jvals + a.jv_base[k] + (i0 - 1) * E::JV_STRIDE;
-                sJV[k] = smem + C::S_JV + k * C::JV_ONE + phase_of(gJV[k]);
-            }
-        }
-
-        TileSink<E, F> s;
-#pragma unroll
-        for (int k = 0; k < (C::NRED > 0 ? C::NRED : 1); ++k) s.red[k] = 0.0;
-        s.owner = active && tid >= 1;
-        s.giver = active && tid < nown;
-        s.c_ = sC + (tid - 1) * E::CB;
-        s.jo_ = sJ + (tid - 1) * E::J_BLOCK;
-        s.jn_ = sJ + tid * E::J_BLOCK;
-        s.ho_ = sH + (tid - 1) * E::H_BLOCK;
-        s.go_ = sG + (tid - 1) * E::BLK;
-        if constexpr (C::WJ && C::NV > 0) {
-#pragma unroll
-            for (int k = 0; k < C::NV; ++k) s.jv_[k] = sJV[k] + (tid - 1) * E::JV_STRIDE;
-        }
-
+        const long long left = last - i0 + 1;
+        const int nown = (int)(left < C::OWN ? (left < 0 ? 0 : left) : C::OWN);
+        const long long i = i0 - 1 + lane;                            // this thread's step
+        const bool active = nown > 0 && lane <= nown;
+        double* ws = smem + warp * C::WARP_DOUBLES;
+        double z[E::NZ], lam[E::CB];
+        TimeArgs<E::NV> Tm;
         if (active) {
-            double z[E::NZ], lam[E::CB];
             load_step<E>(x, a.nvar, i, z);
 #pragma unroll
             for (int r = 0; r < E::CB; ++r) lam[r] = (C::WH && y) ? y[(i - 1) * E::CB + r] : 0.0;
-            TimeArgs<E::NV> Tm;
             time_args<E>(a, z + E::NOWN + E::NNEXT, p, i, Tm);
-            if constexpr (C::WG) {
-                if (s.owner) {
-#pragma unroll
-                    for (int k = 0; k < E::BLK; ++k) s.go_[k] = 0.0;
-                }
-            }
-            if constexpr (C::WC || C::WJ || C::WH) E::template step<C::WC, C::WJ, C::WH>(z, Tm, p, lam, a.sigma, s);
-            if constexpr (C::WG) E::grad_step(z, Tm, p, s);
-            if constexpr (C::WO) { if (s.owner) s.red[C::R_O] += E::cost_step(z, Tm, p); }
         }
-        if constexpr ((C::WH && E::NH_NEXT > 0) || (C::WG && E::NG_NEXT > 0)) {
-            __syncthreads();
-            if (s.giver) {
-                if constexpr (C::WH) {
-#pragma unroll
-                    for (int n = 0; n < E::NH_NEXT; ++n) sH[tid * E::H_BLOCK + E::H_NEXT(n, 2)] += s.hn_[n];
-                }
-                if constexpr (C::WG) {
-#pragma unroll
-                    for (int n = 0; n < E::NG_NEXT; ++n) sG[tid * E::BLK + E::G_NEXT(n, 2)] += s.gn_[n];
-                }
-            }
-        }
-        __syncthreads();
-        if (nown > 0) {
-            if constexpr (C::WC) store_range(gC, sC, nown * E::CB, tid, T);
-            if constexpr (C::WJ) {
-                store_range(gJ, sJ, nown * E::J_BLOCK, tid, T);
-                if constexpr (C::NV > 0) {
-#pragma unroll
-                    for (int k = 0; k < C::NV; ++k) store_range(gJV[k], sJV[k], nown * E::JV_STRIDE, tid, T);
-                }
-            }
-            if constexpr (C::WH) store_range(gH, sH, nown * E::H_BLOCK, tid, T);
-            if constexpr (C::WG) store_range(gG, sG, nown * E::BLK, tid, T);
-        }
-#pragma unroll
-        for (int k = 0; k < (C::NRED > 0 ? C::NRED : 1); ++k) red[k] = s.red[k];
+        if constexpr (C::PHASE_A)
+            tile_phase<E, F, C::WC, C::WJ, false, C::WG, C::WO>(a, ws, z, lam, Tm, p, red, lane, nown, i0, active, c,
+                                                                  jvals, hvals, grad);
+        if constexpr (C::PHASE_B)
+            tile_phase<E, F, false, false, true, false, false>(a, ws, z, lam, Tm, p, red, lane, nown, i0, active, c,
+                                                                jvals, hvals, grad);
     }
 
     // ---- deterministic reduction of the global sums: (v,v) Hessian entries, d cost / d v, cost
     if constexpr (C::NRED > 0) {
         double* sred = smem + C::S_RED;
         __shared__ int is_last;
-        const int nblk = a.tiles + 1;
-        __syncthreads();
+        const int nblk = a.ctas;
+        __syncthreads();   // (the edge CTA's value buffer may overlap sred)
 #pragma unroll
         for (int k = 0; k < C::NRED; ++k) {
             double v = red[k];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if ((tid & 31) == 0) sred[(tid >> 5) * C::NRED + k] = v;
+            if (lane == 0) sred[warp * C::NRED + k] = v;
         }
         __syncthreads();
         double* part = a.partials + (inst * nblk) * C::NRED;
         if (tid < C::NRED) {
             double v = 0.0;
-            for (int w = 0; w < T / 32; ++w) v += sred[w * C::NRED + tid];
-            part[(long long)tile * C::NRED + tid] = v;
+            for (int w = 0; w < C::WPC; ++w) v += sred[w * C::NRED + tid];
+            part[(long long)cta * C::NRED + tid] = v;
             __threadfence();
         }
         __syncthreads();

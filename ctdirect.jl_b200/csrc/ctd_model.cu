@@ -468,8 +468,13 @@ void Model::ensure_device() {
     CTD_CUDA(cudaMalloc(&d_edge_pos_, sizeof(long long) * std::max<size_t>(edge_pos_.size(), 1)));
     CTD_CUDA(cudaMalloc(&d_sgrid_, sizeof(double) * sgrid_.size()));
     CTD_CUDA(cudaMalloc(&d_params_, sizeof(double) * (size_t)batch_ * npar));
-    const int64_t max_tiles = (N_ >= 3) ? ((int64_t)N_ - 2 + 30) / 31 : 0;  // smallest tile owns 31 steps
-    CTD_CUDA(cudaMalloc(&d_partials_, sizeof(double) * (size_t)batch_ * (max_tiles + 1) * std::max(lc.nred, 1)));
+    int64_t max_ctas = 1;
+    for (int fl : {1, 2, 4, 16, 17, 24, 7, 31}) {
+        const LaunchCfg q = reg_.launcher.cfg(fl);
+        const int64_t tiles = (N_ >= 3) ? ((int64_t)N_ - 2 + q.own - 1) / q.own : 0;
+        max_ctas = std::max<int64_t>(max_ctas, (tiles + q.wpc - 1) / q.wpc + 1);
+    }
+    CTD_CUDA(cudaMalloc(&d_partials_, sizeof(double) * (size_t)batch_ * max_ctas * std::max(lc.nred, 1)));
     CTD_CUDA(cudaMalloc(&d_counters_, sizeof(unsigned int) * batch_));
     CTD_CUDA(cudaMemsetAsync(d_counters_, 0, sizeof(unsigned int) * batch_, stream_));
     CTD_CUDA(cudaMemcpyAsync(d_edge_map_, edge_map_.data(), sizeof(int) * edge_map_.size(), cudaMemcpyHostToDevice, stream_));
@@ -554,9 +559,10 @@ void Model::eval_dev(int flags, const double* x, const double* y, double sigma, 
     EvalArgs a = base_args();
     a.x = x; a.y = y; a.sigma = sigma; a.obj = obj; a.grad = grad; a.c = c; a.jvals = jvals; a.hvals = hvals;
     a.tiles = (N_ >= 3) ? (int)(((int64_t)N_ - 2 + lc.own - 1) / lc.own) : 0;
+    a.ctas = (a.tiles + lc.wpc - 1) / lc.wpc + 1;
     // the edge CTA uses the same dynamic shared memory as its value buffer (its reduction scratch at
     // Cfg::S_RED is only touched after the buffer has been scattered)
-    const size_t edge_smem = sizeof(double) * ((size_t)ne_j_ + ne_h_ + ne_g_ + 2);
+    const size_t edge_smem = sizeof(double) * (3 * ((size_t)ne_j_ + ne_h_ + ne_g_) + 2);
     const size_t smem = std::max(lc.tile_smem, edge_smem);
     auto it = prepared_.find(flags);
     if (it == prepared_.end() || it->second < smem) {
@@ -616,25 +622,35 @@ __global__ void __launch_bounds__(256) ctd_violation_kernel(const double* __rest
     }
 }
 
+void Model::ensure_con_bounds() {
+    if (d_lcon_) return;
+    std::vector<double> l(ncon_), u(ncon_);
+    constraint_bounds(l.data(), u.data());
+    CTD_CUDA(cudaMalloc(&d_lcon_, sizeof(double) * ncon_));
+    CTD_CUDA(cudaMalloc(&d_ucon_, sizeof(double) * ncon_));
+    CTD_CUDA(cudaMalloc(&d_viol_, sizeof(double) * batch_));
+    CTD_CUDA(cudaMemcpyAsync(d_lcon_, l.data(), sizeof(double) * ncon_, cudaMemcpyHostToDevice, stream_));
+    CTD_CUDA(cudaMemcpyAsync(d_ucon_, u.data(), sizeof(double) * ncon_, cudaMemcpyHostToDevice, stream_));
+    CTD_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void Model::violation_dev(const double* c, double* viol) {
+    ensure_device();
+    ensure_con_bounds();
+    if (!c || !viol) throw CtdError{-2, "c / viol is NULL"};
+    ctd_violation_kernel<<<batch_, 256, 0, stream_>>>(c, d_lcon_, d_ucon_, ncon_, viol);
+    CTD_CUDA(cudaGetLastError());
+    ++launches_;
+}
+
 void Model::norms_dev(const double* x, double* obj, double* viol) {
     ensure_device();
     ensure_staging();
-    if (!d_lcon_) {
-        std::vector<double> l(ncon_), u(ncon_);
-        constraint_bounds(l.data(), u.data());
-        CTD_CUDA(cudaMalloc(&d_lcon_, sizeof(double) * ncon_));
-        CTD_CUDA(cudaMalloc(&d_ucon_, sizeof(double) * ncon_));
-        CTD_CUDA(cudaMalloc(&d_viol_, sizeof(double) * batch_));
-        CTD_CUDA(cudaMemcpyAsync(d_lcon_, l.data(), sizeof(double) * ncon_, cudaMemcpyHostToDevice, stream_));
-        CTD_CUDA(cudaMemcpyAsync(d_ucon_, u.data(), sizeof(double) * ncon_, cudaMemcpyHostToDevice, stream_));
-        CTD_CUDA(cudaStreamSynchronize(stream_));
-    }
+    ensure_con_bounds();
     if (!viol) viol = d_viol_;
     if (!obj) obj = d_obj_;
     eval_dev(F_CONS | F_OBJ, x, nullptr, 1.0, obj, nullptr, d_c_, nullptr, nullptr);
-    ctd_violation_kernel<<<batch_, 256, 0, stream_>>>(d_c_, d_lcon_, d_ucon_, ncon_, viol);
-    CTD_CUDA(cudaGetLastError());
-    ++launches_;
+    violation_dev(d_c_, viol);
 }
 
 void Model::norms_host(const double* x, double* obj, double* viol) {

@@ -17,7 +17,7 @@
 namespace ctd {
 
 struct LaunchCfg {
-    int threads = 0, own = 0, nred = 0;
+    int threads = 0, own = 0, nred = 0, wpc = 1;
     size_t tile_smem = 0;
     int map_step = 0, map_fp = 0, map_bc = 0;  // map sizes
 };
@@ -86,6 +86,7 @@ class Model {
     void eval_host(int flags, const double* x, const double* y, double sigma, double* obj, double* grad, double* c,
                    double* jvals, double* hvals);
     void norms_dev(const double* x, double* obj, double* viol);
+    void violation_dev(const double* c, double* viol);
     void norms_host(const double* x, double* obj, double* viol);
     void set_params(const double* params, int n_params);
     void sync();
@@ -97,6 +98,7 @@ class Model {
     void build_edge_tables();
     void ensure_device();
     void ensure_staging();
+    void ensure_con_bounds();
     EvalArgs base_args() const;
 
     Registration reg_;

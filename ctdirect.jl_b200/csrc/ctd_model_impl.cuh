@@ -18,6 +18,7 @@ struct ElementLauncher {
         LaunchCfg c;
         c.threads = C::T;
         c.own = C::OWN;
+        c.wpc = C::WPC;
         c.nred = C::NRED;
         c.tile_smem = C::TILE_SMEM;
         c.map_step = C::M_STEP + 1;
@@ -43,7 +44,7 @@ struct ElementLauncher {
         return (int)cudaErrorInvalidValue;
     }
     static int launch(const EvalArgs& a, int flags, int batch, size_t smem, cudaStream_t st) {
-        dim3 grid((unsigned)(a.tiles + 1), (unsigned)batch, 1);
+        dim3 grid((unsigned)a.ctas, (unsigned)batch, 1);
         switch (flags) {
 #define CTD_X(F) \
     case F: ctd_eval_kernel<E, F><<<grid, Cfg<E, F>::T, smem, st>>>(a); break;

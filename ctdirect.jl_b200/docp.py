@@ -192,6 +192,32 @@ class DOCP:
                       _ptr(res.get("grad")), _ptr(res.get("cons")), _ptr(res.get("jac")), _ptr(res.get("hess"))))
         return res
 
+    def bind(self, what: int, x, y=None, obj_weight: float = 1.0, out=None):
+        """Validate the buffers once and return a zero-argument callable that issues the same evaluation
+        again (solver loops call the same buffers every iteration; this keeps the per-call host cost at
+        one ctypes call).  Returns (callable, result dict)."""
+        x = self._check_in(x, self.nvar, "x")
+        y = self._check_in(y, self.ncon, "y")
+        dev = _is_torch(x)
+        out = dict(out or {})
+        res = {}
+        for bit, key, n in ((OBJ, "obj", 1), (GRAD, "grad", self.nvar), (CONS, "cons", self.ncon),
+                            (JAC, "jac", self.nnzj), (HESS, "hess", self.nnzh)):
+            if what & bit:
+                buf = out.get(key)
+                res[key] = self._check_in(buf, n, key) if buf is not None else self._empty_like(x, n)
+        fn = self._lib.ctd_eval_dev if dev else self._lib.ctd_eval
+        args = (self._h, int(what), _ptr(x), _ptr(y), C.c_double(float(obj_weight)), _ptr(res.get("obj")),
+                _ptr(res.get("grad")), _ptr(res.get("cons")), _ptr(res.get("jac")), _ptr(res.get("hess")))
+        keep = (x, y, res)
+
+        def call(_fn=fn, _args=args, _keep=keep):
+            code = _fn(*_args)
+            if code != 0:
+                _lib.check(code)
+
+        return call, res
+
     def norms(self, x):
         """Per-instance (objective, max constraint violation): what a batched MPC driver gathers."""
         x = self._check_in(x, self.nvar, "x")
@@ -204,6 +230,15 @@ class DOCP:
             obj, viol = np.empty(self.batch), np.empty(self.batch)
             _lib.check(self._lib.ctd_norms(self._h, _ptr(x), _ptr(obj), _ptr(viol)))
         return obj, viol
+
+    def violation(self, c, viol=None):
+        """max_k max(lcon_k - c_k, c_k - ucon_k, 0) per instance, from constraint values on the device."""
+        import torch
+        c = self._check_in(c, self.ncon, "c")
+        if viol is None:
+            viol = torch.empty(self.batch, dtype=torch.float64, device=c.device)
+        _lib.check(self._lib.ctd_violation_dev(self._h, _ptr(c), _ptr(viol)))
+        return viol
 
     def set_params(self, params):
         par = np.ascontiguousarray(params, dtype=np.float64).ravel()

@@ -51,15 +51,18 @@ class TimeSyms:
 
 
 class Differ:
-    """Total derivatives with respect to local variables, time symbols folded in by the chain rule."""
+    """Total derivatives with respect to local variables.  Time symbols and *intermediate* symbols
+    (midpoint / stage states and times, which the kernels evaluate once, in the reference's association
+    order, and feed to the nonlinear OCP functions) are folded in by the chain rule."""
 
-    def __init__(self, z, nv_off, nv, ts: TimeSyms):
+    def __init__(self, z, nv_off, nv, ts: TimeSyms, inter=None):
         self.z = z
         self.nv_off = nv_off
         self.nv = nv
         self.ts = ts
+        self.inter = list(inter or [])   # [(symbol, defining expression in z / time / tableau symbols)]
 
-    def d(self, e, a):
+    def _base(self, e, a):
         e = sp.sympify(e)
         r = sp.diff(e, self.z[a])
         k = a - self.nv_off
@@ -70,6 +73,15 @@ class Differ:
                 r = r + sp.diff(e, self.ts.tp) * self.ts.dtp[k]
             if k in self.ts.dh:
                 r = r + sp.diff(e, self.ts.h) * self.ts.dh[k]
+        return r
+
+    def d(self, e, a):
+        e = sp.sympify(e)
+        r = self._base(e, a)
+        for sym, expr in self.inter:
+            de = sp.diff(e, sym)
+            if de != 0:
+                r = r + de * self._base(expr, a)
         return r
 
 
@@ -105,6 +117,9 @@ class StepElement:
     # c-value code pieces (dynamics evaluations kept apart so that the scheme formula can be
     # emitted in the reference's association order)
     cons_code: dict = field(default_factory=dict)
+    inter: list = field(default_factory=list)        # [(symbol, expr)] intermediates (see Differ)
+    inter_code: list = field(default_factory=list)   # C lines defining them in the reference's order
+    u_node: list = field(default_factory=list)       # control used by the path constraints of the step
 
 
 def _time_syms(ocp: OCP, prefix=""):
@@ -148,10 +163,20 @@ def build_step_element(ocp: OCP, scheme: str, pattern_mode: str = "reference") -
 
     rows = []
     cost = sp.Integer(0)
+    inter, icode = [], []
+    zn = [f"z{a}" for a in range(L.nz)]
     if scheme == "midpoint":
+        # midpoint.jl:54-66: ts = 0.5*(ti + tip1), xs = 0.5*(xi + xip1)
         ui = z[nx:nx + nu]
-        tsm = half * (ti + tp)
-        xs = [half * (xi[k] + xn[k]) for k in range(nx)]
+        tsm = sp.Symbol("m_t")
+        inter.append((tsm, half * (ti + tp)))
+        icode.append("const double m_t = CTD_MUL(0.5, CTD_ADD(ti, tp));")
+        xs = []
+        for k in range(nx):
+            sk = sp.Symbol(f"m_x{k}")
+            xs.append(sk)
+            inter.append((sk, half * (xi[k] + xn[k])))
+            icode.append(f"const double m_x{k} = CTD_MUL(0.5, CTD_ADD({zn[k]}, {zn[L.n_own + k]}));")
         f = dyn(tsm, xs, ui)
         rows = [xn[k] - (xi[k] + h * f[k]) for k in range(nx)]
         cost = h * lag(tsm, xs, ui)
@@ -168,23 +193,45 @@ def build_step_element(ocp: OCP, scheme: str, pattern_mode: str = "reference") -
         A, Bw, Cw = butcher_symbols(s)
         cb = L.control_block
         ks = [z[nx + cb + j * nx: nx + cb + (j + 1) * nx] for j in range(s)]
+        kn = [[zn[nx + cb + j * nx + k] for k in range(nx)] for j in range(s)]
         if L.stagewise:
             us = [z[nx + j * nu: nx + (j + 1) * nu] for j in range(s)]
-            u_node = [sum(Bw[j] * us[j][k] for j in range(s)) for k in range(nu)]  # irk_stagewise.jl:197-205
+            # b-weighted average control (irk_stagewise.jl:197-205), accumulated left to right
+            u_node = []
+            for k in range(nu):
+                sk = sp.Symbol(f"s_un{k}")
+                inter.append((sk, sum(Bw[j] * us[j][k] for j in range(s))))
+                e = f"CTD_MUL(BB0, {zn[nx + k]})"
+                for j in range(1, s):
+                    e = f"CTD_ADD({e}, CTD_MUL(BB{j}, {zn[nx + j * nu + k]}))"
+                icode.append(f"const double s_un{k} = {e};")
+                u_node.append(sk)
         else:
             us = [z[nx:nx + nu]] * s
             u_node = z[nx:nx + nu]
         stage_rows = []
         lsum = sp.Integer(0)
         for j in range(s):
-            tij = ti + Cw[j] * h
-            xij = [xi[k] + sum(h * A[j][l] * ks[l][k] for l in range(s)) for k in range(nx)]
+            # irk.jl:262-302 / irk_stagewise.jl:424-454: tij = ti + c_j*hi ; xij = xi + sum_l (hi*a_jl)*k_l
+            tij = sp.Symbol(f"s{j}_t")
+            inter.append((tij, ti + Cw[j] * h))
+            icode.append(f"const double s{j}_t = CTD_ADD(ti, CTD_MUL(BC{j}, hh));")
+            xij = []
+            for k in range(nx):
+                sk = sp.Symbol(f"s{j}_x{k}")
+                xij.append(sk)
+                inter.append((sk, xi[k] + sum(h * A[j][l] * ks[l][k] for l in range(s))))
+                e = zn[k]
+                for l in range(s):
+                    e = f"CTD_ADD({e}, CTD_MUL(CTD_MUL(hh, BA{j}{l}), {kn[l][k]}))"
+                icode.append(f"const double s{j}_x{k} = {e};")
             f = dyn(tij, xij, us[j])
             stage_rows += [ks[j][k] - f[k] for k in range(nx)]
             lsum = lsum + Bw[j] * lag(tij, xij, us[j])
         state_rows = [xn[k] - (xi[k] + h * sum(Bw[j] * ks[j][k] for j in range(s))) for k in range(nx)]
         rows = state_rows + stage_rows
         cost = h * lsum
+    E.inter, E.inter_code, E.u_node = inter, icode, list(u_node)
     if npc:
         rows += [sp.sympify(e) for e in ocp.path(ti, xi, u_node, v, p)]
     assert len(rows) == L.cblock
@@ -218,7 +265,7 @@ def build_step_element(ocp: OCP, scheme: str, pattern_mode: str = "reference") -
     def which(a):
         return "own" if a < L.n_own else ("next" if a < L.n_own + L.n_next else "v")
 
-    D = Differ(z, L.n_own + L.n_next, nv, ts)
+    D = Differ(z, L.n_own + L.n_next, nv, ts, inter)
     jv_stride = None
     if nv > 0:
         c0 = int(jptr[nvar - nv])

@@ -99,7 +99,9 @@ def _dyn_lines(ocp: OCP, tag, tname, xnames, unames, vsyms, psyms):
 
 
 def _cons_lines(ocp: OCP, E: el.StepElement):
-    """Constraint rows in the reference's evaluation order (see module docstring of elements.py)."""
+    """Constraint rows in the reference's evaluation order.  The dynamics are evaluated at the
+    intermediate points defined by the prologue (E.inter_code); CTD_ADD / CTD_SUB / CTD_MUL are
+    non-contracting (no FMA), so the scheme formulas round exactly like the reference's Julia code."""
     L = E.L
     d = L.dims
     nx, nu, nv, npc, s = d.nx, d.nu, d.nv, d.np, L.stage
@@ -109,54 +111,33 @@ def _cons_lines(ocp: OCP, E: el.StepElement):
     xn = z[L.n_own:L.n_own + nx]
     out = []
     if E.scheme == "midpoint":
-        # midpoint.jl:54-66 (work array) and :139 (c = xip1 - (xi + hi*f))
-        out.append("const double c_ts = 0.5 * (ti + tp);")
+        # midpoint.jl:139  c = xip1 - (xi + hi*f(ts, xs, ui, v))
+        out += _dyn_lines(ocp, "c_", "m_t", [f"m_x{k}" for k in range(nx)], z[nx:nx + nu], vs, E.p)
         for k in range(nx):
-            out.append(f"const double c_xs{k} = 0.5 * ({xi[k]} + {xn[k]});")
-        out += _dyn_lines(ocp, "c_", "c_ts", [f"c_xs{k}" for k in range(nx)], z[nx:nx + nu], vs, E.p)
-        for k in range(nx):
-            out.append(f"s.template c<{k}>({xn[k]} - ({xi[k]} + hh * c_f{k}));")
-        unode = z[nx:nx + nu]
+            out.append(f"s.template c<{k}>(CTD_SUB({xn[k]}, CTD_ADD({xi[k]}, CTD_MUL(hh, c_f{k}))));")
     elif E.scheme == "trapeze":
-        # trapeze.jl:60-69 and :128-140 (x_next = xi + half_hi*(f_i + f_ip1))
+        # trapeze.jl:128-140  c = xip1 - (xi + half_hi*(f_i + f_ip1))
         out += _dyn_lines(ocp, "ci_", "ti", xi, z[nx:nx + nu], vs, E.p)
         out += _dyn_lines(ocp, "cn_", "tp", xn, z[L.n_own + nx:L.n_own + nx + nu], vs, E.p)
-        out.append("const double c_hh2 = 0.5 * (tp - ti);")
+        out.append("const double c_hh2 = CTD_MUL(0.5, CTD_SUB(tp, ti));")
         for k in range(nx):
-            out.append(f"s.template c<{k}>({xn[k]} - ({xi[k]} + c_hh2 * (ci_f{k} + cn_f{k})));")
-        unode = z[nx:nx + nu]
+            out.append(f"s.template c<{k}>(CTD_SUB({xn[k]}, CTD_ADD({xi[k]}, CTD_MUL(c_hh2, CTD_ADD(ci_f{k}, cn_f{k})))));")
     else:
         cb = L.control_block
         kname = lambda j, k: z[nx + cb + j * nx + k]
         for j in range(s):
-            # irk.jl:262-302 / irk_stagewise.jl:424-454
-            out.append(f"const double c_t{j} = ti + BC{j} * hh;")
-            for k in range(nx):
-                e = xi[k]
-                for l in range(s):
-                    e = f"({e} + (hh * BA{j}{l}) * {kname(l, k)})"
-                out.append(f"const double c_x{j}_{k} = {e};")
+            # irk.jl:286-302 / irk_stagewise.jl:440-454  c_stage = k_j - f(tij, xij, u, v)
             un = z[nx + j * nu:nx + (j + 1) * nu] if L.stagewise else z[nx:nx + nu]
-            out += _dyn_lines(ocp, f"c{j}_", f"c_t{j}", [f"c_x{j}_{k}" for k in range(nx)], un, vs, E.p)
+            out += _dyn_lines(ocp, f"c{j}_", f"s{j}_t", [f"s{j}_x{k}" for k in range(nx)], un, vs, E.p)
             for k in range(nx):
-                out.append(f"s.template c<{nx + j * nx + k}>({kname(j, k)} - c{j}_f{k});")
+                out.append(f"s.template c<{nx + j * nx + k}>(CTD_SUB({kname(j, k)}, c{j}_f{k}));")
         for k in range(nx):
-            e = f"BB0 * {kname(0, k)}"
+            e = f"CTD_MUL(BB0, {kname(0, k)})"
             for j in range(1, s):
-                e = f"({e} + BB{j} * {kname(j, k)})"
-            out.append(f"s.template c<{k}>({xn[k]} - ({xi[k]} + hh * ({e})));")
-        if L.stagewise:
-            unode = []
-            for k in range(nu):
-                e = f"BB0 * {z[nx + k]}"
-                for j in range(1, s):
-                    e = f"({e} + BB{j} * {z[nx + j * nu + k]})"
-                out.append(f"const double c_un{k} = {e};")
-                unode.append(f"c_un{k}")
-        else:
-            unode = z[nx:nx + nu]
+                e = f"CTD_ADD({e}, CTD_MUL(BB{j}, {kname(j, k)}))"
+            out.append(f"s.template c<{k}>(CTD_SUB({xn[k]}, CTD_ADD({xi[k]}, CTD_MUL(hh, {e}))));")
     if npc:
-        g = ocp.path(sp.Symbol("ti"), [sp.Symbol(n) for n in xi], [sp.Symbol(n) for n in unode], vs, E.p)
+        g = ocp.path(sp.Symbol("ti"), [sp.Symbol(n) for n in xi], list(E.u_node), vs, E.p)
         lines, outs = cse_block(g, "c_pw")
         out += lines
         for r, o in enumerate(outs):
@@ -164,7 +145,7 @@ def _cons_lines(ocp: OCP, E: el.StepElement):
     return out
 
 
-def _prologue(nz, nlam, npar, ts: el.TimeSyms, use_time=True):
+def _prologue(nz, nlam, npar, ts: el.TimeSyms, use_time=True, inter_code=()):
     out = [f"const double z{a} = z[{a}];" for a in range(nz)]
     out += [f"const double lam{r} = lam[{r}];" for r in range(nlam)]
     out += [f"const double p{k} = p[{k}];" for k in range(npar)]
@@ -172,6 +153,7 @@ def _prologue(nz, nlam, npar, ts: el.TimeSyms, use_time=True):
         out += ["const double ti = T.ti, tp = T.tp, hh = T.hh;"]
         for k in sorted(ts.dti):
             out.append(f"const double dti{k} = T.dti[{k}], dtp{k} = T.dtp[{k}], dh{k} = T.dh[{k}];")
+    out += list(inter_code)
     return out
 
 
@@ -262,7 +244,7 @@ def emit_pair(ocp: OCP, scheme: str, pattern_mode: str = "reference") -> str:
     o.append("  template <bool WC, bool WJ, bool WH, class S>\n"
              "  __device__ __forceinline__ static void step(const double* __restrict__ z, const ctd::TimeArgs<NV>& T,\n"
              "      const double* __restrict__ p, const double* __restrict__ lam, const double sg, S& s) {\n")
-    o.append(_indent(_prologue(L.nz, L.cblock, ocp.npar, E.ts)))
+    o.append(_indent(_prologue(L.nz, L.cblock, ocp.npar, E.ts, inter_code=E.inter_code)))
     o.append("    if constexpr (WC) {\n" + _indent(_cons_lines(ocp, E), 6) + "    }\n")
     jex = [e[3] for e in E.j_own] + [e[3] for e in E.j_next] + [e[3] for e in E.j_v]
     hex_ = [e[3] for e in E.h_own] + [e[3] for e in E.h_next] + [e[3] for e in E.h_vv]
@@ -335,7 +317,7 @@ def emit_pair(ocp: OCP, scheme: str, pattern_mode: str = "reference") -> str:
     o.append("  __device__ __forceinline__ static double cost_step(const double* __restrict__ z, const ctd::TimeArgs<NV>& T,\n"
              "      const double* __restrict__ p) {\n")
     if d.lagrange:
-        o.append(_indent(_prologue(L.nz, 0, ocp.npar, E.ts)))
+        o.append(_indent(_prologue(L.nz, 0, ocp.npar, E.ts, inter_code=E.inter_code)))
         lines, outs = cse_block([E.cost], "w")
         o.append(_indent(lines))
         o.append(f"    return {outs[0]};\n")
@@ -358,7 +340,7 @@ def emit_pair(ocp: OCP, scheme: str, pattern_mode: str = "reference") -> str:
     o.append("  template <class S>\n  __device__ __forceinline__ static void grad_step(const double* __restrict__ z, const ctd::TimeArgs<NV>& T,\n"
              "      const double* __restrict__ p, S& s) {\n")
     if d.lagrange:
-        o.append(_indent(_prologue(L.nz, 0, ocp.npar, E.ts)))
+        o.append(_indent(_prologue(L.nz, 0, ocp.npar, E.ts, inter_code=E.inter_code)))
         lines, outs = cse_block([e[3] for e in E.g_own] + [e[3] for e in E.g_next] + [e[3] for e in E.g_v], "w")
         o.append(_indent(lines))
         k = 0

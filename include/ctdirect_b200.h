@@ -113,6 +113,8 @@ CTD_API int ctd_eval_dev(ctd_handle h, int what, const double* x, const double* 
  * numbers a batched MPC driver gathers across GPUs); obj and viol have `batch` entries (device) */
 CTD_API int ctd_norms_dev(ctd_handle h, const double* x, double* obj, double* viol);
 CTD_API int ctd_norms(ctd_handle h, const double* x, double* obj, double* viol);
+/* violation only, from constraint values c already on the device (e.g. produced by ctd_eval_dev) */
+CTD_API int ctd_violation_dev(ctd_handle h, const double* c, double* viol);
 /* replace the problem parameters (n = npar or batch*npar), e.g. new MPC scenarios */
 CTD_API int ctd_set_params(ctd_handle h, const double* params, int32_t n);
 CTD_API int ctd_sync(ctd_handle h);
