@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libctdirect_b200.so")
+LIB_PATH = os.environ.get("CTD_LIB") or os.path.join(HERE, "lib", "libctdirect_b200.so")
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int64)

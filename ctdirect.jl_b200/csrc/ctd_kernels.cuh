@@ -53,7 +53,7 @@ struct EvalArgs {
     const double* params;
     long long x_stride, y_stride, c_stride, j_stride, h_stride, g_stride;
     double sigma;
-    const double* sgrid;   // normalized time grid (N+1), or nullptr for the uniform grid j/N
+    const double* sgrid;   // normalized time grid (N+1 values in [0,1])
     int N;
     int tiles;             // warp tiles per instance
     int ctas;              // CTAs per instance: CTA 0 is the edge CTA, CTAs 1.. hold WPC warp tiles each
@@ -68,7 +68,8 @@ struct EvalArgs {
     int ne_j, ne_h, ne_g;         // edge-buffer sections: J values, H values, gradient entries
     int ntask;
     EdgeTask task[MAX_TASKS];
-    int fp_map_off, bc_map_off;
+    int fp_map_off, bc_map_off, nmap;
+    long long* trace;             // debug builds (-DCTD_TRACE): per-warp timestamps, else nullptr
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -89,22 +90,36 @@ struct Cfg {
     // warps per CTA: 4 when a CTA's staged tiles stay small (many CTAs per SM), fewer for wide
     // elements (e.g. 3-stage IRK of a 6-state problem)
     static constexpr int SMEM_MAX = 200 * 1024;
-    static constexpr int WPC = (PER_STEP * 8 * 31 * 4 <= 96 * 1024) ? 4 : (PER_STEP * 8 * 31 * 2 <= 128 * 1024) ? 2 : 1;
+#ifndef CTD_WPC
+#define CTD_WPC 8
+#endif
+    static constexpr int WPC = (PER_STEP * 8 * 32 * CTD_WPC <= 200 * 1024) ? CTD_WPC : 1;
     static constexpr int T = WPC * 32;
-    static constexpr int FIT = PER_STEP > 0 ? (SMEM_MAX / WPC - 512) / (PER_STEP * 8) : 31;
+    // light elements: cap registers at 88/thread so that 22 warps (682 owned steps) are resident per SM,
+    // i.e. a grid of 1e5 steps is ONE wave on 148 SMs; wide elements keep the full register file
+    // light elements (midpoint / trapeze of small systems): registers are capped so that 24 warps (744
+    // owned steps) are resident per SM and a grid of 1e5 steps is ONE wave on 148 SMs; wide elements
+    // keep the full register file
+#ifndef CTD_MAXNREG
+#define CTD_MAXNREG 80
+#endif
+    static constexpr bool LIGHT = PER_STEP <= 64;
+    static constexpr int FIT = PER_STEP > 0 ? (SMEM_MAX / WPC - 512) / (PER_STEP * 8) - 1 : 31;
     static constexpr int OWN = (31 < FIT) ? 31 : FIT;  // owned steps per warp tile
     static_assert(OWN >= 1, "element too wide for one SM's shared memory");
     // sub-buffers of a warp's region (each with 2 doubles of slack so that the staged range can be
     // given the same 16-byte phase as its destination in global memory)
     static constexpr int even(int n) { return (n + 3) & ~1; }
     static constexpr int S_C = 0;
-    static constexpr int S_J = S_C + (WC ? even(OWN * E::CB) : 0);
-    static constexpr int S_JV = S_J + (WJ ? even(OWN * E::J_BLOCK) : 0);
-    static constexpr int JV_ONE = even(OWN * E::JV_STRIDE);
+    // (OWN + 1 blocks each: the last one is a dump block, written by the halo lane's "own" values and
+    // the last lane's "next" values, so that the sinks store without predicates or branches)
+    static constexpr int S_J = S_C + (WC ? even((OWN + 1) * E::CB) : 0);
+    static constexpr int S_JV = S_J + (WJ ? even((OWN + 1) * E::J_BLOCK) : 0);
+    static constexpr int JV_ONE = even((OWN + 1) * E::JV_STRIDE);
     static constexpr int S_G = S_JV + (WJ ? NV * JV_ONE : 0);
-    static constexpr int A_END = S_G + (WG ? even(OWN * E::BLK) : 0);
+    static constexpr int A_END = S_G + (WG ? even((OWN + 1) * E::BLK) : 0);
     static constexpr int S_H = 0;
-    static constexpr int B_END = WH ? even(OWN * E::H_BLOCK) : 0;
+    static constexpr int B_END = WH ? even((OWN + 1) * E::H_BLOCK) : 0;
     static constexpr int WARP_DOUBLES = ((A_END > B_END ? A_END : B_END) + 1) & ~1;
     static constexpr int S_RED = WPC * WARP_DOUBLES;
     static constexpr int S_END = S_RED + WPC * (NRED > 0 ? NRED : 1) + 2;
@@ -119,8 +134,13 @@ struct Cfg {
 
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double grid_point(const EvalArgs& a, long long j /*0-based node*/) {
-    // DOCP_data.jl:176-214: collect(LinRange(0,1,N+1))[j+1] == fl(j/N) for the default grid
-    return a.sgrid ? a.sgrid[j] : (double)j / (double)a.N;
+    // DOCP_data.jl:176-214: the normalized grid (collect(LinRange(0,1,N+1)) by default) is built once on
+    // the host; it is shared by all instances and evaluations, so it stays L2-resident
+#ifdef CTD_USE_DIV
+    return (double)j / (double)a.N;
+#else
+    return __ldg(a.sgrid + j);
+#endif
 }
 
 template <class E>
@@ -159,6 +179,48 @@ __device__ __forceinline__ void store_range(double* __restrict__ g, const double
     if (done < n && tid == nthreads - 1) g[done] = s[done];
 }
 
+// ---- TMA bulk store (cp.async.bulk, shared::cta -> global): one elected lane hands a staged range to
+// the copy engine, the warp's issue slots stay free for the next phase.
+#ifndef CTD_TMA_STORE
+#define CTD_TMA_STORE 1
+#endif
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// contiguous shared -> global copy of n doubles; s and g have the same 16-byte phase.  Called by the
+// whole warp after fence_proxy_async_smem() + __syncwarp(); lane 0 issues the bulk copy of the
+// 16-byte-aligned body, the (at most one) leading and trailing doubles are stored directly.
+__device__ __forceinline__ void bulk_store_range(double* __restrict__ g, const double* __restrict__ s, int n, int lane) {
+    const int ph = (int)((reinterpret_cast<unsigned long long>(g) >> 3) & 1ull);
+    const int head = ph < n ? ph : n;
+    const int n2 = (n - head) >> 1;
+    if (lane == 0) {
+        if (n2 > 0) {
+            const unsigned int saddr = (unsigned int)__cvta_generic_to_shared(s + head);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         :: "l"(g + head), "r"(saddr), "r"(n2 * 16) : "memory");
+        }
+    } else if (lane == 1) {
+        if (head) g[0] = s[0];
+        const int done = head + 2 * n2;
+        if (done < n) g[done] = s[done];
+    }
+}
+
+#ifdef CTD_TRACE
+__device__ __forceinline__ long long gtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define CTD_STAMP(k) do { if (a.trace && lane == 0) a.trace[((long long)cta * C::WPC + warp) * 8 + (k)] = gtime(); } while (0)
+#else
+#define CTD_STAMP(k) do { } while (0)
+#endif
+
 __device__ __forceinline__ int phase_of(const double* g) {
     return (int)((reinterpret_cast<unsigned long long>(g) >> 3) & 1ull);
 }
@@ -180,21 +242,23 @@ struct TileSink {
     double gn_[E::NG_NEXT > 0 ? E::NG_NEXT : 1];
     double* red;
 
-    template <int R> __device__ __forceinline__ void c(double v) { if (PC && owner) c_[R] = v; }
-    template <int N> __device__ __forceinline__ void jo(double v) { if (PJ && owner) jo_[E::J_OWN(N, 2)] = v; }
-    template <int N> __device__ __forceinline__ void jn(double v) { if (PJ && giver) jn_[E::J_NEXT(N, 2)] = v; }
+    template <int R> __device__ __forceinline__ void c(double v) { if (PC) c_[R] = v; }
+    template <int N> __device__ __forceinline__ void jo(double v) { if (PJ) jo_[E::J_OWN(N, 2)] = v; }
+    template <int N> __device__ __forceinline__ void jn(double v) { if (PJ) jn_[E::J_NEXT(N, 2)] = v; }
     template <int N> __device__ __forceinline__ void jv(double v) {
-        if (PJ && owner) jv_[E::J_V(N, 1)][E::J_V(N, 2)] = v;
+        if (PJ) jv_[E::J_V(N, 1)][E::J_V(N, 2)] = v;
     }
-    template <int N> __device__ __forceinline__ void ho(double v) { if (PH && owner) ho_[E::H_OWN(N, 2)] = v; }
+    template <int N> __device__ __forceinline__ void ho(double v) { if (PH) ho_[E::H_OWN(N, 2)] = v; }
     template <int N> __device__ __forceinline__ void hn(double v) { if (PH) hn_[N] = v; }
-    template <int K> __device__ __forceinline__ void hv(double v) { if (PH && owner) red[C::R_H + K] += v; }
-    template <int N> __device__ __forceinline__ void go(double v) { if (PG && owner) go_[E::G_OWN(N, 2)] = v; }
+    template <int K> __device__ __forceinline__ void hv(double v) { if (PH) red[C::R_H + K] += owner ? v : 0.0; }
+    template <int N> __device__ __forceinline__ void go(double v) { if (PG) go_[E::G_OWN(N, 2)] = v; }
     template <int N> __device__ __forceinline__ void gn(double v) { if (PG) gn_[N] = v; }
-    template <int N> __device__ __forceinline__ void gv(double v) { if (PG && owner) red[C::R_G + E::G_V(N, 2)] += v; }
+    template <int N> __device__ __forceinline__ void gv(double v) { if (PG) red[C::R_G + E::G_V(N, 2)] += owner ? v : 0.0; }
 };
 
-// Sink of an edge task: values are accumulated into the edge buffer through the host-built map.
+// Sink of an edge job: every value goes to its own entry of one layer of the edge buffer (plain
+// stores: inside a layer no two values share an entry), through the host-built map.
+// map codes: >= 0 edge-buffer index, -1 not in the pattern (dropped), <= -2 reduction slot -(m+2).
 template <class E, int F>
 struct EdgeSink {
     using C = Cfg<E, F>;
@@ -203,7 +267,7 @@ struct EdgeSink {
     double* crow;     // destination of the constraint rows (global) or nullptr
     double* red;
     __device__ __forceinline__ void put(int m, double v) {
-        if (m >= 0) atomicAdd(&buf[m], v);
+        if (m >= 0) buf[m] = v;
     }
     template <int R> __device__ __forceinline__ void c(double v) { if (crow) crow[R] = v; }
     template <int N> __device__ __forceinline__ void jo(double v) { put(map[C::M_JO + N], v); }
@@ -225,21 +289,19 @@ struct EdgeElemSink {
     const int* map;
     double* crow;
     double* red;
-    // map codes: >= 0 edge-buffer index, -1 not in the pattern (dropped), <= -2 reduction slot -(m+2)
-    // ((v,v) Hessian entry for h<>, d/dv_k of the cost for g<>)
     template <int R> __device__ __forceinline__ void c(double v) { if (crow) crow[R] = v; }
     template <int N> __device__ __forceinline__ void j(double v) {
         const int m = map[MJ + N];
-        if (m >= 0) atomicAdd(&buf[m], v);
+        if (m >= 0) buf[m] = v;
     }
     template <int N> __device__ __forceinline__ void h(double v) {
         const int m = map[MH + N];
-        if (m >= 0) atomicAdd(&buf[m], v);
+        if (m >= 0) buf[m] = v;
         else if (m <= -2) red[C::R_H + (-m - 2)] += v;
     }
     template <int N> __device__ __forceinline__ void g(double v) {
         const int m = map[MG + N];
-        if (m >= 0) atomicAdd(&buf[m], v);
+        if (m >= 0) buf[m] = v;
         else if (m <= -2) red[C::R_G + (-m - 2)] += v;
     }
 };
@@ -250,15 +312,40 @@ __device__ __forceinline__ void load_step(const double* __restrict__ x, long lon
                                           double* __restrict__ z) {
     const double* xo = x + (i - 1) * E::BLK;
 #pragma unroll
-    for (int k = 0; k < E::NOWN + E::NNEXT; ++k) z[k] = xo[k];
+    for (int k = 0; k < E::NOWN + E::NNEXT; ++k) z[k] = __ldg(xo + k);
 #pragma unroll
-    for (int k = 0; k < E::NV; ++k) z[E::NOWN + E::NNEXT + k] = x[nvar - E::NV + k];
+    for (int k = 0; k < E::NV; ++k) z[E::NOWN + E::NNEXT + k] = __ldg(x + nvar - E::NV + k);
 }
 
-// Edge CTA: the elements that touch column blocks 1, N, N+1 and the boundary / final-path rows.  Every
-// job (a step element, the final-path element, the boundary+Mayer element) is run by lane 0 of a warp;
-// jobs of different kinds accumulate into different layers of the edge buffer, which are summed in a
-// fixed order when the buffer is scattered (deterministic whatever the warp interleaving).
+// Edge CTA: the elements that touch column blocks 1, N, N+1 and the boundary / final-path rows.  The
+// work is cut into jobs -- (step element, phase A), (step element, phase B), final-path element,
+// boundary+Mayer element -- each run by lane 0 of a warp.  Jobs whose values can land on the same entry
+// write to different layers of the edge buffer, which are summed in a fixed order when the buffer is
+// scattered (deterministic whatever the warp interleaving, and no atomics).
+constexpr int EDGE_LAYERS = 4;   // step tasks 0/2, step task 1, final path, boundary
+
+template <class E, int F, bool PA, bool PB>
+__device__ __forceinline__ void edge_step_job(const EvalArgs& a, const EdgeTask& tk, const double* __restrict__ x,
+                                              const double* __restrict__ y, const double* __restrict__ p, double* c,
+                                              double* layer, const int* smap, double* red) {
+    using C = Cfg<E, F>;
+    constexpr bool JC = PA && C::WC, JJ = PA && C::WJ, JH = PB && C::WH, JG = PA && C::WG, JO = PA && C::WO;
+    double z[E::NZ], lam[E::CB];
+    load_step<E>(x, a.nvar, tk.step, z);
+#pragma unroll
+    for (int r = 0; r < E::CB; ++r) lam[r] = (JH && y) ? __ldg(y + (long long)(tk.step - 1) * E::CB + r) : 0.0;
+    TimeArgs<E::NV> Tm;
+    time_args<E>(a, z + E::NOWN + E::NNEXT, p, tk.step, Tm);
+    EdgeSink<E, F> s;
+    s.buf = layer;
+    s.map = smap + tk.map_off;
+    s.crow = (JC && tk.own) ? c + (long long)(tk.step - 1) * E::CB : nullptr;
+    s.red = red;
+    if constexpr (JC || JJ || JH) E::template step<JC, JJ, JH>(z, Tm, p, lam, a.sigma, s);
+    if constexpr (JG) E::grad_step(z, Tm, p, s);
+    if constexpr (JO) { if (tk.own) red[C::R_O] += E::cost_step(z, Tm, p); }
+}
+
 template <class E, int F>
 __device__ void edge_cta(const EvalArgs& a, const double* __restrict__ x, const double* __restrict__ y,
                          const double* __restrict__ p, double* c, double* jvals, double* hvals, double* grad,
@@ -268,51 +355,52 @@ __device__ void edge_cta(const EvalArgs& a, const double* __restrict__ x, const 
     constexpr int T = C::T;
     constexpr int NW = C::WPC;
     const int ne = a.ne_j + a.ne_h + a.ne_g;
-    for (int k = tid; k < 3 * ne; k += T) buf[k] = 0.0;
+    // the position maps are staged in shared memory first (one coalesced pass): the sinks look up one
+    // map entry per value, and those lookups must not be dependent global loads
+    int* smap = reinterpret_cast<int*>(buf + EDGE_LAYERS * ne);
+    for (int k = tid; k < a.nmap; k += T) smap[k] = __ldg(a.edge_map + k);
+    for (int k = tid; k < EDGE_LAYERS * ne; k += T) buf[k] = 0.0;
     __syncthreads();
     if ((tid & 31) == 0) {
-        const int njobs = a.ntask + 2;
+        constexpr bool TWO = C::PHASE_A && C::PHASE_B;
+        constexpr int PER_TASK = TWO ? 2 : 1;
+        const int nstep = a.ntask * PER_TASK;
+        const int njobs = nstep + 2;
         for (int job = tid >> 5; job < njobs; job += NW) {
-            if (job < a.ntask) {
+            if (job < nstep) {
                 // step elements: stepStateConstraints! / stepPathConstraints! of steps 1, N-1, N
-                const EdgeTask tk = a.task[job];
-                double z[E::NZ], lam[E::CB];
-                load_step<E>(x, a.nvar, tk.step, z);
-#pragma unroll
-                for (int r = 0; r < E::CB; ++r) lam[r] = (C::WH && y) ? y[(long long)(tk.step - 1) * E::CB + r] : 0.0;
-                TimeArgs<E::NV> Tm;
-                time_args<E>(a, z + E::NOWN + E::NNEXT, p, tk.step, Tm);
-                EdgeSink<E, F> s;
-                s.buf = buf;
-                s.map = a.edge_map + tk.map_off;
-                s.crow = (C::WC && tk.own) ? c + (long long)(tk.step - 1) * E::CB : nullptr;
-                s.red = red;
-                if constexpr (C::WC || C::WJ || C::WH) E::template step<C::WC, C::WJ, C::WH>(z, Tm, p, lam, a.sigma, s);
-                if constexpr (C::WG) E::grad_step(z, Tm, p, s);
-                if constexpr (C::WO) { if (tk.own) red[C::R_O] += E::cost_step(z, Tm, p); }
-            } else if (job == a.ntask) {
+                const int t = job / PER_TASK, part = job % PER_TASK;
+                const EdgeTask tk = a.task[t];
+                double* layer = buf + (t & 1) * ne;
+                if constexpr (TWO) {
+                    if (part == 0) edge_step_job<E, F, true, false>(a, tk, x, y, p, c, layer, smap, red);
+                    else edge_step_job<E, F, false, true>(a, tk, x, y, p, c, layer, smap, red);
+                } else {
+                    edge_step_job<E, F, C::PHASE_A, C::PHASE_B>(a, tk, x, y, p, c, layer, smap, red);
+                }
+            } else if (job == nstep) {
                 // final path constraints g(t_f, x_f, u_f, v)  (DOCP_functions.jl:100)
                 if constexpr (E::NP > 0 && (C::WC || C::WJ || C::WH)) {
                     double z[E::FP_NLOC], lam[E::NP];
                     const long long N = a.N;
                     if (E::FINAL_CONTROL) {
 #pragma unroll
-                        for (int k = 0; k < E::NX + E::NU; ++k) z[k] = x[N * E::BLK + k];
+                        for (int k = 0; k < E::NX + E::NU; ++k) z[k] = __ldg(x + N * E::BLK + k);
                     } else {
 #pragma unroll
-                        for (int k = 0; k < E::CTRL_BLK; ++k) z[k] = x[(N - 1) * E::BLK + E::NX + k];
+                        for (int k = 0; k < E::CTRL_BLK; ++k) z[k] = __ldg(x + (N - 1) * E::BLK + E::NX + k);
 #pragma unroll
-                        for (int k = 0; k < E::NX; ++k) z[E::CTRL_BLK + k] = x[N * E::BLK + k];
+                        for (int k = 0; k < E::NX; ++k) z[E::CTRL_BLK + k] = __ldg(x + N * E::BLK + k);
                     }
 #pragma unroll
-                    for (int k = 0; k < E::NV; ++k) z[E::FP_NLOC - E::NV + k] = x[a.nvar - E::NV + k];
+                    for (int k = 0; k < E::NV; ++k) z[E::FP_NLOC - E::NV + k] = __ldg(x + a.nvar - E::NV + k);
 #pragma unroll
-                    for (int r = 0; r < E::NP; ++r) lam[r] = (C::WH && y) ? y[N * E::CB + r] : 0.0;
+                    for (int r = 0; r < E::NP; ++r) lam[r] = (C::WH && y) ? __ldg(y + N * E::CB + r) : 0.0;
                     TimeArgs<E::NV> Tm;
                     time_args<E>(a, z + E::FP_NLOC - E::NV, p, N + 1, Tm);
                     EdgeElemSink<E, F, C::M_FP_J, C::M_FP_H, 0> s;
-                    s.buf = buf + ne;
-                    s.map = a.edge_map + a.fp_map_off;
+                    s.buf = buf + 2 * ne;
+                    s.map = smap + a.fp_map_off;
                     s.crow = C::WC ? c + N * E::CB : nullptr;
                     s.red = red;
                     E::template fpath<C::WC, C::WJ, C::WH>(z, Tm, p, lam, s);
@@ -322,14 +410,14 @@ __device__ void edge_cta(const EvalArgs& a, const double* __restrict__ x, const 
                 double z[E::BC_NLOC], lam[E::NB > 0 ? E::NB : 1];
                 const long long N = a.N;
 #pragma unroll
-                for (int k = 0; k < E::NX; ++k) { z[k] = x[k]; z[E::NX + k] = x[N * E::BLK + k]; }
+                for (int k = 0; k < E::NX; ++k) { z[k] = __ldg(x + k); z[E::NX + k] = __ldg(x + N * E::BLK + k); }
 #pragma unroll
-                for (int k = 0; k < E::NV; ++k) z[2 * E::NX + k] = x[a.nvar - E::NV + k];
+                for (int k = 0; k < E::NV; ++k) z[2 * E::NX + k] = __ldg(x + a.nvar - E::NV + k);
 #pragma unroll
-                for (int r = 0; r < E::NB; ++r) lam[r] = (C::WH && y) ? y[a.ncon - E::NB + r] : 0.0;
+                for (int r = 0; r < E::NB; ++r) lam[r] = (C::WH && y) ? __ldg(y + a.ncon - E::NB + r) : 0.0;
                 EdgeElemSink<E, F, C::M_BC_J, C::M_BC_H, C::M_BC_G> s;
-                s.buf = buf + 2 * ne;
-                s.map = a.edge_map + a.bc_map_off;
+                s.buf = buf + 3 * ne;
+                s.map = smap + a.bc_map_off;
                 s.crow = (C::WC && E::NB > 0) ? c + (a.ncon - E::NB) : nullptr;
                 s.red = red;
                 if constexpr (C::WC || C::WJ || C::WH) E::template bc<C::WC, C::WJ, C::WH>(z, p, lam, a.sigma, s);
@@ -340,12 +428,14 @@ __device__ void edge_cta(const EvalArgs& a, const double* __restrict__ x, const 
     }
     __syncthreads();
     // ---- scatter the edge buffer (layers summed in a fixed order)
+    auto total = [&](int k) { return ((buf[k] + buf[ne + k]) + buf[2 * ne + k]) + buf[3 * ne + k]; };
     if constexpr (C::WJ)
-        for (int k = tid; k < a.ne_j; k += T) jvals[a.edge_pos[k]] = (buf[k] + buf[ne + k]) + buf[2 * ne + k];
+        for (int k = tid; k < a.ne_j; k += T) jvals[__ldg(a.edge_pos + k)] = total(k);
     if constexpr (C::WH)
-        for (int k = a.ne_j + tid; k < a.ne_j + a.ne_h; k += T) hvals[a.edge_pos[k]] = (buf[k] + buf[ne + k]) + buf[2 * ne + k];
+        for (int k = a.ne_j + tid; k < a.ne_j + a.ne_h; k += T) hvals[__ldg(a.edge_pos + k)] = total(k);
     if constexpr (C::WG)
-        for (int k = a.ne_j + a.ne_h + tid; k < ne; k += T) grad[a.edge_pos[k]] = (buf[k] + buf[ne + k]) + buf[2 * ne + k];
+        for (int k = a.ne_j + a.ne_h + tid; k < ne; k += T) grad[__ldg(a.edge_pos + k)] = total(k);
+    __syncthreads();   // the caller reuses the shared memory of `buf` for its reduction scratch
 }
 
 // One phase of a warp tile: evaluate, stage, add the halo contributions, copy out.
@@ -377,21 +467,21 @@ __device__ __forceinline__ void tile_phase(const EvalArgs& a, double* __restrict
     s.red = red;
     s.owner = active && lane >= 1;
     s.giver = active && lane < nown;
-    s.c_ = sC + (lane - 1) * E::CB;
-    s.jo_ = sJ + (lane - 1) * E::J_BLOCK;
-    s.jn_ = sJ + lane * E::J_BLOCK;
-    s.ho_ = sH + (lane - 1) * E::H_BLOCK;
-    s.go_ = sG + (lane - 1) * E::BLK;
+    const int ob = s.owner ? lane - 1 : C::OWN;   // own block (dump block for the halo lane)
+    const int nb = s.giver ? lane : C::OWN;       // next block (dump block for the last lane)
+    s.c_ = sC + ob * E::CB;
+    s.jo_ = sJ + ob * E::J_BLOCK;
+    s.jn_ = sJ + nb * E::J_BLOCK;
+    s.ho_ = sH + ob * E::H_BLOCK;
+    s.go_ = sG + ob * E::BLK;
     if constexpr (PJ && C::NV > 0) {
 #pragma unroll
-        for (int k = 0; k < C::NV; ++k) s.jv_[k] = sJV[k] + (lane - 1) * E::JV_STRIDE;
+        for (int k = 0; k < C::NV; ++k) s.jv_[k] = sJV[k] + ob * E::JV_STRIDE;
     }
     if (active) {
         if constexpr (PG) {
-            if (s.owner) {
 #pragma unroll
-                for (int k = 0; k < E::BLK; ++k) s.go_[k] = 0.0;
-            }
+            for (int k = 0; k < E::BLK; ++k) s.go_[k] = 0.0;
         }
         if constexpr (PC || PJ || PH) E::template step<PC, PJ, PH>(z, Tm, p, lam, a.sigma, s);
         if constexpr (PG) E::grad_step(z, Tm, p, s);
@@ -399,18 +489,35 @@ __device__ __forceinline__ void tile_phase(const EvalArgs& a, double* __restrict
     }
     __syncwarp();
     if constexpr ((PH && E::NH_NEXT > 0) || (PG && E::NG_NEXT > 0)) {
-        if (s.giver) {
+        if (active) {
             if constexpr (PH) {
 #pragma unroll
-                for (int n = 0; n < E::NH_NEXT; ++n) sH[lane * E::H_BLOCK + E::H_NEXT(n, 2)] += s.hn_[n];
+                for (int n = 0; n < E::NH_NEXT; ++n) sH[nb * E::H_BLOCK + E::H_NEXT(n, 2)] += s.hn_[n];
             }
             if constexpr (PG) {
 #pragma unroll
-                for (int n = 0; n < E::NG_NEXT; ++n) sG[lane * E::BLK + E::G_NEXT(n, 2)] += s.gn_[n];
+                for (int n = 0; n < E::NG_NEXT; ++n) sG[nb * E::BLK + E::G_NEXT(n, 2)] += s.gn_[n];
             }
         }
         __syncwarp();
     }
+#if CTD_TMA_STORE
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (nown > 0) {
+        if constexpr (PC) bulk_store_range(gC, sC, nown * E::CB, lane);
+        if constexpr (PJ) {
+            bulk_store_range(gJ, sJ, nown * E::J_BLOCK, lane);
+            if constexpr (C::NV > 0) {
+#pragma unroll
+                for (int k = 0; k < C::NV; ++k) bulk_store_range(gJV[k], sJV[k], nown * E::JV_STRIDE, lane);
+            }
+        }
+        if constexpr (PH) bulk_store_range(gH, sH, nown * E::H_BLOCK, lane);
+        if constexpr (PG) bulk_store_range(gG, sG, nown * E::BLK, lane);
+        if (lane == 0) bulk_commit();
+    }
+#else
     if (nown > 0) {
         if constexpr (PC) store_range(gC, sC, nown * E::CB, lane, 32);
         if constexpr (PJ) {
@@ -424,10 +531,11 @@ __device__ __forceinline__ void tile_phase(const EvalArgs& a, double* __restrict
         if constexpr (PG) store_range(gG, sG, nown * E::BLK, lane, 32);
     }
     __syncwarp();
+#endif
 }
 
 template <class E, int F>
-__global__ void __launch_bounds__(Cfg<E, F>::T) ctd_eval_kernel(const EvalArgs a) {
+__device__ __forceinline__ void eval_body(const EvalArgs& a) {
     using C = Cfg<E, F>;
     constexpr int T = C::T;
     extern __shared__ __align__(16) double smem[];
@@ -447,9 +555,16 @@ __global__ void __launch_bounds__(Cfg<E, F>::T) ctd_eval_kernel(const EvalArgs a
     double red[C::NRED > 0 ? C::NRED : 1];
 #pragma unroll
     for (int k = 0; k < (C::NRED > 0 ? C::NRED : 1); ++k) red[k] = 0.0;
+    __shared__ unsigned int cta_ticket;
+    if constexpr (C::NRED > 0) {
+        if (tid == 0) cta_ticket = 0u;
+        __syncthreads();
+    }
 
+    CTD_STAMP(0);
     if (cta == 0) {
         edge_cta<E, F>(a, x, y, p, c, jvals, hvals, grad, smem, red);
+        CTD_STAMP(4);
     } else {
         const long long tile = (long long)(cta - 1) * C::WPC + warp;
         const long long i0 = 2 + tile * C::OWN;                       // first owned step / column block
@@ -467,60 +582,108 @@ __global__ void __launch_bounds__(Cfg<E, F>::T) ctd_eval_kernel(const EvalArgs a
             for (int r = 0; r < E::CB; ++r) lam[r] = (C::WH && y) ? y[(i - 1) * E::CB + r] : 0.0;
             time_args<E>(a, z + E::NOWN + E::NNEXT, p, i, Tm);
         }
+#ifdef CTD_TRACE
+        if (active && Tm.hh == -1.2345) CTD_STAMP(7);   // forces the loads to have arrived
+        CTD_STAMP(1);
+#endif
         if constexpr (C::PHASE_A)
             tile_phase<E, F, C::WC, C::WJ, false, C::WG, C::WO>(a, ws, z, lam, Tm, p, red, lane, nown, i0, active, c,
                                                                   jvals, hvals, grad);
-        if constexpr (C::PHASE_B)
+        CTD_STAMP(2);
+        if constexpr (C::PHASE_B) {
+#if CTD_TMA_STORE
+            if constexpr (C::PHASE_A) {   // phase B reuses the region: the copy engine must have read it
+                if (lane == 0) bulk_wait_read();
+                __syncwarp();
+            }
+#endif
+            CTD_STAMP(3);
             tile_phase<E, F, false, false, true, false, false>(a, ws, z, lam, Tm, p, red, lane, nown, i0, active, c,
                                                                 jvals, hvals, grad);
+        }
+#if CTD_TMA_STORE
+        CTD_STAMP(4);
+        if (lane == 0) bulk_wait_read();   // shared memory must outlive the copies that read it
+#endif
+        CTD_STAMP(5);
     }
 
-    // ---- deterministic reduction of the global sums: (v,v) Hessian entries, d cost / d v, cost
+    // ---- deterministic reduction of the global sums: (v,v) Hessian entries, d cost / d v, cost.
+    // No CTA barrier: the last warp of a CTA to arrive combines the CTA's warps in a fixed order and
+    // publishes one partial; the last CTA to publish sums all partials in a fixed order.
     if constexpr (C::NRED > 0) {
         double* sred = smem + C::S_RED;
-        __shared__ int is_last;
         const int nblk = a.ctas;
-        __syncthreads();   // (the edge CTA's value buffer may overlap sred)
+        double wv[C::NRED];
 #pragma unroll
         for (int k = 0; k < C::NRED; ++k) {
             double v = red[k];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) sred[warp * C::NRED + k] = v;
+            wv[k] = v;
         }
-        __syncthreads();
-        double* part = a.partials + (inst * nblk) * C::NRED;
-        if (tid < C::NRED) {
-            double v = 0.0;
-            for (int w = 0; w < C::WPC; ++w) v += sred[w * C::NRED + tid];
-            part[(long long)cta * C::NRED + tid] = v;
-            __threadfence();
+        unsigned int flag = 0;
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < C::NRED; ++k) sred[warp * C::NRED + k] = wv[k];
+            __threadfence_block();
+            flag = (atomicAdd(&cta_ticket, 1u) == (unsigned int)(C::WPC - 1));
         }
-        __syncthreads();
-        if (tid == 0) {
-            const unsigned int ticket = atomicAdd(&a.counters[inst], 1u);
-            is_last = (ticket == (unsigned int)(nblk - 1));
-        }
-        __syncthreads();
-        if (is_last) {
-            __threadfence();
-            if (tid < 32) {
+        flag = __shfl_sync(0xffffffffu, flag, 0);
+        if (flag) {
+            __threadfence_block();
+            double* part = a.partials + (inst * nblk) * C::NRED;
+            if (lane < C::NRED) {
+                double v = 0.0;
+                for (int w = 0; w < C::WPC; ++w) v += sred[w * C::NRED + lane];
+                part[(long long)cta * C::NRED + lane] = v;
+                __threadfence();
+            }
+            __syncwarp();
+            unsigned int last = 0;
+            if (lane == 0) last = (atomicAdd(&a.counters[inst], 1u) == (unsigned int)(nblk - 1));
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last) {
+                __threadfence();
+                double acc[C::NRED];
+#pragma unroll
+                for (int k = 0; k < C::NRED; ++k) acc[k] = 0.0;
+                // 16 independent loads per lane in flight (one memory round trip per 512 partials)
+                for (int base = 0; base < nblk; base += 32 * 16) {
+#pragma unroll
+                    for (int k = 0; k < C::NRED; ++k) {
+                        double t[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int b = base + j * 32 + lane;
+                            t[j] = b < nblk ? __ldcg(&part[(long long)b * C::NRED + k]) : 0.0;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) acc[k] += t[j];
+                    }
+                }
 #pragma unroll
                 for (int k = 0; k < C::NRED; ++k) {
-                    double v = 0.0;
-                    for (int b = tid; b < nblk; b += 32) v += __ldcg(&part[(long long)b * C::NRED + k]);
+                    double v = acc[k];
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                    if (tid == 0) {
+                    if (lane == 0) {
                         if (C::WH && k < C::R_G) hvals[a.hvv_pos[k - C::R_H]] = v;
                         else if (C::WG && k < C::R_O) grad[a.nvar - E::NV + (k - C::R_G)] = v;
                         else if (C::WO && a.obj) a.obj[inst] = v;
                     }
                 }
-                if (tid == 0) a.counters[inst] = 0u;
+                if (lane == 0) a.counters[inst] = 0u;
             }
         }
     }
+    CTD_STAMP(6);
 }
+
+// the same body under two register budgets (see Cfg::LIGHT)
+template <class E, int F>
+__global__ void __maxnreg__(CTD_MAXNREG) ctd_eval_kernel_light(const EvalArgs a) { eval_body<E, F>(a); }
+template <class E, int F>
+__global__ void __launch_bounds__(Cfg<E, F>::T) ctd_eval_kernel(const EvalArgs a) { eval_body<E, F>(a); }
 
 }  // namespace ctd

@@ -8,6 +8,8 @@
 //                                    irk_stagewise.jl:468-638; common.jl:285-312
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -530,7 +532,7 @@ EvalArgs Model::base_args() const {
     std::memset(&a, 0, sizeof(a));
     a.params = d_params_;
     a.x_stride = nvar_; a.y_stride = ncon_; a.c_stride = ncon_; a.j_stride = nnzj(); a.h_stride = nnzh(); a.g_stride = nvar_;
-    a.sgrid = uniform_ ? nullptr : d_sgrid_;
+    a.sgrid = d_sgrid_;
     a.N = N_;
     a.nvar = nvar_; a.ncon = ncon_;
     for (int k = 0; k < MAX_NV; ++k) a.jv_base[k] = jv_base_[k];
@@ -543,6 +545,7 @@ EvalArgs Model::base_args() const {
     a.ntask = ntask_;
     for (int t = 0; t < MAX_TASKS; ++t) a.task[t] = task_[t];
     a.fp_map_off = fp_map_off_; a.bc_map_off = bc_map_off_;
+    a.nmap = (int)edge_map_.size();
     return a;
 }
 
@@ -562,7 +565,7 @@ void Model::eval_dev(int flags, const double* x, const double* y, double sigma, 
     a.ctas = (a.tiles + lc.wpc - 1) / lc.wpc + 1;
     // the edge CTA uses the same dynamic shared memory as its value buffer (its reduction scratch at
     // Cfg::S_RED is only touched after the buffer has been scattered)
-    const size_t edge_smem = sizeof(double) * (3 * ((size_t)ne_j_ + ne_h_ + ne_g_) + 2);
+    const size_t edge_smem = sizeof(double) * (EDGE_LAYERS * ((size_t)ne_j_ + ne_h_ + ne_g_) + 2) + sizeof(int) * (edge_map_.size() + 2);
     const size_t smem = std::max(lc.tile_smem, edge_smem);
     auto it = prepared_.find(flags);
     if (it == prepared_.end() || it->second < smem) {
@@ -570,9 +573,29 @@ void Model::eval_dev(int flags, const double* x, const double* y, double sigma, 
         if (e != 0) throw CtdError{e, std::string("cudaFuncSetAttribute failed: ") + cudaGetErrorString((cudaError_t)e)};
         prepared_[flags] = smem;
     }
+#ifdef CTD_TRACE
+    // debug builds only: per-warp timestamps of the launch, dumped as raw int64 to $CTD_TRACE_FILE
+    long long* d_trace = nullptr;
+    const size_t ntrace = (size_t)a.ctas * lc.wpc * 8;
+    const char* trace_file = getenv("CTD_TRACE_FILE");
+    if (trace_file) {
+        CTD_CUDA(cudaMalloc(&d_trace, ntrace * sizeof(long long)));
+        CTD_CUDA(cudaMemsetAsync(d_trace, 0, ntrace * sizeof(long long), stream_));
+        a.trace = d_trace;
+    }
+#endif
     const int e = reg_.launcher.launch(a, flags, batch_, smem, stream_);
     if (e != 0) throw CtdError{e, std::string("kernel launch failed: ") + cudaGetErrorString((cudaError_t)e)};
     ++launches_;
+#ifdef CTD_TRACE
+    if (d_trace) {
+        std::vector<long long> h(ntrace);
+        CTD_CUDA(cudaMemcpyAsync(h.data(), d_trace, ntrace * sizeof(long long), cudaMemcpyDeviceToHost, stream_));
+        CTD_CUDA(cudaStreamSynchronize(stream_));
+        if (FILE* f = fopen(trace_file, "wb")) { fwrite(h.data(), sizeof(long long), ntrace, f); fclose(f); }
+        cudaFree(d_trace);
+    }
+#endif
 }
 
 void Model::eval_host(int flags, const double* x, const double* y, double sigma, double* obj, double* grad, double* c,

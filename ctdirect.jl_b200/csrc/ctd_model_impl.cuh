@@ -37,7 +37,8 @@ struct ElementLauncher {
     static int prepare(int flags, size_t smem) {
         switch (flags) {
 #define CTD_X(F) \
-    case F: return (int)cudaFuncSetAttribute(ctd_eval_kernel<E, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    case F: if constexpr (Cfg<E, F>::LIGHT) return (int)cudaFuncSetAttribute(ctd_eval_kernel_light<E, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            else return (int)cudaFuncSetAttribute(ctd_eval_kernel<E, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             CTD_FOR_EACH_FLAGSET(CTD_X)
 #undef CTD_X
         }
@@ -47,7 +48,8 @@ struct ElementLauncher {
         dim3 grid((unsigned)a.ctas, (unsigned)batch, 1);
         switch (flags) {
 #define CTD_X(F) \
-    case F: ctd_eval_kernel<E, F><<<grid, Cfg<E, F>::T, smem, st>>>(a); break;
+    case F: if constexpr (Cfg<E, F>::LIGHT) ctd_eval_kernel_light<E, F><<<grid, Cfg<E, F>::T, smem, st>>>(a); \
+            else ctd_eval_kernel<E, F><<<grid, Cfg<E, F>::T, smem, st>>>(a); break;
             CTD_FOR_EACH_FLAGSET(CTD_X)
 #undef CTD_X
             default: return (int)cudaErrorInvalidValue;

@@ -37,6 +37,9 @@ class CudaPrinter(C99CodePrinter):
             return f"(1.0/sqrt({self._print(b)}))"
         return super()._print_Pow(expr)
 
+    def _print_rcp(self, expr):
+        return f"(1.0/({self._print(expr.args[0])}))"
+
     def _print_Integer(self, expr):
         return f"{int(expr)}.0" if abs(int(expr)) < 2**53 else super()._print_Integer(expr)
 
@@ -51,9 +54,21 @@ def cc(e):
     return _PR.doprint(sp.sympify(e))
 
 
+class rcp(sp.Function):
+    """1/x as an opaque function, so that CSE shares ONE reciprocal per base between all negative powers
+    of it (an FP64 division costs ~30 instructions on the GPU; x**-3 becomes rcp(x)**3)."""
+    nargs = 1
+
+
+def _share_reciprocals(e):
+    e = sp.sympify(e)
+    return e.replace(lambda q: q.is_Pow and q.exp.is_Integer and q.exp < 0,
+                     lambda q: sp.Pow(rcp(q.base), -q.exp))
+
+
 def cse_block(exprs, tmp_prefix):
     """Return (list of 'const double t = ...;' lines, list of C strings for the outputs)."""
-    exprs = [sp.sympify(e) for e in exprs]
+    exprs = [_share_reciprocals(e) for e in exprs]
     if not exprs:
         return [], []
     repl, red = sp.cse(exprs, symbols=sp.numbered_symbols(tmp_prefix), order="none")
