@@ -309,7 +309,7 @@ def main():
                 "grad": torch.empty((bl, bd.nvar), dtype=torch.float64, device=dev),
                 "obj": torch.empty(bl, dtype=torch.float64, device=dev)}
         norms = torch.empty((2, bl), dtype=torch.float64, device=dev)
-        gathered = torch.empty((world, 2, bl), dtype=torch.float64, device=dev)
+        gathered = torch.empty((world * 2, bl), dtype=torch.float64, device=dev)
         ALL = ctd.CONS | ctd.JAC | ctd.HESS | ctd.GRAD | ctd.OBJ
         bstream = torch.cuda.ExternalStream(bd.cuda_stream, device=dev)
         bsteps = max(3, min(args.steps, 50))

@@ -9,6 +9,7 @@ instance in batched mode).  Sources in the reference tree:
   stagewise_scalar           test/ci/test_discretization_stagewise.jl:1-14
   bolza_freetf               test/problems/bolza.jl:3-18
   vanderpol                  test/problems/vanderpol.jl:3-19
+  estimate_*                 test/problems/autonomous_system.jl:6-90 (no control: NLP_u = 0)
   robot                      NOT in the reference (synthetic, after the COPS robot arm)
 """
 from __future__ import annotations
@@ -180,7 +181,25 @@ robot = OCP(
     synthetic=True,
 )
 
+# parameter estimation without control (NLP_u = 0): test/problems/autonomous_system.jl:6-90
+estimate_initial_condition = OCP(
+    name="estimate_initial_condition", nx=2, nu=0, nv=2, params=[], t0=("const", 0.0), tf=("const", _PI / 2),
+    dynamics=lambda t, x, u, v, p: [-x[1], x[0]],
+    mayer=lambda x0, xf, v, p: (xf[0] - 0) ** 2 + (xf[1] - 1) ** 2,
+    boundary=lambda x0, xf, v, p: [x0[0] - v[0], x0[1] - v[1]],
+    bc_lb=[0.0, 0.0], bc_ub=[0.0, 0.0],
+)
+
+estimate_rotation_rate = OCP(
+    name="estimate_rotation_rate", nx=2, nu=0, nv=1, params=[], t0=("const", 0.0), tf=("const", 1.0),
+    dynamics=lambda t, x, u, v, p: [v[0] * (-x[1]), v[0] * x[0]],
+    mayer=lambda x0, xf, v, p: (xf[0] - 0) ** 2 + (xf[1] - 1) ** 2 + sp.Float(0.01) * v[0] ** 2,
+    boundary=lambda x0, xf, v, p: [x0[0] - 1, x0[1] - 0],
+    bc_lb=[0.0, 0.0], bc_ub=[0.0, 0.0],
+    variable_box=[(0.0, 1, 10.0)],
+)
+
 ALL = {o.name: o for o in (
     goddard, goddard_all, double_integrator_minenergy, double_integrator_mintf, stagewise_scalar,
-    bolza_freetf, vanderpol, robot,
+    bolza_freetf, vanderpol, robot, estimate_initial_condition, estimate_rotation_rate,
 )}

@@ -111,6 +111,8 @@ void* orc_create(const char* problem, const char* scheme, int grid_size, const d
         ORC_P(BolzaFreeTf)
         ORC_P(VanDerPol)
         ORC_P(RobotArm)
+        ORC_P(EstimateInitialCondition)
+        ORC_P(EstimateRotationRate)
 #undef ORC_P
         if (!m) g_err = std::string("unknown problem: ") + problem;
         return m;

@@ -8,7 +8,8 @@
 // Sources: reference test/problems/goddard.jl:7-49,87-158,
 //          test/problems/double_integrator.jl:4-19,40-56,
 //          test/ci/test_discretization_stagewise.jl:1-14,
-//          test/problems/bolza.jl:3-18, test/problems/vanderpol.jl:3-19.
+//          test/problems/bolza.jl:3-18, test/problems/vanderpol.jl:3-19,
+//          test/problems/autonomous_system.jl:6-90.
 // The robot arm is NOT in the reference tree: it is a synthetic
 // problem defined in this repository after the COPS robot-arm model.
 #pragma once
@@ -341,6 +342,70 @@ struct RobotArm {
         m.init_control = {0.0, 0.0, 0.0};
         m.init_variable = {1.0};
         m.default_params = {5.0};
+        return m;
+    }
+};
+
+// ---------------------------------------------------------------------------
+// Parameter-estimation problems WITHOUT control (NLP_u = 0): test/problems/autonomous_system.jl:6-90
+// ---------------------------------------------------------------------------
+struct EstimateInitialCondition {
+    static constexpr const char* name = "estimate_initial_condition";
+    static constexpr int nx = 2, nu = 0, nv = 2, np = 0, nb = 2, npar = 0;
+    static constexpr bool free_t0 = false, free_tf = false, has_lagrange = false, has_mayer = true,
+                          is_max = false;
+    template <class T> static T t0(const T*, const double*) { return T(0.0); }
+    template <class T> static T tf(const T*, const double*) { return T(3.14159265358979323846 / 2); }
+    template <class T>
+    static void dynamics(T* r, const T&, const T* x, const T*, const T*, const double*) {
+        r[0] = -x[1];
+        r[1] = x[0];
+    }
+    template <class T> static T lagrange(const T&, const T*, const T*, const T*, const double*) { return T(0.0); }
+    template <class T> static T mayer(const T*, const T* xf, const T*, const double*) {
+        return sq(xf[0] - 0.0) + sq(xf[1] - 1.0);
+    }
+    template <class T> static void path(T*, const T&, const T*, const T*, const T*, const double*) {}
+    template <class T>
+    static void boundary(T* r, const T* x0, const T*, const T* v, const double*) {
+        r[0] = x0[0] - v[0];
+        r[1] = x0[1] - v[1];
+    }
+    static ProblemMeta meta() {
+        ProblemMeta m;
+        m.bc_lb = {0, 0};
+        m.bc_ub = {0, 0};
+        return m;
+    }
+};
+
+struct EstimateRotationRate {
+    static constexpr const char* name = "estimate_rotation_rate";
+    static constexpr int nx = 2, nu = 0, nv = 1, np = 0, nb = 2, npar = 0;
+    static constexpr bool free_t0 = false, free_tf = false, has_lagrange = false, has_mayer = true,
+                          is_max = false;
+    template <class T> static T t0(const T*, const double*) { return T(0.0); }
+    template <class T> static T tf(const T*, const double*) { return T(1.0); }
+    template <class T>
+    static void dynamics(T* r, const T&, const T* x, const T*, const T* v, const double*) {
+        r[0] = v[0] * (-x[1]);
+        r[1] = v[0] * x[0];
+    }
+    template <class T> static T lagrange(const T&, const T*, const T*, const T*, const double*) { return T(0.0); }
+    template <class T> static T mayer(const T*, const T* xf, const T* v, const double*) {
+        return sq(xf[0] - 0.0) + sq(xf[1] - 1.0) + 0.01 * sq(v[0]);
+    }
+    template <class T> static void path(T*, const T&, const T*, const T*, const T*, const double*) {}
+    template <class T>
+    static void boundary(T* r, const T* x0, const T*, const T*, const double*) {
+        r[0] = x0[0] - 1.0;
+        r[1] = x0[1] - 0.0;
+    }
+    static ProblemMeta meta() {
+        ProblemMeta m;
+        m.variable_box = {{0.0, 1, 10.0}};
+        m.bc_lb = {0, 0};
+        m.bc_ub = {0, 0};
         return m;
     }
 };

@@ -1,0 +1,64 @@
+"""Host-side logic of the multi-GPU path on CPU: instance sharding and the (objective, violation)
+all-gather over gloo with world_size 2 (the GPU run uses the same code over NCCL)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+
+def test_shard_range_partitions():
+    from ctdirect_b200.batch import shard_range
+    for n, w in ((4096, 8), (4096, 1), (10, 4), (3, 8), (0, 2)):
+        parts = [shard_range(n, w, r) for r in range(w)]
+        assert parts[0][0] == 0 and parts[-1][1] == n
+        assert all(parts[r][1] == parts[r + 1][0] for r in range(w - 1))
+        sizes = [hi - lo for lo, hi in parts]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+def _worker(rank, world, port, n, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ctdirect_b200.batch import gather_norms, shard_range
+        lo, hi = shard_range(n, world, rank)
+        obj = torch.arange(lo, hi, dtype=torch.float64) * 1.5
+        viol = torch.arange(lo, hi, dtype=torch.float64) * -2.0
+        g_obj, g_viol = gather_norms(obj, viol, n)
+        q.put((rank, g_obj.numpy().copy(), g_viol.numpy().copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [7, 8])
+def test_gather_norms_gloo_world2(n):
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=60) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, g_obj, g_viol in res:
+        np.testing.assert_array_equal(g_obj, np.arange(n) * 1.5)
+        np.testing.assert_array_equal(g_viol, np.arange(n) * -2.0)
+
+
+def test_gather_norms_single_process():
+    import torch
+    from ctdirect_b200.batch import gather_norms
+    o, v = gather_norms(torch.tensor([1.0, 2.0], dtype=torch.float64), torch.tensor([0.5, 0.0], dtype=torch.float64), 2)
+    assert o.tolist() == [1.0, 2.0] and v.tolist() == [0.5, 0.0]

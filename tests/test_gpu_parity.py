@@ -57,3 +57,137 @@ def test_all_models_small_grids(ctd, oracle_mod, N):
         assert_close(r["hess"], h_ref, scale=sh * 1e-3, rtol=RTOL, what=tag + " fused hess")
         assert_close(r["grad"], g_ref, scale=sg * 1e-3, rtol=RTOL, what=tag + " fused grad")
         assert_close(r["obj"], f_ref, scale=1.0, rtol=RTOL, what=tag + " fused obj")
+
+
+def _compare_all(ctd, o, d, x, y, sigma, tag, rtol=RTOL):
+    nlp = d.nlp_model()
+    g_ref, j_ref, h_ref = o.derivs(x, y, sigma)
+    c_ref, f_ref = o.cons(x), o.obj(x)
+    sx = max(1.0, float(np.abs(x).max()))
+    r = nlp.eval_all(x, y, obj_weight=sigma)
+    assert_close(r["cons"], c_ref, scale=sx, rtol=rtol, what=tag + " cons")
+    assert_close(r["jac"], j_ref, scale=1e-3 * max(1.0, float(np.abs(j_ref).max())), rtol=rtol, what=tag + " jac")
+    assert_close(r["hess"], h_ref, scale=1e-3 * max(1e-300, float(np.abs(h_ref).max())), rtol=rtol, what=tag + " hess")
+    assert_close(r["grad"], g_ref, scale=1e-3 * max(1.0, float(np.abs(g_ref).max())), rtol=rtol, what=tag + " grad")
+    assert_close(r["obj"], f_ref, scale=1.0, rtol=rtol, what=tag + " obj")
+    return r
+
+
+@pytest.mark.parametrize("problem,scheme,N", [
+    ("double_integrator_minenergy", "trapeze", 100),            # BASELINE config 1
+    ("goddard", "midpoint", 100_000),                           # config 2
+    ("goddard", "gauss_legendre_3_constant_control", 20_000),   # config 3 (constant control)
+    ("goddard", "gauss_legendre_3", 20_000),                    # config 3 (stagewise = :gauss_legendre_3 today)
+    ("robot", "trapeze", 100_000),                              # config 4 (synthetic robot arm)
+])
+def test_baseline_configs_full_size(ctd, oracle_mod, problem, scheme, N):
+    for mode in ("reference", "corrected"):
+        o = oracle_mod.OracleModel(problem, scheme, N, pattern_mode=mode)
+        d = ctd.DOCP(problem, N, scheme, pattern_mode=mode)
+        x, y = synthetic_point(o)
+        r = _compare_all(ctd, o, d, x, y, 1.0, f"{problem}/{scheme}/{mode}/N={N}")
+        # size-independent properties: the Hessian is linear in (y, obj_weight); evaluation is deterministic
+        nlp = d.nlp_model()
+        h1 = nlp.hess_coord(x, y, obj_weight=0.25)
+        h2 = nlp.hess_coord(x, 2.0 * y, obj_weight=0.5)
+        assert_close(h2, 2.0 * h1, scale=1e-3 * max(1e-300, float(np.abs(h1).max())), rtol=1e-13, what="hessian linearity")
+        r2 = nlp.eval_all(x, y, obj_weight=1.0)
+        for k in ("cons", "jac", "hess", "grad", "obj"):
+            assert np.array_equal(r[k], r2[k]), f"{k} not reproducible bit for bit"
+
+
+def test_jacobian_directional_derivative_full_size(ctd):
+    """J(x) d against central differences of c at grid size 1e5 (independent of the oracle)."""
+    d = ctd.DOCP("goddard", 100_000, "midpoint")
+    nlp = d.nlp_model()
+    rng = np.random.default_rng(5)
+    x = nlp.meta.x0 * (1 + 1e-3 * rng.uniform(-1, 1, d.nvar))
+    dirv = rng.standard_normal(d.nvar)
+    rows, cols = nlp.jac_structure()
+    jd = np.zeros(d.ncon)
+    np.add.at(jd, rows - 1, nlp.jac_coord(x) * dirv[cols - 1])
+    eps = 1e-7
+    fd = (nlp.cons(x + eps * dirv) - nlp.cons(x - eps * dirv)) / (2 * eps)
+    assert np.abs(jd - fd).max() <= 1e-6 * max(1.0, np.abs(jd).max())
+
+
+def test_batched_instances_match_single_instance_oracles(ctd, oracle_mod):
+    """BASELINE config 5 in miniature and at full size: per-instance parameters (Tmax) and points."""
+    rng = np.random.default_rng(11)
+    for B, N, check in ((5, 64, range(5)), (4096, 1000, range(0, 4096, 517))):
+        par = np.tile(np.array([310.0, 500.0, 2.0, 3.5]), (B, 1))
+        par[:, 3] = rng.uniform(1.0, 3.5, B)      # continuation range, test/ci/test_initial_guess.jl:242
+        d = ctd.DOCP("goddard", N, "midpoint", params=par, batch=B)
+        x, y = synthetic_point(d, seed=77, batch=B)
+        r = d.evaluate(ctd.CONS | ctd.JAC | ctd.HESS | ctd.GRAD | ctd.OBJ, x, y, 1.0)
+        assert r["jac"].shape == (B, d.nnzj) and r["obj"].shape == (B,)
+        obj, viol = d.norms(x)
+        lvar, uvar, lcon, ucon = d.bounds()
+        for b in check:
+            o = oracle_mod.OracleModel("goddard", "midpoint", N, params=par[b])
+            g, j, h = o.derivs(x[b], y[b], 1.0)
+            c = o.cons(x[b])
+            tag = f"instance {b}/{B}"
+            assert_close(r["cons"][b], c, scale=max(1.0, np.abs(x[b]).max()), what=tag + " cons")
+            assert_close(r["jac"][b], j, scale=1e-3 * np.abs(j).max(), what=tag + " jac")
+            assert_close(r["hess"][b], h, scale=1e-3 * np.abs(h).max(), what=tag + " hess")
+            assert_close(r["grad"][b], g, scale=1e-3, what=tag + " grad")
+            assert_close(r["obj"][b], o.obj(x[b]), scale=1.0, what=tag + " obj")
+            assert_close(obj[b], o.obj(x[b]), scale=1.0, what=tag + " norms obj")
+            v_ref = max(0.0, float(np.max(np.maximum(lcon - c, c - ucon))))
+            assert_close(viol[b], v_ref, scale=max(1.0, np.abs(x[b]).max()), what=tag + " violation")
+        # new scenarios on the same handle
+        par2 = par.copy()
+        par2[:, 3] = 2.0
+        d.set_params(par2)
+        o = oracle_mod.OracleModel("goddard", "midpoint", N, params=par2[0])
+        assert_close(d.evaluate(ctd.CONS, x)["cons"][0], o.cons(x[0]), scale=max(1.0, np.abs(x[0]).max()), what="set_params")
+
+
+def test_device_tensors_and_host_arrays_agree(ctd):
+    import torch
+    d = ctd.DOCP("goddard_all", 500, "trapeze")
+    x, y = synthetic_point(d, seed=3)
+    rh = d.evaluate(ctd.CONS | ctd.JAC | ctd.HESS | ctd.GRAD | ctd.OBJ, x, y, 0.3)
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    out = {"jac": torch.empty(d.nnzj, dtype=torch.float64, device="cuda")}
+    rd = d.evaluate(ctd.CONS | ctd.JAC | ctd.HESS | ctd.GRAD | ctd.OBJ, xd, yd, 0.3, out=out)
+    d.synchronize()
+    assert rd["jac"].data_ptr() == out["jac"].data_ptr()          # caller-owned buffers are filled in place
+    for k in rh:
+        assert np.array_equal(rh[k], rd[k].cpu().numpy()), k
+    with pytest.raises(TypeError):
+        d.evaluate(ctd.HESS, xd, y)                                # mixed host / device arguments
+    with pytest.raises(ValueError):
+        d.evaluate(ctd.CONS, x[:-1])
+
+
+def test_nonuniform_time_grid(ctd, oracle_mod):
+    rng = np.random.default_rng(2)
+    grid = np.sort(np.concatenate(([0.0, 1.0], rng.uniform(0, 1, 200))))
+    for problem, scheme in (("goddard", "midpoint"), ("bolza_freetf", "gauss_legendre_2"), ("vanderpol", "trapeze")):
+        o = oracle_mod.OracleModel(problem, scheme, time_grid=grid)
+        d = ctd.DOCP(problem, scheme=scheme, time_grid=grid)
+        x, y = synthetic_point(o, seed=9)
+        _compare_all(ctd, o, d, x, y, 0.9, f"{problem}/{scheme}/nonuniform")
+
+
+def test_stagewise_known_answer_on_gpu(ctd):
+    """test/ci/test_discretization_stagewise.jl:93-99 through the CUDA path: c == bounds, objective 4/3."""
+    grid = np.array([0.0, 0.2, 0.6, 1.0])
+    for scheme, stage, block in (("gauss_legendre_2", 2, 5), ("gauss_legendre_3", 3, 7)):
+        d = ctd.DOCP("stagewise_scalar", scheme=scheme, time_grid=grid)
+        nodes = {2: [0.5 - np.sqrt(3) / 6, 0.5 + np.sqrt(3) / 6], 3: [0.5 - 0.1 * np.sqrt(15), 0.5, 0.5 + 0.1 * np.sqrt(15)]}[stage]
+        xu = np.zeros(d.nvar)
+        for i in range(4):
+            xu[i * block] = grid[i] ** 2
+        for i in range(3):
+            h = grid[i + 1] - grid[i]
+            for j in range(stage):
+                xu[i * block + 1 + j] = xu[i * block + 1 + stage + j] = 2 * (grid[i] + nodes[j] * h)
+        nlp = d.nlp_model()
+        _, _, lcon, ucon = d.bounds()
+        c = nlp.cons(xu)
+        np.testing.assert_allclose(c, lcon, atol=1e-12)
+        np.testing.assert_allclose(c, ucon, atol=1e-12)
+        assert abs(nlp.obj(xu) - 4.0 / 3.0) <= 1e-12
