@@ -146,6 +146,8 @@ class DOCP:
 
     # ---- evaluation --------------------------------------------------------------------------------
     def _shape(self, n):
+        if n == 1:
+            return (self.batch,)          # one objective value per instance
         return (n,) if self.batch == 1 else (self.batch, n)
 
     def _empty_like(self, x, n):

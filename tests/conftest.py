@@ -49,6 +49,8 @@ def assert_close(a, b, scale=None, rtol=1e-12, what=""):
     numerically zero or the result of cancellation)."""
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
+    if a.size == b.size == 1:
+        a, b = a.reshape(1), b.reshape(1)
     assert a.shape == b.shape, (what, a.shape, b.shape)
     if a.size == 0:
         return
