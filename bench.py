@@ -172,6 +172,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--streams", type=int, default=3, help="independent evaluation streams in flight")
     ap.add_argument("--no-batched", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -195,6 +196,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -210,13 +213,20 @@ def main():
         return ms
 
     FLAGS = ctd.CONS | ctd.JAC | ctd.HESS
-    docp = ctd.DOCP(PROBLEM, GRID, SCHEME, device=local_rank)
+    # Evaluations are independent of each other (MPC scenarios, trial points): they are issued round-robin
+    # on NSTREAMS handles, each with its own CUDA stream, so that the launch latency and the tail of one
+    # evaluation overlap the body of the next.  The single-stream figure is reported beside it.
+    NSTREAMS = max(1, args.streams)
+    docps = [ctd.DOCP(PROBLEM, GRID, SCHEME, device=local_rank) for _ in range(NSTREAMS)]
+    docp = docps[0]
     nlp = docp.nlp_model()
     nvar, ncon, nnzj, nnzh = docp.nvar, docp.ncon, docp.nnzj, docp.nnzh
     alg_bytes = 8 * (nvar + 2 * ncon + nnzj + nnzh)
-    stream = torch.cuda.ExternalStream(docp.cuda_stream, device=dev)
+    streams = [torch.cuda.ExternalStream(d.cuda_stream, device=dev) for d in docps]
+    stream = streams[0]
     # rotating buffer sets so that consecutive evaluations do not find their lines in the 126 MB L2
     nsets = max(3, int(np.ceil(1.5 * 126e6 / alg_bytes)))
+    nsets = ((nsets + NSTREAMS - 1) // NSTREAMS) * NSTREAMS
     xh, yh = synthetic_point(nlp.meta.x0, ncon, SEED + rank)
     sets = []
     for s in range(nsets):
@@ -228,32 +238,41 @@ def main():
                     "hess": torch.empty(nnzh, dtype=torch.float64, device=dev)},
         })
     torch.cuda.synchronize()
+    # buffer set k is always evaluated by handle k % NSTREAMS
+    calls = [docps[k % NSTREAMS].bind(FLAGS, s["x"], s["y"], 1.0, out=s["out"])[0] for k, s in enumerate(sets)]
+    calls1 = [docp.bind(FLAGS, s["x"], s["y"], 1.0, out=s["out"])[0] for s in sets]
 
-    calls = [docp.bind(FLAGS, s["x"], s["y"], 1.0, out=s["out"])[0] for s in sets]
-
-    def step(i):
-        calls[i % nsets]()
+    def timed(call_list, used_streams, steps, warmup):
+        for i in range(warmup):
+            call_list[i % nsets]()
+        barrier()
+        l0 = sum(d.launch_count for d in docps)
+        ev0 = [torch.cuda.Event(enable_timing=True) for _ in used_streams]
+        ev1 = [torch.cuda.Event(enable_timing=True) for _ in used_streams]
+        for e, st in zip(ev0, used_streams):
+            e.record(st)
+        for i in range(steps):
+            call_list[i % nsets]()
+        for e, st in zip(ev1, used_streams):
+            e.record(st)
+        barrier()
+        # every stream starts at the barrier; the region ends when the last stream finishes
+        ms = max(a.elapsed_time(b) for a, b in zip(ev0, ev1))
+        return ms, sum(d.launch_count for d in docps) - l0
 
     sampler = ClockSampler(local_rank)
-    with torch.cuda.stream(stream):
-        for i in range(args.warmup):
-            step(i)
-        barrier()
-        l0 = docp.launch_count
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sampler.start()
-        e0.record(stream)
-        for i in range(args.steps):
-            step(i)
-        e1.record(stream)
-        barrier()
-        launches = docp.launch_count - l0
-        ms_local = e0.elapsed_time(e1)
+    # (1) single stream: the kernel timed back to back on its own -> roofline of the kernel
+    ms1_local, _ = timed(calls1, [stream], args.steps, args.warmup)
+    # (2) NSTREAMS handles in flight -> whole-job throughput (`value`)
+    sampler.start()
+    ms_local, launches = timed(calls, streams, args.steps, args.warmup)
     ms = max_over_ranks(ms_local)
+    ms1 = max_over_ranks(ms1_local)
     value = world * args.steps / (ms * 1e-3)
     peak, peak_src = measured_peak()
-    launch_s = ms_local * 1e-3 / args.steps
+    launch_s = ms1_local * 1e-3 / args.steps
     achieved = alg_bytes / launch_s / 1e9
+    achieved_ov = alg_bytes / (ms_local * 1e-3 / args.steps) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
@@ -262,8 +281,13 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "ctd_eval_kernel<E_goddard__midpoint, CONS|JAC|HESS>",
-                "algorithmic_bytes_per_launch": alg_bytes, "launch_us": launch_s * 1e6, "peak_source": peak_src}
+                "traffic": traffic, "kernel": "ctd_eval_kernel_light<E_goddard__midpoint, CONS|JAC|HESS>",
+                "algorithmic_bytes_per_launch": alg_bytes, "launch_us": launch_s * 1e6, "peak_source": peak_src,
+                "how": "one stream, launches back to back, CUDA events over the timed region / steps",
+                "overlapped": {"streams": NSTREAMS, "achieved": achieved_ov, "frac": achieved_ov / peak,
+                               "us_per_eval": ms_local * 1e3 / args.steps,
+                               "how": "same kernel, evaluations issued round-robin on independent streams"}}
+    single_stream = {"value": world * args.steps / (ms1 * 1e-3), "unit": "evals/s", "ms_per_step": ms1 / args.steps}
 
     # ---- e2e: host buffers through the host-pointer C ABI call (H2D + kernel + D2H every step)
     e2e = None
@@ -364,7 +388,10 @@ def main():
             "config": {"workload": f"{PROBLEM}/{SCHEME}/grid_size={GRID}: fused cons+jac+hess (one launch), :manual "
                                    f"pattern, nvar={nvar} ncon={ncon} nnzj={nnzj} nnzh={nnzh}; one instance per GPU",
                        "l2": f"rotating {nsets} input/output buffer sets ({nsets * alg_bytes / 1e6:.0f} MB > 126 MB L2)",
-                       "timing": "CUDA events on the handle's stream, max over ranks"},
+                       "streams": f"{NSTREAMS} independent evaluations in flight per GPU (one handle + CUDA stream each); "
+                                  "single_stream / roofline give the one-stream figures",
+                       "timing": "CUDA events on the handles' streams, max over streams and ranks"},
+            "single_stream": single_stream,
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "batched": batched,
         }
