@@ -318,8 +318,8 @@ __device__ __forceinline__ void load_step(const double* __restrict__ x, long lon
 }
 
 // Edge CTA: the elements that touch column blocks 1, N, N+1 and the boundary / final-path rows.  The
-// work is cut into jobs -- (step element, phase A), (step element, phase B), final-path element,
-// boundary+Mayer element -- each run by lane 0 of a warp.  Jobs whose values can land on the same entry
+// work is cut into jobs -- (step elements, phase A), (step elements, phase B), final-path element,
+// boundary+Mayer element -- one warp each; the step elements of one phase run in the lanes of one warp.  Jobs whose values can land on the same entry
 // write to different layers of the edge buffer, which are summed in a fixed order when the buffer is
 // scattered (deterministic whatever the warp interleaving, and no atomics).
 constexpr int EDGE_LAYERS = 4;   // step tasks 0/2, step task 1, final path, boundary
@@ -346,14 +346,13 @@ __device__ __forceinline__ void edge_step_job(const EvalArgs& a, const EdgeTask&
     if constexpr (JO) { if (tk.own) red[C::R_O] += E::cost_step(z, Tm, p); }
 }
 
-template <class E, int F>
+template <class E, int F, int NW>
 __device__ void edge_cta(const EvalArgs& a, const double* __restrict__ x, const double* __restrict__ y,
                          const double* __restrict__ p, double* c, double* jvals, double* hvals, double* grad,
                          double* buf, double* red) {
     using C = Cfg<E, F>;
     const int tid = threadIdx.x;
-    constexpr int T = C::T;
-    constexpr int NW = C::WPC;
+    constexpr int T = NW * 32;
     const int ne = a.ne_j + a.ne_h + a.ne_g;
     // the position maps are staged in shared memory first (one coalesced pass): the sinks look up one
     // map entry per value, and those lookups must not be dependent global loads
@@ -361,24 +360,25 @@ __device__ void edge_cta(const EvalArgs& a, const double* __restrict__ x, const 
     for (int k = tid; k < a.nmap; k += T) smap[k] = __ldg(a.edge_map + k);
     for (int k = tid; k < EDGE_LAYERS * ne; k += T) buf[k] = 0.0;
     __syncthreads();
-    if ((tid & 31) == 0) {
+    {
+        // warp roles: the step elements of all edge tasks run side by side in the lanes of one warp
+        // (phase A on one warp, phase B on another when both are requested); the final-path and the
+        // boundary element take lane 0 of the next warps (round robin when the CTA has fewer warps).
         constexpr bool TWO = C::PHASE_A && C::PHASE_B;
-        constexpr int PER_TASK = TWO ? 2 : 1;
-        const int nstep = a.ntask * PER_TASK;
-        const int njobs = nstep + 2;
-        for (int job = tid >> 5; job < njobs; job += NW) {
-            if (job < nstep) {
-                // step elements: stepStateConstraints! / stepPathConstraints! of steps 1, N-1, N
-                const int t = job / PER_TASK, part = job % PER_TASK;
-                const EdgeTask tk = a.task[t];
-                double* layer = buf + (t & 1) * ne;
-                if constexpr (TWO) {
-                    if (part == 0) edge_step_job<E, F, true, false>(a, tk, x, y, p, c, layer, smap, red);
-                    else edge_step_job<E, F, false, true>(a, tk, x, y, p, c, layer, smap, red);
-                } else {
-                    edge_step_job<E, F, C::PHASE_A, C::PHASE_B>(a, tk, x, y, p, c, layer, smap, red);
-                }
-            } else if (job == nstep) {
+        constexpr int W_A = 0, W_B = TWO ? (1 % NW) : 0, W_FP = (TWO ? 2 : 1) % NW, W_BC = (TWO ? 3 : 2) % NW;
+        const int lane_ = tid & 31, warp_ = tid >> 5;
+        if (lane_ < a.ntask) {
+            const EdgeTask tk = a.task[lane_];
+            double* layer = buf + (lane_ & 1) * ne;
+            if constexpr (TWO) {
+                if (warp_ == W_A) edge_step_job<E, F, true, false>(a, tk, x, y, p, c, layer, smap, red);
+                if (warp_ == W_B) edge_step_job<E, F, false, true>(a, tk, x, y, p, c, layer, smap, red);
+            } else {
+                if (warp_ == W_A) edge_step_job<E, F, C::PHASE_A, C::PHASE_B>(a, tk, x, y, p, c, layer, smap, red);
+            }
+        }
+        if (lane_ == 0) {
+            if (warp_ == W_FP) {
                 // final path constraints g(t_f, x_f, u_f, v)  (DOCP_functions.jl:100)
                 if constexpr (E::NP > 0 && (C::WC || C::WJ || C::WH)) {
                     double z[E::FP_NLOC], lam[E::NP];
@@ -405,7 +405,8 @@ __device__ void edge_cta(const EvalArgs& a, const double* __restrict__ x, const 
                     s.red = red;
                     E::template fpath<C::WC, C::WJ, C::WH>(z, Tm, p, lam, s);
                 }
-            } else {
+            }
+            if (warp_ == W_BC) {
                 // boundary constraints + Mayer cost  (DOCP_functions.jl:103-111, 35-39)
                 double z[E::BC_NLOC], lam[E::NB > 0 ? E::NB : 1];
                 const long long N = a.N;
@@ -534,6 +535,82 @@ __device__ __forceinline__ void tile_phase(const EvalArgs& a, double* __restrict
 #endif
 }
 
+// Deterministic reduction of the global sums ((v,v) Hessian entries, d cost / d v, cost) over the grid.
+// No CTA barrier: the last warp of a CTA to arrive combines the CTA's NW warps in a fixed order and
+// publishes one partial; the last CTA to publish sums all partials in a fixed order.
+template <class E, int F, int NW>
+__device__ __forceinline__ void publish_reduction(const EvalArgs& a, const double* red, double* sred,
+                                                  unsigned int* cta_ticket_p, long long inst, int cta, int lane,
+                                                  int warp, double* hvals, double* grad) {
+    using C = Cfg<E, F>;
+    if constexpr (C::NRED > 0) {
+        unsigned int& cta_ticket = *cta_ticket_p;
+        const int nblk = a.ctas;
+        double wv[C::NRED];
+#pragma unroll
+        for (int k = 0; k < C::NRED; ++k) {
+            double v = red[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            wv[k] = v;
+        }
+        unsigned int flag = 0;
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < C::NRED; ++k) sred[warp * C::NRED + k] = wv[k];
+            __threadfence_block();
+            flag = (atomicAdd(&cta_ticket, 1u) == (unsigned int)(NW - 1));
+        }
+        flag = __shfl_sync(0xffffffffu, flag, 0);
+        if (flag) {
+            __threadfence_block();
+            double* part = a.partials + (inst * nblk) * C::NRED;
+            if (lane < C::NRED) {
+                double v = 0.0;
+                for (int w = 0; w < NW; ++w) v += sred[w * C::NRED + lane];
+                part[(long long)cta * C::NRED + lane] = v;
+                __threadfence();
+            }
+            __syncwarp();
+            unsigned int last = 0;
+            if (lane == 0) last = (atomicAdd(&a.counters[inst], 1u) == (unsigned int)(nblk - 1));
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last) {
+                __threadfence();
+                double acc[C::NRED];
+#pragma unroll
+                for (int k = 0; k < C::NRED; ++k) acc[k] = 0.0;
+                // 16 independent loads per lane in flight (one memory round trip per 512 partials)
+                for (int base = 0; base < nblk; base += 32 * 16) {
+#pragma unroll
+                    for (int k = 0; k < C::NRED; ++k) {
+                        double t[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int b = base + j * 32 + lane;
+                            t[j] = b < nblk ? __ldcg(&part[(long long)b * C::NRED + k]) : 0.0;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) acc[k] += t[j];
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < C::NRED; ++k) {
+                    double v = acc[k];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (lane == 0) {
+                        if (C::WH && k < C::R_G) hvals[a.hvv_pos[k - C::R_H]] = v;
+                        else if (C::WG && k < C::R_O) grad[a.nvar - E::NV + (k - C::R_G)] = v;
+                        else if (C::WO && a.obj) a.obj[inst] = v;
+                    }
+                }
+                if (lane == 0) a.counters[inst] = 0u;
+            }
+        }
+    }
+}
+
 template <class E, int F>
 __device__ __forceinline__ void eval_body(const EvalArgs& a) {
     using C = Cfg<E, F>;
@@ -563,7 +640,7 @@ __device__ __forceinline__ void eval_body(const EvalArgs& a) {
 
     CTD_STAMP(0);
     if (cta == 0) {
-        edge_cta<E, F>(a, x, y, p, c, jvals, hvals, grad, smem, red);
+        edge_cta<E, F, C::WPC>(a, x, y, p, c, jvals, hvals, grad, smem, red);
         CTD_STAMP(4);
     } else {
         const long long tile = (long long)(cta - 1) * C::WPC + warp;
@@ -608,76 +685,219 @@ __device__ __forceinline__ void eval_body(const EvalArgs& a) {
         CTD_STAMP(5);
     }
 
-    // ---- deterministic reduction of the global sums: (v,v) Hessian entries, d cost / d v, cost.
-    // No CTA barrier: the last warp of a CTA to arrive combines the CTA's warps in a fixed order and
-    // publishes one partial; the last CTA to publish sums all partials in a fixed order.
+    publish_reduction<E, F, C::WPC>(a, red, smem + C::S_RED, &cta_ticket, inst, cta, lane, warp, hvals, grad);
+    CTD_STAMP(6);
+}
+
+// =============================================================================================
+// "Parts" kernel for wide elements on small grids (e.g. 3-stage IRK at N = 2e4: only 645 tiles, four
+// warps per SM if one warp did a whole tile).  A CTA of P warps owns ONE tile; every warp evaluates the
+// same 31+1 steps but keeps only its share of the outputs (the generated straight-line code is
+// instantiated once per part; the unused values and everything that only feeds them are removed by
+// dead-code elimination).  All outputs of the tile are staged together; after a CTA barrier warp 0
+// hands the ranges to the copy engine.
+// =============================================================================================
+#ifndef CTD_PARTS
+#define CTD_PARTS 2
+#endif
+
+template <class E, int F>
+struct PCfg {
+    using C = Cfg<E, F>;
+    static constexpr int P = CTD_PARTS;
+    static constexpr int T = 32 * P;
+    static constexpr int PER_STEP = (C::WC ? E::CB : 0) + (C::WJ ? E::J_BLOCK + C::NJV : 0) + (C::WH ? E::H_BLOCK : 0) +
+                                    (C::WG ? E::BLK : 0);
+    static constexpr int FIT = PER_STEP > 0 ? (C::SMEM_MAX - 2048) / (PER_STEP * 8) - 1 : 31;
+    static constexpr int OWN = (31 < FIT) ? 31 : FIT;
+    static_assert(OWN >= 1, "element too wide for one SM's shared memory");
+    static constexpr int even(int n) { return (n + 3) & ~1; }
+    static constexpr int S_C = 0;
+    static constexpr int S_J = S_C + (C::WC ? even((OWN + 1) * E::CB) : 0);
+    static constexpr int S_JV = S_J + (C::WJ ? even((OWN + 1) * E::J_BLOCK) : 0);
+    static constexpr int JV_ONE = even((OWN + 1) * E::JV_STRIDE);
+    static constexpr int S_H = S_JV + (C::WJ ? C::NV * JV_ONE : 0);
+    static constexpr int S_G = S_H + (C::WH ? even((OWN + 1) * E::H_BLOCK) : 0);
+    static constexpr int S_RED = S_G + (C::WG ? even((OWN + 1) * E::BLK) : 0);
+    static constexpr int S_END = S_RED + P * (C::NRED > 0 ? C::NRED : 1) + 2;
+    static constexpr size_t TILE_SMEM = (size_t)S_END * sizeof(double);
+    // every output of the element gets a running index; part = index * P / TOT
+    static constexpr int O_C = 0;
+    static constexpr int O_JO = O_C + (C::WC ? E::CB : 0);
+    static constexpr int O_JN = O_JO + (C::WJ ? E::NJ_OWN : 0);
+    static constexpr int O_JV = O_JN + (C::WJ ? E::NJ_NEXT : 0);
+    static constexpr int O_HO = O_JV + (C::WJ ? E::NJ_V : 0);
+    static constexpr int O_HN = O_HO + (C::WH ? E::NH_OWN : 0);
+    static constexpr int O_HV = O_HN + (C::WH ? E::NH_NEXT : 0);
+    static constexpr int O_GO = O_HV + (C::WH ? C::NVV : 0);
+    static constexpr int O_GN = O_GO + (C::WG ? E::NG_OWN : 0);
+    static constexpr int O_GV = O_GN + (C::WG ? E::NG_NEXT : 0);
+    static constexpr int TOT = O_GV + (C::WG ? E::NG_V : 0);
+    static constexpr int part_of(int g) { return TOT > 0 ? (int)((long long)g * P / TOT) : 0; }
+};
+
+template <class E, int F, int PART>
+struct PartSink {
+    using C = Cfg<E, F>;
+    using PC = PCfg<E, F>;
+    double *c_, *jo_, *jn_, *ho_, *go_;
+    double* jv_[E::NV > 0 ? E::NV : 1];
+    bool owner;
+    double hn_[E::NH_NEXT > 0 ? E::NH_NEXT : 1];
+    double gn_[E::NG_NEXT > 0 ? E::NG_NEXT : 1];
+    double* red;
+    static constexpr bool mine(int g) { return PC::part_of(g) == PART; }
+    template <int R> __device__ __forceinline__ void c(double v) { if constexpr (C::WC && mine(PC::O_C + R)) c_[R] = v; }
+    template <int N> __device__ __forceinline__ void jo(double v) { if constexpr (C::WJ && mine(PC::O_JO + N)) jo_[E::J_OWN(N, 2)] = v; }
+    template <int N> __device__ __forceinline__ void jn(double v) { if constexpr (C::WJ && mine(PC::O_JN + N)) jn_[E::J_NEXT(N, 2)] = v; }
+    template <int N> __device__ __forceinline__ void jv(double v) {
+        if constexpr (C::WJ && mine(PC::O_JV + N)) jv_[E::J_V(N, 1)][E::J_V(N, 2)] = v;
+    }
+    template <int N> __device__ __forceinline__ void ho(double v) { if constexpr (C::WH && mine(PC::O_HO + N)) ho_[E::H_OWN(N, 2)] = v; }
+    template <int N> __device__ __forceinline__ void hn(double v) { if constexpr (C::WH && mine(PC::O_HN + N)) hn_[N] = v; }
+    template <int K> __device__ __forceinline__ void hv(double v) {
+        if constexpr (C::WH && mine(PC::O_HV + K)) red[C::R_H + K] += owner ? v : 0.0;
+    }
+    template <int N> __device__ __forceinline__ void go(double v) { if constexpr (C::WG && mine(PC::O_GO + N)) go_[E::G_OWN(N, 2)] = v; }
+    template <int N> __device__ __forceinline__ void gn(double v) { if constexpr (C::WG && mine(PC::O_GN + N)) gn_[N] = v; }
+    template <int N> __device__ __forceinline__ void gv(double v) {
+        if constexpr (C::WG && mine(PC::O_GV + N)) red[C::R_G + E::G_V(N, 2)] += owner ? v : 0.0;
+    }
+};
+
+template <class E, int F, int PART>
+__device__ __forceinline__ void run_part(const EvalArgs& a, const double* z, const double* lam, const TimeArgs<E::NV>& Tm,
+                                         const double* __restrict__ p, double* red, bool active, bool owner, int ob, int nb,
+                                         double* sC, double* sJ, double* const* sJV, double* sH, double* sG) {
+    using C = Cfg<E, F>;
+    using PC = PCfg<E, F>;
+    PartSink<E, F, PART> s;
+    s.red = red;
+    s.owner = owner;
+    s.c_ = sC + ob * E::CB;
+    s.jo_ = sJ + ob * E::J_BLOCK;
+    s.jn_ = sJ + nb * E::J_BLOCK;
+    s.ho_ = sH + ob * E::H_BLOCK;
+    s.go_ = sG + ob * E::BLK;
+    if constexpr (C::WJ && C::NV > 0) {
+#pragma unroll
+        for (int k = 0; k < C::NV; ++k) s.jv_[k] = sJV[k] + ob * E::JV_STRIDE;
+    }
+    if (active) {
+        if constexpr (C::WG && !E::LAGRANGE && PART == 0) {
+#pragma unroll
+            for (int k = 0; k < E::BLK; ++k) s.go_[k] = 0.0;
+        }
+        if constexpr (C::WC || C::WJ || C::WH) E::template step<C::WC, C::WJ, C::WH>(z, Tm, p, lam, a.sigma, s);
+        if constexpr (C::WG) E::grad_step(z, Tm, p, s);
+        if constexpr (C::WO && PART == 0) { if (owner) red[C::R_O] += E::cost_step(z, Tm, p); }
+    }
+    __syncthreads();   // all owners have stored: the neighbours' contributions can be added
+    if (active) {
+        if constexpr (C::WH) {
+#pragma unroll
+            for (int n = 0; n < E::NH_NEXT; ++n)
+                if (PartSink<E, F, PART>::mine(PC::O_HN + n)) sH[nb * E::H_BLOCK + E::H_NEXT(n, 2)] += s.hn_[n];
+        }
+        if constexpr (C::WG) {
+#pragma unroll
+            for (int n = 0; n < E::NG_NEXT; ++n)
+                if (PartSink<E, F, PART>::mine(PC::O_GN + n)) sG[nb * E::BLK + E::G_NEXT(n, 2)] += s.gn_[n];
+        }
+    }
+}
+
+template <class E, int F, int PART>
+struct PartDispatch {
+    template <class... A>
+    __device__ __forceinline__ static void run(int warp, A&&... args) {
+        if (warp == PART) run_part<E, F, PART>(args...);
+        else if constexpr (PART + 1 < PCfg<E, F>::P) PartDispatch<E, F, PART + 1>::run(warp, args...);
+    }
+};
+
+template <class E, int F>
+__global__ void __launch_bounds__(PCfg<E, F>::T) ctd_eval_kernel_parts(const EvalArgs a) {
+    using C = Cfg<E, F>;
+    using PC = PCfg<E, F>;
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int cta = blockIdx.x;
+    const long long inst = blockIdx.y;
+    const double* __restrict__ x = a.x + inst * a.x_stride;
+    const double* __restrict__ y = a.y ? a.y + inst * a.y_stride : nullptr;
+    const double* __restrict__ p = a.params + inst * (E::NPAR > 0 ? E::NPAR : 1);
+    double* c = C::WC ? a.c + inst * a.c_stride : nullptr;
+    double* jvals = C::WJ ? a.jvals + inst * a.j_stride : nullptr;
+    double* hvals = C::WH ? a.hvals + inst * a.h_stride : nullptr;
+    double* grad = C::WG ? a.grad + inst * a.g_stride : nullptr;
+    double red[C::NRED > 0 ? C::NRED : 1];
+#pragma unroll
+    for (int k = 0; k < (C::NRED > 0 ? C::NRED : 1); ++k) red[k] = 0.0;
+    __shared__ unsigned int cta_ticket;
     if constexpr (C::NRED > 0) {
-        double* sred = smem + C::S_RED;
-        const int nblk = a.ctas;
-        double wv[C::NRED];
+        if (tid == 0) cta_ticket = 0u;
+        __syncthreads();
+    }
+    if (cta == 0) {
+        edge_cta<E, F, PC::P>(a, x, y, p, c, jvals, hvals, grad, smem, red);
+    } else {
+        const long long i0 = 2 + (long long)(cta - 1) * PC::OWN;
+        const long long left = (long long)a.N - 1 - i0 + 1;
+        const int nown = (int)(left < PC::OWN ? (left < 0 ? 0 : left) : PC::OWN);
+        const long long i = i0 - 1 + lane;
+        const bool active = nown > 0 && lane <= nown;
+        const bool owner = active && lane >= 1;
+        const bool giver = active && lane < nown;
+        const int ob = owner ? lane - 1 : PC::OWN;
+        const int nb = giver ? lane : PC::OWN;
+        double* gC = C::WC ? c + (i0 - 1) * E::CB : nullptr;
+        double* gJ = C::WJ ? jvals + E::J_FIRST + (i0 - 2) * E::J_BLOCK : nullptr;
+        double* gH = C::WH ? hvals + E::H_FIRST + (i0 - 2) * E::H_BLOCK : nullptr;
+        double* gG = C::WG ? grad + (i0 - 1) * E::BLK : nullptr;
+        double* sC = smem + PC::S_C + (C::WC ? phase_of(gC) : 0);
+        double* sJ = smem + PC::S_J + (C::WJ ? phase_of(gJ) : 0);
+        double* sH = smem + PC::S_H + (C::WH ? phase_of(gH) : 0);
+        double* sG = smem + PC::S_G + (C::WG ? phase_of(gG) : 0);
+        double* gJV[C::NV > 0 ? C::NV : 1];
+        double* sJV[C::NV > 0 ? C::NV : 1];
+        if constexpr (C::WJ && C::NV > 0) {
 #pragma unroll
-        for (int k = 0; k < C::NRED; ++k) {
-            double v = red[k];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            wv[k] = v;
-        }
-        unsigned int flag = 0;
-        if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < C::NRED; ++k) sred[warp * C::NRED + k] = wv[k];
-            __threadfence_block();
-            flag = (atomicAdd(&cta_ticket, 1u) == (unsigned int)(C::WPC - 1));
-        }
-        flag = __shfl_sync(0xffffffffu, flag, 0);
-        if (flag) {
-            __threadfence_block();
-            double* part = a.partials + (inst * nblk) * C::NRED;
-            if (lane < C::NRED) {
-                double v = 0.0;
-                for (int w = 0; w < C::WPC; ++w) v += sred[w * C::NRED + lane];
-                part[(long long)cta * C::NRED + lane] = v;
-                __threadfence();
+            for (int k = 0; k < C::NV; ++k) {
+                gJV[k] = jvals + a.jv_base[k] + (i0 - 1) * E::JV_STRIDE;
+                sJV[k] = smem + PC::S_JV + k * PC::JV_ONE + phase_of(gJV[k]);
             }
-            __syncwarp();
-            unsigned int last = 0;
-            if (lane == 0) last = (atomicAdd(&a.counters[inst], 1u) == (unsigned int)(nblk - 1));
-            last = __shfl_sync(0xffffffffu, last, 0);
-            if (last) {
-                __threadfence();
-                double acc[C::NRED];
+        }
+        double z[E::NZ], lam[E::CB];
+        TimeArgs<E::NV> Tm;
+        if (active) {
+            load_step<E>(x, a.nvar, i, z);
 #pragma unroll
-                for (int k = 0; k < C::NRED; ++k) acc[k] = 0.0;
-                // 16 independent loads per lane in flight (one memory round trip per 512 partials)
-                for (int base = 0; base < nblk; base += 32 * 16) {
+            for (int r = 0; r < E::CB; ++r) lam[r] = (C::WH && y) ? __ldg(y + (i - 1) * E::CB + r) : 0.0;
+            time_args<E>(a, z + E::NOWN + E::NNEXT, p, i, Tm);
+        }
+        PartDispatch<E, F, 0>::run(warp, a, z, lam, Tm, p, red, active, owner, ob, nb, sC, sJ, sJV, sH, sG);
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (warp == 0 && nown > 0) {
+            if constexpr (C::WC) bulk_store_range(gC, sC, nown * E::CB, lane);
+            if constexpr (C::WJ) {
+                bulk_store_range(gJ, sJ, nown * E::J_BLOCK, lane);
+                if constexpr (C::NV > 0) {
 #pragma unroll
-                    for (int k = 0; k < C::NRED; ++k) {
-                        double t[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int b = base + j * 32 + lane;
-                            t[j] = b < nblk ? __ldcg(&part[(long long)b * C::NRED + k]) : 0.0;
-                        }
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) acc[k] += t[j];
-                    }
+                    for (int k = 0; k < C::NV; ++k) bulk_store_range(gJV[k], sJV[k], nown * E::JV_STRIDE, lane);
                 }
-#pragma unroll
-                for (int k = 0; k < C::NRED; ++k) {
-                    double v = acc[k];
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                    if (lane == 0) {
-                        if (C::WH && k < C::R_G) hvals[a.hvv_pos[k - C::R_H]] = v;
-                        else if (C::WG && k < C::R_O) grad[a.nvar - E::NV + (k - C::R_G)] = v;
-                        else if (C::WO && a.obj) a.obj[inst] = v;
-                    }
-                }
-                if (lane == 0) a.counters[inst] = 0u;
+            }
+            if constexpr (C::WH) bulk_store_range(gH, sH, nown * E::H_BLOCK, lane);
+            if constexpr (C::WG) bulk_store_range(gG, sG, nown * E::BLK, lane);
+            if (lane == 0) {
+                bulk_commit();
+                bulk_wait_read();   // shared memory must outlive the copies that read it
             }
         }
     }
-    CTD_STAMP(6);
+    publish_reduction<E, F, PC::P>(a, red, smem + PC::S_RED, &cta_ticket, inst, cta, lane, warp, hvals, grad);
 }
 
 // the same body under two register budgets (see Cfg::LIGHT)

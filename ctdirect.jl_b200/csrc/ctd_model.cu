@@ -475,6 +475,7 @@ void Model::ensure_device() {
         const LaunchCfg q = reg_.launcher.cfg(fl);
         const int64_t tiles = (N_ >= 3) ? ((int64_t)N_ - 2 + q.own - 1) / q.own : 0;
         max_ctas = std::max<int64_t>(max_ctas, (tiles + q.wpc - 1) / q.wpc + 1);
+        if (q.p_threads > 0) max_ctas = std::max<int64_t>(max_ctas, ((N_ >= 3) ? ((int64_t)N_ - 2 + q.p_own - 1) / q.p_own : 0) + 1);
     }
     CTD_CUDA(cudaMalloc(&d_partials_, sizeof(double) * (size_t)batch_ * max_ctas * std::max(lc.nred, 1)));
     CTD_CUDA(cudaMalloc(&d_counters_, sizeof(unsigned int) * batch_));
@@ -563,15 +564,29 @@ void Model::eval_dev(int flags, const double* x, const double* y, double sigma, 
     a.x = x; a.y = y; a.sigma = sigma; a.obj = obj; a.grad = grad; a.c = c; a.jvals = jvals; a.hvals = hvals;
     a.tiles = (N_ >= 3) ? (int)(((int64_t)N_ - 2 + lc.own - 1) / lc.own) : 0;
     a.ctas = (a.tiles + lc.wpc - 1) / lc.wpc + 1;
+    // wide elements on small grids: one tile per CTA, the tile's outputs split over the CTA's warps
+    // (enough warps to occupy the GPU although the grid has few steps)
+    int parts = 0;
+    size_t tile_smem = lc.tile_smem;
+    if (lc.p_threads > 0) {
+        const int64_t ptiles = (N_ >= 3) ? ((int64_t)N_ - 2 + lc.p_own - 1) / lc.p_own : 0;
+        if (ptiles * batch_ * (lc.p_threads / 32) <= (int64_t)148 * 48) {
+            parts = 1;
+            a.tiles = (int)ptiles;
+            a.ctas = (int)ptiles + 1;
+            tile_smem = lc.p_smem;
+        }
+    }
     // the edge CTA uses the same dynamic shared memory as its value buffer (its reduction scratch at
-    // Cfg::S_RED is only touched after the buffer has been scattered)
+    // S_RED is only touched after the buffer has been scattered)
     const size_t edge_smem = sizeof(double) * (EDGE_LAYERS * ((size_t)ne_j_ + ne_h_ + ne_g_) + 2) + sizeof(int) * (edge_map_.size() + 2);
-    const size_t smem = std::max(lc.tile_smem, edge_smem);
-    auto it = prepared_.find(flags);
+    const size_t smem = std::max(tile_smem, edge_smem);
+    const int pkey = flags + 256 * parts;
+    auto it = prepared_.find(pkey);
     if (it == prepared_.end() || it->second < smem) {
-        const int e = reg_.launcher.prepare(flags, smem);
+        const int e = reg_.launcher.prepare(flags, smem, parts);
         if (e != 0) throw CtdError{e, std::string("cudaFuncSetAttribute failed: ") + cudaGetErrorString((cudaError_t)e)};
-        prepared_[flags] = smem;
+        prepared_[pkey] = smem;
     }
 #ifdef CTD_TRACE
     // debug builds only: per-warp timestamps of the launch, dumped as raw int64 to $CTD_TRACE_FILE
@@ -584,7 +599,7 @@ void Model::eval_dev(int flags, const double* x, const double* y, double sigma, 
         a.trace = d_trace;
     }
 #endif
-    const int e = reg_.launcher.launch(a, flags, batch_, smem, stream_);
+    const int e = reg_.launcher.launch(a, flags, batch_, smem, stream_, parts);
     if (e != 0) throw CtdError{e, std::string("kernel launch failed: ") + cudaGetErrorString((cudaError_t)e)};
     ++launches_;
 #ifdef CTD_TRACE

@@ -20,13 +20,16 @@ struct LaunchCfg {
     int threads = 0, own = 0, nred = 0, wpc = 1;
     size_t tile_smem = 0;
     int map_step = 0, map_fp = 0, map_bc = 0;  // map sizes
+    // "parts" variant for wide elements on small grids (0 threads: not compiled for this element)
+    int p_threads = 0, p_own = 0;
+    size_t p_smem = 0;
 };
 
 struct Launcher {
     // returns cudaError_t as int
-    int (*launch)(const EvalArgs& a, int flags, int batch, size_t smem, cudaStream_t st) = nullptr;
+    int (*launch)(const EvalArgs& a, int flags, int batch, size_t smem, cudaStream_t st, int parts) = nullptr;
     LaunchCfg (*cfg)(int flags) = nullptr;
-    int (*prepare)(int flags, size_t smem) = nullptr;  // opt in to > 48 KB dynamic shared memory
+    int (*prepare)(int flags, size_t smem, int parts) = nullptr;  // opt in to > 48 KB dynamic shared memory
 };
 
 struct Registration {
@@ -123,7 +126,7 @@ class Model {
     unsigned int* d_counters_ = nullptr;
     double *d_x_ = nullptr, *d_y_ = nullptr, *d_c_ = nullptr, *d_j_ = nullptr, *d_h_ = nullptr, *d_g_ = nullptr,
            *d_obj_ = nullptr, *d_lcon_ = nullptr, *d_ucon_ = nullptr, *d_viol_ = nullptr;
-    std::map<int, size_t> prepared_;  // flags -> dynamic smem size
+    std::map<int, size_t> prepared_;  // flags (+ 256 for the parts variant) -> dynamic smem size
     int64_t launches_ = 0;
 };
 

@@ -24,6 +24,12 @@ struct ElementLauncher {
         c.map_step = C::M_STEP + 1;
         c.map_fp = C::M_FP;
         c.map_bc = C::M_BC;
+        if constexpr (!C::LIGHT) {
+            using PC = PCfg<E, F>;
+            c.p_threads = PC::T;
+            c.p_own = PC::OWN;
+            c.p_smem = PC::TILE_SMEM;
+        }
         return c;
     }
     static LaunchCfg cfg(int flags) {
@@ -34,7 +40,16 @@ struct ElementLauncher {
         }
         return LaunchCfg();
     }
-    static int prepare(int flags, size_t smem) {
+    static int prepare(int flags, size_t smem, int parts) {
+        if (parts) {
+            switch (flags) {
+#define CTD_X(F) \
+    case F: if constexpr (!Cfg<E, F>::LIGHT) return (int)cudaFuncSetAttribute(ctd_eval_kernel_parts<E, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); else return (int)cudaErrorInvalidValue;
+                CTD_FOR_EACH_FLAGSET(CTD_X)
+#undef CTD_X
+            }
+            return (int)cudaErrorInvalidValue;
+        }
         switch (flags) {
 #define CTD_X(F) \
     case F: if constexpr (Cfg<E, F>::LIGHT) return (int)cudaFuncSetAttribute(ctd_eval_kernel_light<E, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
@@ -44,8 +59,18 @@ struct ElementLauncher {
         }
         return (int)cudaErrorInvalidValue;
     }
-    static int launch(const EvalArgs& a, int flags, int batch, size_t smem, cudaStream_t st) {
+    static int launch(const EvalArgs& a, int flags, int batch, size_t smem, cudaStream_t st, int parts) {
         dim3 grid((unsigned)a.ctas, (unsigned)batch, 1);
+        if (parts) {
+            switch (flags) {
+#define CTD_X(F) \
+    case F: if constexpr (!Cfg<E, F>::LIGHT) ctd_eval_kernel_parts<E, F><<<grid, PCfg<E, F>::T, smem, st>>>(a); break;
+                CTD_FOR_EACH_FLAGSET(CTD_X)
+#undef CTD_X
+                default: return (int)cudaErrorInvalidValue;
+            }
+            return (int)cudaGetLastError();
+        }
         switch (flags) {
 #define CTD_X(F) \
     case F: if constexpr (Cfg<E, F>::LIGHT) ctd_eval_kernel_light<E, F><<<grid, Cfg<E, F>::T, smem, st>>>(a); \
