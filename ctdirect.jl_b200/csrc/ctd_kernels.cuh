@@ -93,7 +93,9 @@ struct Cfg {
 #ifndef CTD_WPC
 #define CTD_WPC 8
 #endif
-    static constexpr int WPC = (PER_STEP * 8 * 32 * CTD_WPC <= 200 * 1024) ? CTD_WPC : 1;
+    static constexpr int WARP_BYTES = PER_STEP * 8 * 32;
+    static constexpr int WPC = (WARP_BYTES * CTD_WPC <= 72 * 1024) ? CTD_WPC
+                               : (WARP_BYTES * 4 <= 100 * 1024) ? 4 : (WARP_BYTES * 2 <= 100 * 1024) ? 2 : 1;
     static constexpr int T = WPC * 32;
     // light elements: cap registers at 88/thread so that 22 warps (682 owned steps) are resident per SM,
     // i.e. a grid of 1e5 steps is ONE wave on 148 SMs; wide elements keep the full register file
@@ -611,10 +613,25 @@ __device__ __forceinline__ void publish_reduction(const EvalArgs& a, const doubl
     }
 }
 
+// Programmatic dependent launch: a launch made with the programmatic-stream-serialization attribute may
+// be scheduled while the previous kernel of the stream is still draining; `griddepcontrol.wait` blocks
+// until that kernel has completed and its memory is visible, so only launch latency and CTA scheduling
+// overlap -- results and the handle's scratch buffers are never touched early.
+#ifndef CTD_PDL
+#define CTD_PDL 1
+#endif
+__device__ __forceinline__ void pdl_entry() {
+#if CTD_PDL
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
 template <class E, int F>
 __device__ __forceinline__ void eval_body(const EvalArgs& a) {
     using C = Cfg<E, F>;
     constexpr int T = C::T;
+    pdl_entry();
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -820,6 +837,7 @@ template <class E, int F>
 __global__ void __launch_bounds__(PCfg<E, F>::T) ctd_eval_kernel_parts(const EvalArgs a) {
     using C = Cfg<E, F>;
     using PC = PCfg<E, F>;
+    pdl_entry();
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;

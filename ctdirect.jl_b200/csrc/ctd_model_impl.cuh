@@ -10,6 +10,22 @@ namespace ctd {
 //   cons | jac | hess | obj | cons+obj | grad+obj | cons+jac+hess | everything
 #define CTD_FOR_EACH_FLAGSET(X) X(1) X(2) X(4) X(16) X(17) X(24) X(7) X(31)
 
+// launch with the programmatic-stream-serialization attribute (see pdl_entry() in ctd_kernels.cuh)
+template <class K>
+inline void launch_pdl(K kernel, dim3 grid, int threads, size_t smem, cudaStream_t st, const EvalArgs& a) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3((unsigned)threads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = CTD_PDL;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, a);
+}
+
 template <class E>
 struct ElementLauncher {
     template <int F>
@@ -64,7 +80,7 @@ struct ElementLauncher {
         if (parts) {
             switch (flags) {
 #define CTD_X(F) \
-    case F: if constexpr (!Cfg<E, F>::LIGHT) ctd_eval_kernel_parts<E, F><<<grid, PCfg<E, F>::T, smem, st>>>(a); break;
+    case F: if constexpr (!Cfg<E, F>::LIGHT) launch_pdl(ctd_eval_kernel_parts<E, F>, grid, PCfg<E, F>::T, smem, st, a); break;
                 CTD_FOR_EACH_FLAGSET(CTD_X)
 #undef CTD_X
                 default: return (int)cudaErrorInvalidValue;
@@ -73,8 +89,8 @@ struct ElementLauncher {
         }
         switch (flags) {
 #define CTD_X(F) \
-    case F: if constexpr (Cfg<E, F>::LIGHT) ctd_eval_kernel_light<E, F><<<grid, Cfg<E, F>::T, smem, st>>>(a); \
-            else ctd_eval_kernel<E, F><<<grid, Cfg<E, F>::T, smem, st>>>(a); break;
+    case F: if constexpr (Cfg<E, F>::LIGHT) launch_pdl(ctd_eval_kernel_light<E, F>, grid, Cfg<E, F>::T, smem, st, a); \
+            else launch_pdl(ctd_eval_kernel<E, F>, grid, Cfg<E, F>::T, smem, st, a); break;
             CTD_FOR_EACH_FLAGSET(CTD_X)
 #undef CTD_X
             default: return (int)cudaErrorInvalidValue;
