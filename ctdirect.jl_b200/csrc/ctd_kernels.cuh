@@ -218,7 +218,7 @@ __device__ __forceinline__ long long gtime() {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-#define CTD_STAMP(k) do { if (a.trace && lane == 0) a.trace[((long long)cta * C::WPC + warp) * 8 + (k)] = gtime(); } while (0)
+#define CTD_STAMP(k) do { if (a.trace && lane == 0) a.trace[((long long)cta * (blockDim.x >> 5) + warp) * 8 + (k)] = gtime(); } while (0)
 #else
 #define CTD_STAMP(k) do { } while (0)
 #endif
@@ -348,13 +348,13 @@ __device__ __forceinline__ void edge_step_job(const EvalArgs& a, const EdgeTask&
     if constexpr (JO) { if (tk.own) red[C::R_O] += E::cost_step(z, Tm, p); }
 }
 
-template <class E, int F, int NW>
+template <class E, int F>
 __device__ void edge_cta(const EvalArgs& a, const double* __restrict__ x, const double* __restrict__ y,
                          const double* __restrict__ p, double* c, double* jvals, double* hvals, double* grad,
-                         double* buf, double* red) {
+                         double* buf, double* red, const int NW) {
     using C = Cfg<E, F>;
     const int tid = threadIdx.x;
-    constexpr int T = NW * 32;
+    const int T = NW * 32;
     const int ne = a.ne_j + a.ne_h + a.ne_g;
     // the position maps are staged in shared memory first (one coalesced pass): the sinks look up one
     // map entry per value, and those lookups must not be dependent global loads
@@ -367,7 +367,7 @@ __device__ void edge_cta(const EvalArgs& a, const double* __restrict__ x, const 
         // (phase A on one warp, phase B on another when both are requested); the final-path and the
         // boundary element take lane 0 of the next warps (round robin when the CTA has fewer warps).
         constexpr bool TWO = C::PHASE_A && C::PHASE_B;
-        constexpr int W_A = 0, W_B = TWO ? (1 % NW) : 0, W_FP = (TWO ? 2 : 1) % NW, W_BC = (TWO ? 3 : 2) % NW;
+        const int W_A = 0, W_B = TWO ? (1 % NW) : 0, W_FP = (TWO ? 2 : 1) % NW, W_BC = (TWO ? 3 : 2) % NW;
         const int lane_ = tid & 31, warp_ = tid >> 5;
         if (lane_ < a.ntask) {
             const EdgeTask tk = a.task[lane_];
@@ -540,10 +540,10 @@ __device__ __forceinline__ void tile_phase(const EvalArgs& a, double* __restrict
 // Deterministic reduction of the global sums ((v,v) Hessian entries, d cost / d v, cost) over the grid.
 // No CTA barrier: the last warp of a CTA to arrive combines the CTA's NW warps in a fixed order and
 // publishes one partial; the last CTA to publish sums all partials in a fixed order.
-template <class E, int F, int NW>
+template <class E, int F>
 __device__ __forceinline__ void publish_reduction(const EvalArgs& a, const double* red, double* sred,
                                                   unsigned int* cta_ticket_p, long long inst, int cta, int lane,
-                                                  int warp, double* hvals, double* grad) {
+                                                  int warp, double* hvals, double* grad, const int NW) {
     using C = Cfg<E, F>;
     if constexpr (C::NRED > 0) {
         unsigned int& cta_ticket = *cta_ticket_p;
@@ -635,6 +635,7 @@ __device__ __forceinline__ void eval_body(const EvalArgs& a) {
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
+    const int nw = (int)(blockDim.x >> 5);   // warps per CTA: chosen per launch (<= C::WPC)
     const int cta = blockIdx.x;
     const long long inst = blockIdx.y;
 
@@ -657,10 +658,10 @@ __device__ __forceinline__ void eval_body(const EvalArgs& a) {
 
     CTD_STAMP(0);
     if (cta == 0) {
-        edge_cta<E, F, C::WPC>(a, x, y, p, c, jvals, hvals, grad, smem, red);
+        edge_cta<E, F>(a, x, y, p, c, jvals, hvals, grad, smem, red, nw);
         CTD_STAMP(4);
     } else {
-        const long long tile = (long long)(cta - 1) * C::WPC + warp;
+        const long long tile = (long long)(cta - 1) * nw + warp;
         const long long i0 = 2 + tile * C::OWN;                       // first owned step / column block
         const long long last = (long long)a.N - 1;                    // last regular column block
         const long long left = last - i0 + 1;
@@ -702,7 +703,7 @@ __device__ __forceinline__ void eval_body(const EvalArgs& a) {
         CTD_STAMP(5);
     }
 
-    publish_reduction<E, F, C::WPC>(a, red, smem + C::S_RED, &cta_ticket, inst, cta, lane, warp, hvals, grad);
+    publish_reduction<E, F>(a, red, smem + nw * C::WARP_DOUBLES, &cta_ticket, inst, cta, lane, warp, hvals, grad, nw);
     CTD_STAMP(6);
 }
 
@@ -859,7 +860,7 @@ __global__ void __launch_bounds__(PCfg<E, F>::T) ctd_eval_kernel_parts(const Eva
         __syncthreads();
     }
     if (cta == 0) {
-        edge_cta<E, F, PC::P>(a, x, y, p, c, jvals, hvals, grad, smem, red);
+        edge_cta<E, F>(a, x, y, p, c, jvals, hvals, grad, smem, red, PC::P);
     } else {
         const long long i0 = 2 + (long long)(cta - 1) * PC::OWN;
         const long long left = (long long)a.N - 1 - i0 + 1;
@@ -915,7 +916,7 @@ __global__ void __launch_bounds__(PCfg<E, F>::T) ctd_eval_kernel_parts(const Eva
             }
         }
     }
-    publish_reduction<E, F, PC::P>(a, red, smem + PC::S_RED, &cta_ticket, inst, cta, lane, warp, hvals, grad);
+    publish_reduction<E, F>(a, red, smem + PC::S_RED, &cta_ticket, inst, cta, lane, warp, hvals, grad, PC::P);
 }
 
 // the same body under two register budgets (see Cfg::LIGHT)

@@ -474,7 +474,7 @@ void Model::ensure_device() {
     for (int fl : {1, 2, 4, 16, 17, 24, 7, 31}) {
         const LaunchCfg q = reg_.launcher.cfg(fl);
         const int64_t tiles = (N_ >= 3) ? ((int64_t)N_ - 2 + q.own - 1) / q.own : 0;
-        max_ctas = std::max<int64_t>(max_ctas, (tiles + q.wpc - 1) / q.wpc + 1);
+        max_ctas = std::max<int64_t>(max_ctas, tiles + 1);   // (one warp per CTA is the smallest launch configuration)
         if (q.p_threads > 0) max_ctas = std::max<int64_t>(max_ctas, ((N_ >= 3) ? ((int64_t)N_ - 2 + q.p_own - 1) / q.p_own : 0) + 1);
     }
     CTD_CUDA(cudaMalloc(&d_partials_, sizeof(double) * (size_t)batch_ * max_ctas * std::max(lc.nred, 1)));
@@ -562,16 +562,22 @@ void Model::eval_dev(int flags, const double* x, const double* y, double sigma, 
     if ((flags & F_GRAD) && !grad) throw CtdError{-2, "grad is NULL"};
     EvalArgs a = base_args();
     a.x = x; a.y = y; a.sigma = sigma; a.obj = obj; a.grad = grad; a.c = c; a.jvals = jvals; a.hvals = hvals;
+    // warps per CTA: large CTAs for a single instance (a 1e5-step grid is one wave and CTA launch rate
+    // matters), small CTAs for batches (many waves: resources are released per CTA, and the tiles of
+    // an instance rarely fill a large CTA)
+    const int wpc = batch_ > 1 ? std::min(lc.wpc, 3) : lc.wpc;
+    int threads = 32 * wpc;
     a.tiles = (N_ >= 3) ? (int)(((int64_t)N_ - 2 + lc.own - 1) / lc.own) : 0;
-    a.ctas = (a.tiles + lc.wpc - 1) / lc.wpc + 1;
+    a.ctas = (a.tiles + wpc - 1) / wpc + 1;
     // wide elements on small grids: one tile per CTA, the tile's outputs split over the CTA's warps
     // (enough warps to occupy the GPU although the grid has few steps)
     int parts = 0;
-    size_t tile_smem = lc.tile_smem;
+    size_t tile_smem = wpc * lc.warp_smem + sizeof(double) * (wpc * std::max(lc.nred, 1) + 2);
     if (lc.p_threads > 0) {
         const int64_t ptiles = (N_ >= 3) ? ((int64_t)N_ - 2 + lc.p_own - 1) / lc.p_own : 0;
         if (ptiles * batch_ * (lc.p_threads / 32) <= (int64_t)148 * 48) {
             parts = 1;
+            threads = lc.p_threads;
             a.tiles = (int)ptiles;
             a.ctas = (int)ptiles + 1;
             tile_smem = lc.p_smem;
@@ -599,7 +605,7 @@ void Model::eval_dev(int flags, const double* x, const double* y, double sigma, 
         a.trace = d_trace;
     }
 #endif
-    const int e = reg_.launcher.launch(a, flags, batch_, smem, stream_, parts);
+    const int e = reg_.launcher.launch(a, flags, batch_, smem, stream_, parts, threads);
     if (e != 0) throw CtdError{e, std::string("kernel launch failed: ") + cudaGetErrorString((cudaError_t)e)};
     ++launches_;
 #ifdef CTD_TRACE

@@ -18,6 +18,7 @@ namespace ctd {
 
 struct LaunchCfg {
     int threads = 0, own = 0, nred = 0, wpc = 1;
+    size_t warp_smem = 0;   // bytes of one warp's staging region
     size_t tile_smem = 0;
     int map_step = 0, map_fp = 0, map_bc = 0;  // map sizes
     // "parts" variant for wide elements on small grids (0 threads: not compiled for this element)
@@ -27,7 +28,7 @@ struct LaunchCfg {
 
 struct Launcher {
     // returns cudaError_t as int
-    int (*launch)(const EvalArgs& a, int flags, int batch, size_t smem, cudaStream_t st, int parts) = nullptr;
+    int (*launch)(const EvalArgs& a, int flags, int batch, size_t smem, cudaStream_t st, int parts, int threads) = nullptr;
     LaunchCfg (*cfg)(int flags) = nullptr;
     int (*prepare)(int flags, size_t smem, int parts) = nullptr;  // opt in to > 48 KB dynamic shared memory
 };

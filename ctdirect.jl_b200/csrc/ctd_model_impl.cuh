@@ -35,6 +35,7 @@ struct ElementLauncher {
         c.threads = C::T;
         c.own = C::OWN;
         c.wpc = C::WPC;
+        c.warp_smem = (size_t)C::WARP_DOUBLES * sizeof(double);
         c.nred = C::NRED;
         c.tile_smem = C::TILE_SMEM;
         c.map_step = C::M_STEP + 1;
@@ -75,7 +76,7 @@ struct ElementLauncher {
         }
         return (int)cudaErrorInvalidValue;
     }
-    static int launch(const EvalArgs& a, int flags, int batch, size_t smem, cudaStream_t st, int parts) {
+    static int launch(const EvalArgs& a, int flags, int batch, size_t smem, cudaStream_t st, int parts, int threads) {
         dim3 grid((unsigned)a.ctas, (unsigned)batch, 1);
         if (parts) {
             switch (flags) {
@@ -89,8 +90,8 @@ struct ElementLauncher {
         }
         switch (flags) {
 #define CTD_X(F) \
-    case F: if constexpr (Cfg<E, F>::LIGHT) launch_pdl(ctd_eval_kernel_light<E, F>, grid, Cfg<E, F>::T, smem, st, a); \
-            else launch_pdl(ctd_eval_kernel<E, F>, grid, Cfg<E, F>::T, smem, st, a); break;
+    case F: if constexpr (Cfg<E, F>::LIGHT) launch_pdl(ctd_eval_kernel_light<E, F>, grid, threads, smem, st, a); \
+            else launch_pdl(ctd_eval_kernel<E, F>, grid, threads, smem, st, a); break;
             CTD_FOR_EACH_FLAGSET(CTD_X)
 #undef CTD_X
             default: return (int)cudaErrorInvalidValue;
