@@ -47,7 +47,8 @@ const char* ctd_last_error(void) { return g_err.c_str(); }
 int64_t ctd_list_models(char* buf, int64_t buflen) {
     std::string s;
     for (const Registration& r : registry())
-        s += r.info.problem + " " + r.info.scheme + " " + (r.info.pattern_mode ? "corrected" : "reference") + "\n";
+        s += r.info.problem + " " + r.info.scheme + " " +
+             (r.info.pattern_mode == 2 ? "optimized" : r.info.pattern_mode ? "corrected" : "reference") + "\n";
     if (buf && buflen > 0) {
         const size_t n = std::min<size_t>(s.size(), (size_t)buflen - 1);
         std::memcpy(buf, s.data(), n);
@@ -67,8 +68,8 @@ int ctd_create(const ctd_desc* d, ctd_handle* out) {
             if (r.info.problem == d->problem) problem_known = true;
             if (r.info.problem == d->problem && r.info.scheme == d->scheme) {
                 if (r.info.pattern_mode == d->pattern_mode) reg = &r;
-                // a pair without quirks is only compiled in reference mode: both modes coincide
-                else if (!reg && r.info.pattern_mode == 0) reg = &r;
+                // a pair without quirks is only compiled in reference mode: both manual modes coincide
+                else if (!reg && r.info.pattern_mode == 0 && d->pattern_mode != 2) reg = &r;
             }
         }
         if (!reg) {
@@ -77,7 +78,7 @@ int ctd_create(const ctd_desc* d, ctd_handle* out) {
             if (!problem_known) throw CtdError{-5, std::string("unknown problem: ") + d->problem};
             throw CtdError{-5, "this (problem, scheme) pair is not compiled in"};
         }
-        if (d->pattern_mode != 0 && d->pattern_mode != 1) throw CtdError{-2, "pattern_mode must be 0 or 1"};
+        if (d->pattern_mode < 0 || d->pattern_mode > 2) throw CtdError{-2, "pattern_mode must be 0, 1 or 2"};
         Model* m = new Model(*reg, d->grid_size, d->time_grid, d->n_time_grid, d->params, d->n_params,
                              d->batch < 1 ? 1 : d->batch, d->device);
         *out = new ctd_model_s{m};

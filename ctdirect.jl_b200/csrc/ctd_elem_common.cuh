@@ -62,7 +62,8 @@ struct ElemInfo {
     int ctrl_blk = 0, blk = 0, eqs = 0, cb = 0, nown = 0, nnext = 0, nz = 0;
     int j_block = 0, h_block = 0, j_first = 0, h_first = 0, jv_stride = 0, fp_nloc = 0, bc_nloc = 0;
     int n_dropped = 0;
-    SlotTable j_own, j_next, j_v, h_own, h_next, fp_j, fp_h, bc_j, bc_h, g_own, g_next, g_v, bc_g;
+    SlotTable j_own, j_next, j_v, h_own, h_next, h_vv, fp_j, fp_h, bc_j, bc_h, g_own, g_next, g_v, bc_g;
+    SlotTable s_step_j, s_step_h, s_fp_j, s_fp_h, s_bc_j, s_bc_h;   // detected structure (pattern mode 2)
     ProblemMeta meta;
 };
 
@@ -94,6 +95,13 @@ inline ElemInfo make_elem_info() {
     CTD_FILL_TABLE(f, E, J_V, j_v);
     CTD_FILL_TABLE(f, E, H_OWN, h_own);
     CTD_FILL_TABLE(f, E, H_NEXT, h_next);
+    CTD_FILL_TABLE(f, E, H_VV, h_vv);
+    CTD_FILL_TABLE(f, E, S_STEP_J, s_step_j);
+    CTD_FILL_TABLE(f, E, S_STEP_H, s_step_h);
+    CTD_FILL_TABLE(f, E, S_FP_J, s_fp_j);
+    CTD_FILL_TABLE(f, E, S_FP_H, s_fp_h);
+    CTD_FILL_TABLE(f, E, S_BC_J, s_bc_j);
+    CTD_FILL_TABLE(f, E, S_BC_H, s_bc_h);
     CTD_FILL_TABLE(f, E, FP_J, fp_j);
     CTD_FILL_TABLE(f, E, FP_H, fp_h);
     CTD_FILL_TABLE(f, E, BC_J, bc_j);

@@ -602,7 +602,7 @@ __device__ __forceinline__ void publish_reduction(const EvalArgs& a, const doubl
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                     if (lane == 0) {
-                        if (C::WH && k < C::R_G) hvals[a.hvv_pos[k - C::R_H]] = v;
+                        if (C::WH && k < C::R_G) { if (a.hvv_pos[k - C::R_H] >= 0) hvals[a.hvv_pos[k - C::R_H]] = v; }
                         else if (C::WG && k < C::R_O) grad[a.nvar - E::NV + (k - C::R_G)] = v;
                         else if (C::WO && a.obj) a.obj[inst] = v;
                     }

@@ -147,8 +147,63 @@ Model::~Model() {
 }
 
 // --------------------------------------------------------------------------------------------
+// ":optimized" (detected) patterns, pattern mode 2: assembled from the structure lists of the three
+// element kinds that the generator obtained by tracing the OCP expressions (gen/trace.py); the entries are
+// gathered as (column, row) keys, sorted and made unique -- the CSC order of SparseArrays.sparse.
+static Csc csc_from_keys(std::vector<std::pair<int64_t, int64_t>>& key, int64_t m, int64_t n) {
+    std::sort(key.begin(), key.end());
+    key.erase(std::unique(key.begin(), key.end()), key.end());
+    Csc p;
+    p.m = m;
+    p.n = n;
+    p.colptr.assign(n + 1, 0);
+    p.rows.resize(key.size());
+    for (size_t k = 0; k < key.size(); ++k) {
+        p.rows[k] = key[k].second;
+        p.colptr[key[k].first]++;
+    }
+    for (int64_t j = 0; j < n; ++j) p.colptr[j + 1] += p.colptr[j];
+    return p;
+}
+
+void Model::build_detected_patterns() {
+    const ElemInfo& f = reg_.info;
+    const int64_t B = f.blk, CB = f.cb, N = N_, nv = f.nv, nloc = f.nown + f.nnext;
+    auto scol = [&](int64_t i, int a) -> int64_t { return a < nloc ? (i - 1) * B + a + 1 : nvar_ - nv + (a - nloc) + 1; };
+    auto fcol = [&](int a) -> int64_t {   // final-path element: (u_f block, x_f, v), or (x_f, u_f, v) for trapeze
+        const int nl = f.fp_nloc - f.nv;
+        if (a >= nl) return nvar_ - nv + (a - nl) + 1;
+        if (f.final_control) return N * B + a + 1;
+        if (a < f.ctrl_blk) return (N - 1) * B + f.nx + a + 1;
+        return N * B + (a - f.ctrl_blk) + 1;
+    };
+    auto bcol = [&](int a) -> int64_t {   // boundary element: (x_1, x_{N+1}, v)
+        if (a < f.nx) return a + 1;
+        if (a < 2 * f.nx) return N * B + (a - f.nx) + 1;
+        return nvar_ - nv + (a - 2 * f.nx) + 1;
+    };
+    std::vector<std::pair<int64_t, int64_t>> J, H;
+    J.reserve((size_t)N * f.s_step_j.n + 64);
+    H.reserve((size_t)N * f.s_step_h.n + 64);
+    auto addH = [&](int64_t ga, int64_t gb) { H.emplace_back(std::min(ga, gb), std::max(ga, gb)); };   // (col, row), row >= col
+    for (int64_t i = 1; i <= N; ++i) {
+        for (int n = 0; n < f.s_step_j.n; ++n) J.emplace_back(scol(i, f.s_step_j(n, 1)), (i - 1) * CB + f.s_step_j(n, 0) + 1);
+        for (int n = 0; n < f.s_step_h.n; ++n) addH(scol(i, f.s_step_h(n, 0)), scol(i, f.s_step_h(n, 1)));
+    }
+    for (int n = 0; n < f.s_fp_j.n; ++n) J.emplace_back(fcol(f.s_fp_j(n, 1)), N * CB + f.s_fp_j(n, 0) + 1);
+    for (int n = 0; n < f.s_fp_h.n; ++n) addH(fcol(f.s_fp_h(n, 0)), fcol(f.s_fp_h(n, 1)));
+    for (int n = 0; n < f.s_bc_j.n; ++n) J.emplace_back(bcol(f.s_bc_j(n, 1)), ncon_ - f.nb + f.s_bc_j(n, 0) + 1);
+    for (int n = 0; n < f.s_bc_h.n; ++n) addH(bcol(f.s_bc_h(n, 0)), bcol(f.s_bc_h(n, 1)));
+    jac_ = csc_from_keys(J, ncon_, nvar_);
+    hess_ = csc_from_keys(H, nvar_, nvar_);
+}
+
 void Model::build_patterns() {
     const ElemInfo& f = reg_.info;
+    if (f.pattern_mode == 2) {
+        build_detected_patterns();
+        return;
+    }
     const int64_t nx = f.nx, nu = f.nu, nv = f.nv, np = f.np, nb = f.nb, B = f.blk, CB = f.cb, N = N_;
     const int64_t s = f.stage, cblk = f.ctrl_blk;
     const int64_t v0 = nvar_ - nv + 1, v1 = nvar_;
@@ -308,9 +363,8 @@ void Model::build_edge_tables() {
     for (int k = 0; k < nv; ++k) jv_base_[k] = jac_.colptr[nvar_ - nv + k];
     for (int a = 0; a < nv; ++a)
         for (int b = 0; b <= a; ++b) {
-            const int64_t pos = hess_.find(nvar_ - nv + a + 1, nvar_ - nv + b + 1);
-            if (pos < 0) throw CtdError{-9, "internal: (v,v) entry missing from the Hessian pattern"};
-            hvv_pos_[a * (a + 1) / 2 + b] = pos;
+            // -1: the entry is not in the pattern (detected patterns only keep structural nonzeros)
+            hvv_pos_[a * (a + 1) / 2 + b] = hess_.find(nvar_ - nv + a + 1, nvar_ - nv + b + 1);
         }
     // tasks
     ntask_ = 0;

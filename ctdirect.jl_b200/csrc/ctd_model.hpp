@@ -99,6 +99,7 @@ class Model {
 
   private:
     void build_patterns();
+    void build_detected_patterns();
     void build_edge_tables();
     void ensure_device();
     void ensure_staging();

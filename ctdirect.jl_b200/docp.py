@@ -88,7 +88,7 @@ class DOCP:
         d.n_time_grid = 0 if tg is None else len(tg)
         d.params = None if par is None else par.ctypes.data_as(_lib._dp)
         d.n_params = 0 if par is None else len(par)
-        d.pattern_mode = {"reference": 0, "corrected": 1}[pattern_mode]
+        d.pattern_mode = {"reference": 0, "corrected": 1, "optimized": 2}[pattern_mode]
         d.batch = int(batch)
         d.device = int(device)
         h = C.c_void_p()

@@ -24,7 +24,8 @@ from typing import Dict, List, Tuple
 import sympy as sp
 
 from . import patterns as pat
-from .ocps import OCP
+from . import trace as tr
+from .ocps import OCP, ZERO
 
 PROBE_N = 6
 PROBE_I = 3
@@ -120,6 +121,10 @@ class StepElement:
     inter: list = field(default_factory=list)        # [(symbol, expr)] intermediates (see Differ)
     inter_code: list = field(default_factory=list)   # C lines defining them in the reference's order
     u_node: list = field(default_factory=list)       # control used by the path constraints of the step
+    rows_traced: list = field(default_factory=list)  # rows / cost before structural zeros are dropped
+    cost_traced: sp.Expr = sp.Integer(0)
+    structure: dict = None                           # detected structure (pattern_mode 'optimized')
+    h_vv_table: list = field(default_factory=list)   # (kv1, kv2, slot) of the (v,v) Hessian entries in the pattern
 
 
 def _time_syms(ocp: OCP, prefix=""):
@@ -235,12 +240,20 @@ def build_step_element(ocp: OCP, scheme: str, pattern_mode: str = "reference") -
     if npc:
         rows += [sp.sympify(e) for e in ocp.path(ti, xi, u_node, v, p)]
     assert len(rows) == L.cblock
+    E.rows_traced = [sp.sympify(r) for r in rows]
+    E.cost_traced = sp.sympify(cost)
+    rows = [sp.sympify(r).subs(ZERO, 0) for r in rows]
+    cost = sp.sympify(cost).subs(ZERO, 0)
     E.rows = rows
     E.cost = sp.sympify(cost)
 
     # ------------------------------------------------------------------ value slots from the probe
-    jr, jc, jptr = pat.jacobian_pattern(L, pattern_mode)
-    hr, hc, hptr = pat.hessian_pattern(L, pattern_mode)
+    if pattern_mode == "optimized":
+        E.structure = detect_structure(ocp, scheme, L, E)
+        (jr, jc, jptr), (hr, hc, hptr) = optimized_patterns_for(ocp, scheme, L, E.structure)
+    else:
+        jr, jc, jptr = pat.jacobian_pattern(L, pattern_mode)
+        hr, hc, hptr = pat.hessian_pattern(L, pattern_mode)
     B, CB = L.step_block, L.cblock
     nvar = L.nvar
 
@@ -311,8 +324,11 @@ def build_step_element(ocp: OCP, scheme: str, pattern_mode: str = "reference") -
             wa, wb = which(a), which(b)
             if wb == "v":
                 kv1, kv2 = a - L.n_own - L.n_next, b - L.n_own - L.n_next
-                if expr != 0:
+                in_pattern = pat.find_pos(hr, hptr, nvar - nv + kv1 + 1, nvar - nv + kv2 + 1) >= 0
+                if expr != 0 and in_pattern:
                     E.h_vv.append((kv1, kv2, kv1 * (kv1 + 1) // 2 + kv2, expr))
+                elif expr != 0:
+                    E.dropped.append(("H", a, b))
                 continue
             offs = []
             for i in (PROBE_I, PROBE_I + 1):
@@ -330,6 +346,8 @@ def build_step_element(ocp: OCP, scheme: str, pattern_mode: str = "reference") -
                 E.h_own.append((a, b, offs[0], expr))       # owner writes every slot, zeros included
             elif expr != 0:
                 E.h_next.append((a, b, offs[0], expr))      # accumulated into the next block
+    E.h_vv_table = [(k1, k2, k1 * (k1 + 1) // 2 + k2) for k1 in range(nv) for k2 in range(k1 + 1)
+                    if pat.find_pos(hr, hptr, nvar - nv + k1 + 1, nvar - nv + k2 + 1) >= 0]
     # coverage: every slot of an interior column block must be written by its owner / the previous step
     jslots = sorted([e[2] for e in E.j_own] + [e[2] for e in E.j_next])
     assert jslots == list(range(E.j_block)), (scheme, jslots, E.j_block)
@@ -353,6 +371,105 @@ def build_step_element(ocp: OCP, scheme: str, pattern_mode: str = "reference") -
                 else:
                     E.g_v.append((a, a, a - L.n_own - L.n_next, expr))
     return E
+
+
+def _fpath_symbols(ocp: OCP, scheme: str, L, ts, p):
+    """Local variables and rows of the final-path element (see build_final_path)."""
+    d = L.dims
+    nx, nu, nv = d.nx, d.nu, d.nv
+    cb = L.control_block
+    nloc = cb + nx + nv
+    z = [sp.Symbol(f"z{a}") for a in range(nloc)]
+    v = z[cb + nx:]
+    if scheme == "trapeze":
+        x, ublk = z[0:nx], z[nx:nx + nu]
+    else:
+        ublk, x = z[0:cb], z[cb:cb + nx]
+    if L.stagewise:
+        _, Bw, _ = butcher_symbols(L.stage)
+        u = [sum(Bw[j] * ublk[j * nu + k] for j in range(L.stage)) for k in range(nu)]
+    else:
+        u = ublk
+    rows = [sp.sympify(e) for e in ocp.path(ts.ti, x, u, v, p)] if d.np else []
+    return z, rows
+
+
+def _fpath_gcol(L, scheme, a):
+    """1-based global column of local variable a of the final-path element."""
+    d, N, B = L.dims, L.N, L.step_block
+    cb = L.control_block
+    nl = cb + d.nx
+    if a >= nl:
+        return L.nvar - d.nv + (a - nl) + 1
+    if scheme == "trapeze":
+        return N * B + a + 1
+    if a < cb:
+        return (N - 1) * B + d.nx + a + 1
+    return N * B + (a - cb) + 1
+
+
+def _bc_symbols(ocp: OCP, L, p):
+    d = L.dims
+    nx, nv = d.nx, d.nv
+    nloc = 2 * nx + nv
+    z = [sp.Symbol(f"z{a}") for a in range(nloc)]
+    x0, xf, v = z[0:nx], z[nx:2 * nx], z[2 * nx:]
+    rows = [sp.sympify(e) for e in ocp.boundary(x0, xf, v, p)] if d.nb else []
+    cost = sp.sympify(ocp.mayer(x0, xf, v, p)) if ocp.mayer else sp.Integer(0)
+    return z, rows, cost
+
+
+def _bc_gcol(L, a):
+    d, N, B = L.dims, L.N, L.step_block
+    if a < d.nx:
+        return a + 1
+    if a < 2 * d.nx:
+        return N * B + (a - d.nx) + 1
+    return L.nvar - d.nv + (a - 2 * d.nx) + 1
+
+
+def detect_structure(ocp: OCP, scheme: str, L, E):
+    """Structural (":optimized") sparsity of the three element kinds, by tracing (gen/trace.py)."""
+    d = L.dims
+    nvo = L.n_own + L.n_next
+    env = tr.make_env(E.z, E.ts, nvo, d.nv, E.inter)
+    step_J, lag = [], tr.EMPTY
+    for r, e in enumerate(E.rows_traced):
+        t = tr.trace_expr(e, env)
+        step_J += [(r, a) for a in sorted(t[0])]
+        lag = tr._join(lag, t)
+    lag = tr._join(lag, tr.trace_expr(E.cost_traced, env))
+    step_H = sorted(tuple(sorted(q)) if len(q) == 2 else (min(q), min(q)) for q in lag[1])
+    # final path element
+    zf, rows_f = _fpath_symbols(ocp, scheme, L, E.ts, E.p)
+    envf = tr.make_env(zf, TimeSyms(E.ts.ti, E.ts.tp, E.ts.h, E.ts.dti, {}, {}), L.control_block + d.nx, d.nv)
+    fp_J, lagf = [], tr.EMPTY
+    for r, e in enumerate(rows_f):
+        t = tr.trace_expr(e, envf)
+        fp_J += [(r, a) for a in sorted(t[0])]
+        lagf = tr._join(lagf, t)
+    fp_H = sorted(tuple(sorted(q)) if len(q) == 2 else (min(q), min(q)) for q in lagf[1])
+    # boundary + Mayer element (no time dependence)
+    zb, rows_b, cost_b = _bc_symbols(ocp, L, E.p)
+    envb = {s: (frozenset([a]), frozenset()) for a, s in enumerate(zb)}
+    bc_J, lagb = [], tr.EMPTY
+    for r, e in enumerate(rows_b):
+        t = tr.trace_expr(e, envb)
+        bc_J += [(r, a) for a in sorted(t[0])]
+        lagb = tr._join(lagb, t)
+    lagb = tr._join(lagb, tr.trace_expr(cost_b, envb))
+    bc_H = sorted(tuple(sorted(q)) if len(q) == 2 else (min(q), min(q)) for q in lagb[1])
+    return dict(step_J=step_J, step_H=step_H, fp_J=fp_J, fp_H=fp_H, bc_J=bc_J, bc_H=bc_H)
+
+
+def optimized_patterns_for(ocp: OCP, scheme: str, L, S):
+    """CSC patterns of layout L from the detected structure S (detect_structure)."""
+    d, N, cb = L.dims, L.N, L.cblock
+    extra_J = [(N * cb + r + 1, _fpath_gcol(L, scheme, a)) for (r, a) in S["fp_J"]]
+    extra_J += [(L.ncon - d.nb + r + 1, _bc_gcol(L, a)) for (r, a) in S["bc_J"]]
+    extra_H = [(_fpath_gcol(L, scheme, a), _fpath_gcol(L, scheme, b)) for (a, b) in S["fp_H"]]
+    extra_H += [(_bc_gcol(L, a), _bc_gcol(L, b)) for (a, b) in S["bc_H"]]
+    return pat.optimized_patterns(L, S["step_J"], S["step_H"], extra_J, extra_H)
 
 
 @dataclass
@@ -393,18 +510,19 @@ def build_final_path(ocp: OCP, scheme: str, E: StepElement) -> EdgeElement:
     ts = E.ts
     rows = [sp.sympify(e) for e in ocp.path(ts.ti, x, u, v, E.p)] if d.np else []
     D = Differ(z, cb + nx, nv, TimeSyms(ts.ti, ts.tp, ts.h, ts.dti, {}, {}))
+    S = E.structure   # detected structure: its entries are listed even where the derivative vanishes
     jac, hess = [], []
     for r, e in enumerate(rows):
         for a in range(nloc):
             ex = D.d(e, a)
-            if ex != 0:
+            if ex != 0 or (S and (r, a) in S["fp_J"]):
                 jac.append((r, a, r * nloc + a, ex))
     lagr = sum(lam[r] * rows[r] for r in range(len(rows)))
     g = [D.d(lagr, a) for a in range(nloc)]
     for a in range(nloc):
         for b in range(a + 1):
             ex = D.d(g[a], b)
-            if ex != 0:
+            if ex != 0 or (S and (b, a) in S["fp_H"]):
                 hess.append((a, b, a * (a + 1) // 2 + b, ex))
     return EdgeElement("fpath", nloc, len(rows), z, lam, rows, sp.Integer(0), jac, hess, [])
 
@@ -420,17 +538,18 @@ def build_boundary(ocp: OCP, E: StepElement) -> EdgeElement:
     rows = [sp.sympify(e) for e in ocp.boundary(x0, xf, v, E.p)] if d.nb else []
     cost = sp.sympify(ocp.mayer(x0, xf, v, E.p)) if ocp.mayer else sp.Integer(0)
     jac, hess, grad = [], [], []
+    S = E.structure
     for r, e in enumerate(rows):
         for a in range(nloc):
             ex = sp.diff(e, z[a])
-            if ex != 0:
+            if ex != 0 or (S and (r, a) in S["bc_J"]):
                 jac.append((r, a, r * nloc + a, ex))
     lagr = sum(lam[r] * rows[r] for r in range(len(rows))) + E.sg * cost
     g = [sp.diff(lagr, z[a]) for a in range(nloc)]
     for a in range(nloc):
         for b in range(a + 1):
             ex = sp.diff(g[a], z[b])
-            if ex != 0:
+            if ex != 0 or (S and (b, a) in S["bc_H"]):
                 hess.append((a, b, a * (a + 1) // 2 + b, ex))
         ex = sp.diff(cost, z[a])
         if ex != 0:

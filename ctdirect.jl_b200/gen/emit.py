@@ -19,7 +19,7 @@ from sympy.printing.precedence import PRECEDENCE
 
 from . import elements as el
 from . import patterns as pat
-from .ocps import OCP
+from .ocps import OCP, ZERO
 
 
 class CudaPrinter(C99CodePrinter):
@@ -106,7 +106,8 @@ def _named(prefix, n):
 def _dyn_lines(ocp: OCP, tag, tname, xnames, unames, vsyms, psyms):
     """C lines computing {tag}f0.. = dynamics(t, x, u, v) with named inputs."""
     t = sp.Symbol(tname)
-    f = ocp.dynamics(t, [sp.Symbol(n) for n in xnames], [sp.Symbol(n) for n in unames], vsyms, psyms)
+    f = [sp.sympify(e).subs(ZERO, 0) for e in
+         ocp.dynamics(t, [sp.Symbol(n) for n in xnames], [sp.Symbol(n) for n in unames], vsyms, psyms)]
     lines, outs = cse_block(f, f"{tag}w")
     for k, o in enumerate(outs):
         lines.append(f"const double {tag}f{k} = {o};")
@@ -199,7 +200,7 @@ def emit_pair(ocp: OCP, scheme: str, pattern_mode: str = "reference") -> str:
     L = E.L
     d = L.dims
     s = L.stage
-    name = struct_name(ocp.name, scheme) + ("" if pattern_mode == "reference" else "__corrected")
+    name = struct_name(ocp.name, scheme) + ("" if pattern_mode == "reference" else "__" + pattern_mode)
     scheme_id = list(pat.SCHEMES).index(scheme)
     o = []
     o.append(f"// AUTO-GENERATED by ctdirect.jl_b200/gen/generate.py for problem '{ocp.name}', scheme '{scheme}',\n"
@@ -207,7 +208,7 @@ def emit_pair(ocp: OCP, scheme: str, pattern_mode: str = "reference") -> str:
     o.append("namespace ctd_gen {\n")
     o.append(f"struct {name} {{\n")
     o.append(f"  static constexpr const char* PROBLEM = \"{ocp.name}\";\n  static constexpr const char* SCHEME = \"{scheme}\";\n")
-    o.append(f"  static constexpr int SCHEME_ID = {scheme_id}, PATTERN_MODE = {0 if pattern_mode == 'reference' else 1};\n")
+    o.append(f"  static constexpr int SCHEME_ID = {scheme_id}, PATTERN_MODE = {['reference', 'corrected', 'optimized'].index(pattern_mode)};\n")
     o.append(f"  static constexpr int NX = {d.nx}, NU = {d.nu}, NV = {d.nv}, NP = {d.np}, NB = {d.nb}, NPAR = {ocp.npar}, STAGE = {s};\n")
     b = lambda x: "true" if x else "false"
     o.append(f"  static constexpr bool FREE_T0 = {b(ocp.free_t0)}, FREE_TF = {b(ocp.free_tf)}, LAGRANGE = {b(d.lagrange)}, "
@@ -229,6 +230,12 @@ def emit_pair(ocp: OCP, scheme: str, pattern_mode: str = "reference") -> str:
     o.append(_table("J_V", [(r, a - L.n_own - L.n_next, off) for (r, a, off, _) in E.j_v]))
     o.append(_table("H_OWN", E.h_own))
     o.append(_table("H_NEXT", E.h_next))
+    o.append(_table("H_VV", E.h_vv_table))
+    # detected structure (":optimized" pattern mode only): local (row, variable) / (variable, variable) lists
+    S = E.structure or {}
+    for nm, key in (("S_STEP_J", "step_J"), ("S_STEP_H", "step_H"), ("S_FP_J", "fp_J"), ("S_FP_H", "fp_H"),
+                    ("S_BC_J", "bc_J"), ("S_BC_H", "bc_H")):
+        o.append(_table(nm, [(a, b, 0) for (a, b) in S.get(key, [])]))
     o.append(_table("FP_J", FP.jac))
     o.append(_table("FP_H", FP.hess))
     o.append(_table("BC_J", BC.jac))

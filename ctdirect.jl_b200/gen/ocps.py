@@ -21,6 +21,11 @@ import sympy as sp
 
 INF = float("inf")
 
+# A structural zero: `u * ZERO` is numerically 0 but keeps its dependency on u for sparsity DETECTION
+# (the reference's @def Goddard writes the dynamics as F0(x) + u*F1(x) with F1 = [0, Tmax/m, -b*Tmax],
+# test/problems/goddard.jl:7-15,32, and the tracer of the `:optimized` backend does not look at values).
+ZERO = sp.Symbol("CTD_STRUCT_ZERO")
+
 
 @dataclass
 class OCP:
@@ -85,11 +90,17 @@ def _goddard_dyn(t, x, u, v, p):
     return [vel, -D / m - 1 / r**2 + u[0] * Tmax / m, -b * Tmax * u[0]]
 
 
+def _goddard_def_dyn(t, x, u, v, p):
+    """F0(x) + u*F1(x) of the @def version: the first component keeps a structural dependency on u."""
+    f = _goddard_dyn(t, x, u, v, p)
+    return [f[0] + u[0] * ZERO, f[1], f[2]]
+
+
 _GODDARD_PARAMS = [("Cd", 310.0), ("beta", 500.0), ("b", 2.0), ("Tmax", 3.5)]
 
 goddard = OCP(
     name="goddard", nx=3, nu=1, nv=1, params=_GODDARD_PARAMS, t0=("const", 0.0), tf=("var", 0),
-    dynamics=_goddard_dyn,
+    dynamics=_goddard_def_dyn,
     mayer=lambda x0, xf, v, p: xf[0], criterion="max",
     boundary=lambda x0, xf, v, p: [x0[0], x0[1], x0[2], xf[2]],
     bc_lb=[1.0, 0.0, 1.0, 0.6], bc_ub=[1.0, 0.0, 1.0, 0.6],

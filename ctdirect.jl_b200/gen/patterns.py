@@ -197,3 +197,32 @@ def find_pos(rows, colptr, r, c):
     if k < b and rows[k] == r:
         return int(k)
     return -1
+
+
+def optimized_patterns(L: Layout, step_J, step_H, extra_J, extra_H):
+    """`:optimized` (detected) patterns assembled from per-element structure: `step_J` = [(row r, local a)],
+    `step_H` = [(local a, local b)] of one time step; `extra_*` = global 1-based (i, j) entries of the
+    final-path and boundary(+Mayer) elements.  Returns the same CSC triples as the manual builders."""
+    d, N, B, cb = L.dims, L.N, L.step_block, L.cblock
+    nloc = L.n_own + L.n_next
+
+    def gcol(i, a):
+        return (i - 1) * B + a + 1 if a < nloc else L.nvar - d.nv + (a - nloc) + 1
+
+    TJ, TH = _Triplets(), _Triplets()
+    for i in range(1, N + 1):
+        for (r, a) in step_J:
+            TJ.one((i - 1) * cb + r + 1, gcol(i, a))
+        for (a, b) in step_H:
+            TH.one(gcol(i, a), gcol(i, b))
+            TH.one(gcol(i, b), gcol(i, a))
+    for (i, j) in extra_J:
+        TJ.one(i, j)
+    for (i, j) in extra_H:
+        TH.one(i, j)
+        TH.one(j, i)
+    if not TH.i:                       # no second-order term at all: empty pattern
+        hz = (np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64), np.zeros(L.nvar + 1, dtype=np.int64))
+    else:
+        hz = TH.csc(L.nvar, lower=True)
+    return TJ.csc(L.nvar), hz

@@ -41,6 +41,9 @@ typedef struct ctd_model_s* ctd_handle;
 /* pattern_mode */
 #define CTD_PATTERN_REFERENCE 0 /* bit-exact `:manual` patterns of the reference, quirks included */
 #define CTD_PATTERN_CORRECTED 1 /* adds the entries the reference omits        */
+#define CTD_PATTERN_OPTIMIZED 2 /* detected structural pattern (the reference's `:optimized` backend:
+                                   SparseConnectivityTracer over the closures, collocation.jl:131-134);
+                                   compiled for a subset of the (problem, scheme) pairs            */
 
 /* output selection bits of ctd_eval / ctd_eval_dev */
 #define CTD_CONS 1

@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "hdual.hpp"
+#include "tracer.hpp"
 #include "problems.hpp"
 
 namespace oracle {
@@ -174,6 +175,31 @@ struct SeedAcc {
     }
 };
 
+// same local seeding as SeedAcc, for the sparsity tracer (pattern_mode 2, ":optimized")
+template <int NL>
+struct TraceAcc {
+    using T = Tracer<NL>;
+    const double* x;
+    int nr = 0;
+    int start[4], len[4], dir0[4];
+    void add_range(int s, int l) {
+        if (l <= 0) return;
+        dir0[nr] = nr == 0 ? 0 : dir0[nr - 1] + len[nr - 1];
+        start[nr] = s; len[nr] = l; ++nr;
+    }
+    int ndir() const { return nr == 0 ? 0 : dir0[nr - 1] + len[nr - 1]; }
+    int global_of(int d) const {
+        for (int r = 0; r < nr; ++r)
+            if (d >= dir0[r] && d < dir0[r] + len[r]) return start[r] + (d - dir0[r]);
+        return -1;
+    }
+    T operator()(int j) const {
+        for (int r = 0; r < nr; ++r)
+            if (j >= start[r] && j < start[r] + len[r]) return T::variable(0.0, dir0[r] + (j - start[r]));
+        return T(0.0);
+    }
+};
+
 // ---------------------------------------------------------------------------
 // The discretised problem.  DOCP struct + scheme constructors:
 // src/DOCP_data.jl:176-214 (time), 293-365 (DOCP), trapeze.jl:14-42,
@@ -198,7 +224,7 @@ struct Docp {
     std::vector<double> params;
     ProblemMeta meta;
     Butcher bt;
-    int pattern_mode = 0;          // 0 = reference (quirks Q1-Q4 kept), 1 = corrected
+    int pattern_mode = 0;          // 0 = reference (quirks Q1-Q4 kept), 1 = corrected, 2 = optimized (detected)
     int nvar = 0, ncon = 0;
 
     Docp(int grid_size, const double* time_grid, int n_time_grid, const double* par, int npar, int pmode) {
@@ -514,8 +540,87 @@ struct Docp {
 
     // ----- sparsity patterns (1-based, as the reference builds them) ---------------------------
     // trapeze.jl:149-233, midpoint.jl:163-233, irk.jl:315-416, irk_stagewise.jl:468-558
+    // ----- ":optimized" patterns: structural detection by tracing the restated functions piece by piece,
+    // the way ADNLPModels' default backend traces the reference's closures (collocation.jl:131-134) -----
+    template <int NL>
+    void trace_rows(const TraceAcc<NL>& a, const Tracer<NL>* c, int nrows, int64_t row0, TripletList* J) const {
+        if (!J) return;
+        for (int r = 0; r < nrows; ++r)
+            for (int d = 0; d < a.ndir(); ++d)
+                if (c[r].dep(d)) J->add(row0 + r + 1, a.global_of(d) + 1);
+    }
+    template <int NL>
+    void trace_lag(const TraceAcc<NL>& a, const Tracer<NL>& l, TripletList* H) const {
+        if (!H) return;
+        for (int d1 = 0; d1 < a.ndir(); ++d1)
+            for (int d2 = 0; d2 < a.ndir(); ++d2)
+                if (l.pair(d1, d2)) H->add(a.global_of(d1) + 1, a.global_of(d2) + 1);
+    }
+    void detect(TripletList* J, TripletList* H) const {
+        for (int i = 1; i <= N; ++i) {
+            TraceAcc<NL_STEP> a;
+            a.x = nullptr;
+            a.add_range(state_off(i), step_block + nx + (SCH == TRAPEZE ? nu : 0));
+            a.add_range(v_off(), nv);
+            Tracer<NL_STEP> c[cblock > 0 ? cblock : 1];
+            step_state_eqs(a, i, c);
+            if (np > 0) path_at(a, i, c + eqs_block);
+            trace_rows(a, c, cblock, (int64_t)(i - 1) * cblock, J);
+            Tracer<NL_STEP> l(0.0);
+            for (int r = 0; r < cblock; ++r) l = l + c[r];
+            if (P::has_lagrange && SCH != TRAPEZE) l = l + lagrange_step(a, i);
+            trace_lag(a, l, H);
+        }
+        if constexpr (SCH == TRAPEZE) {
+            if (P::has_lagrange)
+                for (int i = 1; i <= N + 1; ++i) {
+                    TraceAcc<NL_NODE> a;
+                    a.x = nullptr;
+                    a.add_range(state_off(i), nx + nu);
+                    a.add_range(v_off(), nv);
+                    trace_lag(a, lagrange_node_trapeze(a, i), H);
+                }
+        }
+        if constexpr (np > 0) {
+            TraceAcc<NL_NODE> a;
+            a.x = nullptr;
+            if (SCH == TRAPEZE) a.add_range(state_off(N + 1), nx + nu);
+            else {
+                a.add_range(control_off(N), control_block);
+                a.add_range(state_off(N + 1), nx);
+            }
+            a.add_range(v_off(), nv);
+            Tracer<NL_NODE> c[np];
+            path_at(a, N + 1, c);
+            trace_rows(a, c, np, (int64_t)N * cblock, J);
+            Tracer<NL_NODE> l(0.0);
+            for (int r = 0; r < np; ++r) l = l + c[r];
+            trace_lag(a, l, H);
+        }
+        {
+            TraceAcc<NL_BC> a;
+            a.x = nullptr;
+            a.add_range(state_off(1), nx);
+            a.add_range(state_off(N + 1), nx);
+            a.add_range(v_off(), nv);
+            Tracer<NL_BC> l(0.0);
+            if constexpr (nb > 0) {
+                Tracer<NL_BC> c[nb];
+                boundary(a, c);
+                trace_rows(a, c, nb, ncon - nb, J);
+                for (int r = 0; r < nb; ++r) l = l + c[r];
+            }
+            if (P::has_mayer) l = l + mayer(a);
+            trace_lag(a, l, H);
+        }
+    }
+
     Pattern jacobian_pattern() const {
         TripletList L;
+        if (pattern_mode == 2) {
+            detect(&L, nullptr);
+            return L.build(ncon, nvar, false);
+        }
         const int64_t v_start = nvar - nv + 1, v_end = nvar;
         const int64_t B = step_block;
         for (int64_t i = 1; i <= N; ++i) {
@@ -583,6 +688,10 @@ struct Docp {
     // trapeze.jl:240-303, midpoint.jl:240-300, irk.jl:423-496, irk_stagewise.jl:565-638; then tril [3P]
     Pattern hessian_pattern() const {
         TripletList L;
+        if (pattern_mode == 2) {
+            detect(nullptr, &L);
+            return L.build(nvar, nvar, true);
+        }
         const int64_t v_start = nvar - nv + 1, v_end = nvar;
         const int64_t B = step_block;
         L.add_block(v_start, v_end, v_start, v_end);

@@ -21,7 +21,7 @@ _ip = C.POINTER(C.c_int64)
 
 def build(force: bool = False) -> str:
     """Compile the oracle (gcc only; no GPU, no reference sources needed)."""
-    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "docp_oracle.hpp", "problems.hpp", "hdual.hpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "docp_oracle.hpp", "problems.hpp", "hdual.hpp", "tracer.hpp")]
     if (
         force
         or not os.path.exists(_LIB_PATH)
@@ -75,7 +75,7 @@ class OracleModel:
         lib = _load()
         tg = None if time_grid is None else np.ascontiguousarray(time_grid, dtype=np.float64)
         par = None if params is None else np.ascontiguousarray(params, dtype=np.float64)
-        pm = {"reference": 0, "corrected": 1}[pattern_mode]
+        pm = {"reference": 0, "corrected": 1, "optimized": 2}[pattern_mode]
         self._h = lib.orc_create(problem.encode(), scheme.encode(), int(grid_size), _p(tg),
                                  0 if tg is None else len(tg), _p(par), 0 if par is None else len(par), pm)
         if not self._h:

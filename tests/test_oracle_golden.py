@@ -11,6 +11,39 @@ def test_goddard_midpoint_manual_counts(oracle_mod):
     assert (m.nvar, m.ncon) == (250 * 4 + 3 + 1, 250 * 3 + 4)
 
 
+def test_goddard_midpoint_optimized_counts(oracle_mod):
+    # test/ci/test_modeler_solver.jl:32 documents the DETECTED pattern of the default `:optimized` backend
+    # (SparseConnectivityTracer over the closures): nnzj 4504, nnzh 5259 for Goddard / midpoint / N = 250.
+    # The oracle re-derives it with an operator-overloading tracer over the restated functions.
+    m = oracle_mod.OracleModel("goddard", "midpoint", 250, pattern_mode="optimized")
+    assert (m.nnzj, m.nnzh) == (4504, 5259)
+    assert (m.nnzj, m.nnzh) == (18 * 250 + 4, 21 * 250 + 9)        # SURVEY.md §8c closed forms
+
+
+@pytest.mark.parametrize("N,nnzh_opt", [(1000, 11011), (10000, 110011)])
+def test_goddard_all_trapeze_optimized_hessian_archive_counts(oracle_mod, N, nnzh_opt):
+    # test/archives/AD_backend.md:57-64: "Hess nnz 11011 (opt)" at N = 1000, 110011 at N = 10000.
+    # (The archived optimized Jacobian counts 28011 / 280011 were produced with the older F0 + u*F1
+    # formulation of goddard_all, whose `u*0` terms add 2 detected entries per step; the functional
+    # version in test/problems/goddard.jl:87-158 gives 26011 / 260011.)
+    m = oracle_mod.OracleModel("goddard_all", "trapeze", N, pattern_mode="optimized")
+    assert m.nnzh == nnzh_opt
+    assert m.nnzj == 26 * N + 11
+
+
+def test_optimized_pattern_contains_every_nonzero_derivative(oracle_mod):
+    rng = np.random.default_rng(4)
+    for prob, scheme in (("goddard", "midpoint"), ("goddard_all", "trapeze"), ("robot", "gauss_legendre_2"),
+                         ("vanderpol", "gauss_legendre_3")):
+        m = oracle_mod.OracleModel(prob, scheme, 7, pattern_mode="optimized")
+        man = oracle_mod.OracleModel(prob, scheme, 7, pattern_mode="corrected")
+        x = m.x0() * (1 + 1e-2 * rng.uniform(-1, 1, m.nvar))
+        y = rng.standard_normal(m.ncon)
+        m.derivs(x, y, 0.7)
+        assert m.dropped == (0, 0), (prob, scheme, m.dropped)      # no nonzero value falls outside the pattern
+        assert m.nnzj <= man.nnzj and m.nnzh <= man.nnzh
+
+
 @pytest.mark.parametrize("N,nvar,ncon,nnzh,nnzj_ref,nnzj_corr", [
     (1000, 4005, 6007, 30024, 39043, 42043),      # test/archives/AD_backend.md:57-64
     (10000, 40005, 60007, 300024, 390043, 420043),
