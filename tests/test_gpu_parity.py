@@ -96,6 +96,29 @@ def test_baseline_configs_full_size(ctd, oracle_mod, problem, scheme, N):
             assert np.array_equal(r[k], r2[k]), f"{k} not reproducible bit for bit"
 
 
+def test_detected_pattern_full_size(ctd, oracle_mod):
+    """`:optimized` pattern at BASELINE size: same values as the manual pattern where both have an entry,
+    every entry the manual pattern adds on top is a structural zero."""
+    N = 100_000
+    o = oracle_mod.OracleModel("goddard", "midpoint", N, pattern_mode="optimized")
+    d = ctd.DOCP("goddard", N, "midpoint", pattern_mode="optimized")
+    assert (d.nnzj, d.nnzh) == (18 * N + 4, 21 * N + 9)
+    x, y = synthetic_point(o)
+    r = _compare_all(ctd, o, d, x, y, 1.0, "goddard/midpoint/optimized/N=1e5")
+    dm = ctd.DOCP("goddard", N, "midpoint")
+    rm = dm.nlp_model().eval_all(x, y, obj_weight=1.0)
+    for key, (ro, co), (rmn, cmn) in (("jac", d.jacobian_structure(), dm.jacobian_structure()),
+                                      ("hess", d.hessian_structure(), dm.hessian_structure())):
+        ko = co.astype(np.int64) * (1 << 32) + ro
+        km = cmn.astype(np.int64) * (1 << 32) + rmn
+        pos = np.searchsorted(km, ko)
+        assert np.array_equal(km[pos], ko)                      # the detected pattern is a subset
+        assert np.array_equal(rm[key][pos], r[key])             # same numbers, bit for bit
+        rest = np.ones(len(km), dtype=bool)
+        rest[pos] = False
+        assert np.all(rm[key][rest] == 0.0)
+
+
 def test_jacobian_directional_derivative_full_size(ctd):
     """J(x) d against central differences of c at grid size 1e5 (independent of the oracle)."""
     d = ctd.DOCP("goddard", 100_000, "midpoint")
