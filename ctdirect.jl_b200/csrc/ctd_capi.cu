@@ -63,10 +63,15 @@ int ctd_create(const ctd_desc* d, ctd_handle* out) {
     return guarded([&] {
         const Registration* reg = nullptr;
         bool scheme_known = false, problem_known = false;
+        // scheme aliases of the reference's switch (src/DOCP_data.jl:315-320)
+        std::string scheme = d->scheme;
+        if (!scheme.empty() && scheme[0] == ':') scheme = scheme.substr(1);
+        if (scheme == "euler_explicit" || scheme == "euler_forward") scheme = "euler";
+        if (scheme == "euler_backward") scheme = "euler_implicit";
         for (const Registration& r : registry()) {
-            if (r.info.scheme == d->scheme) scheme_known = true;
+            if (r.info.scheme == scheme) scheme_known = true;
             if (r.info.problem == d->problem) problem_known = true;
-            if (r.info.problem == d->problem && r.info.scheme == d->scheme) {
+            if (r.info.problem == d->problem && r.info.scheme == scheme) {
                 if (r.info.pattern_mode == d->pattern_mode) reg = &r;
                 // a pair without quirks is only compiled in reference mode: both manual modes coincide
                 else if (!reg && r.info.pattern_mode == 0 && d->pattern_mode != 2) reg = &r;

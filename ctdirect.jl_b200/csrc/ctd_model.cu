@@ -209,6 +209,7 @@ void Model::build_patterns() {
     const int64_t v0 = nvar_ - nv + 1, v1 = nvar_;
     const bool corrected = f.pattern_mode == 1;
     const bool trapeze = f.scheme == "trapeze", midpoint = f.scheme == "midpoint";
+    const bool euler_e = f.scheme == "euler", euler_i = f.scheme == "euler_implicit";
     BlockPattern J, H;
     H.add(v0, v1, v0, v1);
     for (int64_t i = 1; i <= N; ++i) {
@@ -220,6 +221,25 @@ void Model::build_patterns() {
             J.add(co + 1, co + CB, v0, v1);                     // everything depends on v
             H.add(vo + 1, vo + B + nx, vo + 1, vo + B + nx);
             H.add(vo + 1, vo + B + nx, v0, v1, true);
+        } else if (euler_e || euler_i) {   // euler.jl:166-355
+            const int64_t p0 = co + nx + 1, p1 = co + CB;
+            const int64_t u0 = vo + nx + 1, u1 = vo + nx + nu;
+            J.add(dyn0, dyn1, vo + 1, vo + nx);
+            J.add(dyn0, dyn1, u0, vo + B + nx);
+            J.add(dyn0, dyn1, v0, v1);
+            J.add(p0, p1, vo + 1, vo + nx);
+            J.add(p0, p1, u0, u1);
+            J.add(p0, p1, v0, v1);
+            H.add(u0, u1, u0, u1);
+            H.add(u0, u1, v0, v1, true);
+            if (euler_i) {
+                H.add(vo + B + 1, vo + B + nx, vo + B + 1, vo + B + nx);
+                H.add(vo + B + 1, vo + B + nx, u0, u1, true);
+                H.add(vo + B + 1, vo + B + nx, v0, v1, true);
+            }
+            H.add(vo + 1, vo + nx, vo + 1, vo + nx);
+            H.add(vo + 1, vo + nx, u0, u1, true);
+            H.add(vo + 1, vo + nx, v0, v1, true);
         } else if (trapeze) {
             const int64_t p0 = co + nx + 1, p1 = co + CB;
             J.add(dyn0, dyn1, vo + 1, vo + nx);
@@ -259,7 +279,8 @@ void Model::build_patterns() {
         J.add(bo + 1, bo + nb, 1, nx);
         J.add(bo + 1, bo + nb, xf0, xf1);
         J.add(bo + 1, bo + nb, v0, v1);
-        if (f.stagewise && f.lagrange && !corrected) J.add(ncon_, ncon_, nx, nx);  // irk_stagewise.jl:550-552
+        if ((f.stagewise || euler_e || euler_i) && f.lagrange && !corrected)
+            J.add(ncon_, ncon_, nx, nx);  // irk_stagewise.jl:550-552, euler.jl:257-259
         if (f.irk) {
             H.add(xf0, xf1, xf0, xf1);
             H.add(uf0, uf1, uf0, uf1);
@@ -272,8 +293,8 @@ void Model::build_patterns() {
             }
             H.add(uf0, uf1, v0, v1, true);
             H.add(1, nx, xf0, xf1, true);
-        } else if (midpoint) {
-            H.add(1, nx, xf0, xf1, true);  // midpoint.jl:286-291: unconditional
+        } else if (midpoint || euler_e || euler_i) {
+            H.add(1, nx, xf0, xf1, true);  // midpoint.jl:286-291, euler.jl:345-350: unconditional
         } else if (f.mayer || nb > 0) {
             H.add(1, nx, xf0, xf1, true);  // trapeze.jl:288-295
         }

@@ -24,7 +24,7 @@ from . import _lib
 CONS, JAC, HESS, GRAD, OBJ = 1, 2, 4, 8, 16
 
 SCHEMES = (
-    "trapeze", "midpoint", "gauss_legendre_2", "gauss_legendre_3",
+    "trapeze", "midpoint", "euler", "euler_implicit", "gauss_legendre_2", "gauss_legendre_3",
     "gauss_legendre_1_constant_control", "gauss_legendre_2_constant_control", "gauss_legendre_3_constant_control",
 )
 

@@ -186,6 +186,20 @@ def build_step_element(ocp: OCP, scheme: str, pattern_mode: str = "reference") -
         rows = [xn[k] - (xi[k] + h * f[k]) for k in range(nx)]
         cost = h * lag(tsm, xs, ui)
         u_node = ui
+    elif scheme in ("euler", "euler_implicit"):
+        # euler.jl:79-159: f at (t_i, x_i, U_i) (explicit) or at (t_{i+1}, x_{i+1}, U_i) (implicit)
+        ui = z[nx:nx + nu]
+        if scheme == "euler":
+            f = dyn(ti, xi, ui)
+            cost = h * lag(ti, xi, ui)
+        else:
+            if npc:
+                raise NotImplementedError("implicit Euler with path constraints: node i reads U_{i-1} "
+                                          "(euler.jl:66-69), which the step element does not hold")
+            f = dyn(tp, xn, ui)
+            cost = h * lag(tp, xn, ui)
+        rows = [xn[k] - (xi[k] + h * f[k]) for k in range(nx)]
+        u_node = ui
     elif scheme == "trapeze":
         ui = z[nx:nx + nu]
         un = z[L.n_own + nx:L.n_own + nx + nu]

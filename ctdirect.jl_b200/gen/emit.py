@@ -131,6 +131,14 @@ def _cons_lines(ocp: OCP, E: el.StepElement):
         out += _dyn_lines(ocp, "c_", "m_t", [f"m_x{k}" for k in range(nx)], z[nx:nx + nu], vs, E.p)
         for k in range(nx):
             out.append(f"s.template c<{k}>(CTD_SUB({xn[k]}, CTD_ADD({xi[k]}, CTD_MUL(hh, c_f{k}))));")
+    elif E.scheme in ("euler", "euler_implicit"):
+        # euler.jl:140-159  c = xip1 - (xi + hi*f), f at node i (explicit) or node i+1 (implicit)
+        if E.scheme == "euler":
+            out += _dyn_lines(ocp, "c_", "ti", xi, z[nx:nx + nu], vs, E.p)
+        else:
+            out += _dyn_lines(ocp, "c_", "tp", xn, z[nx:nx + nu], vs, E.p)
+        for k in range(nx):
+            out.append(f"s.template c<{k}>(CTD_SUB({xn[k]}, CTD_ADD({xi[k]}, CTD_MUL(hh, c_f{k}))));")
     elif E.scheme == "trapeze":
         # trapeze.jl:128-140  c = xip1 - (xi + half_hi*(f_i + f_ip1))
         out += _dyn_lines(ocp, "ci_", "ti", xi, z[nx:nx + nu], vs, E.p)

@@ -24,6 +24,8 @@ SCHEMES = {
     "gauss_legendre_3_constant_control": (3, True, False, False),
     "gauss_legendre_2": (2, True, True, False),
     "gauss_legendre_3": (3, True, True, False),
+    "euler": (0, False, False, False),            # explicit Euler, src/ode/euler.jl
+    "euler_implicit": (0, False, False, False),   # implicit Euler, src/ode/euler.jl (explicit=false)
 }
 
 
@@ -108,6 +110,15 @@ def jacobian_pattern(L: Layout, pattern_mode: str = "reference"):
             T.block(dyn0, dyn1, vo + 1, vo + B + nx)
             T.block(co + nx + 1, co + cb, vo + 1, vo + nx + nu)
             T.block(co + 1, co + cb, v0, v1)
+        elif L.scheme in ("euler", "euler_implicit"):
+            # euler.jl:166-262 (the Lagrange-cost lines repeat entries of the dynamics block)
+            p0, p1 = co + nx + 1, co + cb
+            T.block(dyn0, dyn1, vo + 1, vo + nx)
+            T.block(dyn0, dyn1, vo + nx + 1, vo + B + nx)
+            T.block(dyn0, dyn1, v0, v1)
+            T.block(p0, p1, vo + 1, vo + nx)
+            T.block(p0, p1, vo + nx + 1, vo + nx + nu)
+            T.block(p0, p1, v0, v1)
         elif L.scheme == "trapeze":
             p0, p1 = co + nx + 1, co + cb
             T.block(dyn0, dyn1, vo + 1, vo + nx)
@@ -145,8 +156,8 @@ def jacobian_pattern(L: Layout, pattern_mode: str = "reference"):
     T.block(bo + 1, bo + nb, 1, nx)
     T.block(bo + 1, bo + nb, xf0, xf1)
     T.block(bo + 1, bo + nb, v0, v1)
-    if L.stagewise and d.lagrange and pattern_mode == "reference":
-        T.one(L.ncon, nx)  # irk_stagewise.jl:550-552 (quirk Q3)
+    if (L.stagewise or L.scheme in ("euler", "euler_implicit")) and d.lagrange and pattern_mode == "reference":
+        T.one(L.ncon, nx)  # irk_stagewise.jl:550-552, euler.jl:257-259 (quirk Q3)
     return T.csc(L.nvar)
 
 
@@ -161,6 +172,20 @@ def hessian_pattern(L: Layout, pattern_mode: str = "reference"):
         if L.scheme == "midpoint":
             T.block(vo + 1, vo + B + nx, vo + 1, vo + B + nx)
             T.block(vo + 1, vo + B + nx, v0, v1, sym=True)
+        elif L.scheme in ("euler", "euler_implicit"):
+            # euler.jl:269-355
+            x0_, x1_ = vo + 1, vo + nx
+            xn0, xn1 = vo + B + 1, vo + B + nx
+            u0_, u1_ = vo + nx + 1, vo + nx + nu
+            T.block(u0_, u1_, u0_, u1_)
+            T.block(u0_, u1_, v0, v1, sym=True)
+            if L.scheme == "euler_implicit":
+                T.block(xn0, xn1, xn0, xn1)
+                T.block(xn0, xn1, u0_, u1_, sym=True)
+                T.block(xn0, xn1, v0, v1, sym=True)
+            T.block(x0_, x1_, x0_, x1_)
+            T.block(x0_, x1_, u0_, u1_, sym=True)
+            T.block(x0_, x1_, v0, v1, sym=True)
         elif L.scheme == "trapeze":
             T.block(vo + 1, vo + 2 * B, vo + 1, vo + 2 * B)
             T.block(vo + 1, vo + 2 * B, v0, v1, sym=True)
@@ -182,8 +207,8 @@ def hessian_pattern(L: Layout, pattern_mode: str = "reference"):
             T.block(xf0, xf1, v0, v1, sym=True)
         T.block(uf0, uf1, v0, v1, sym=True)
         T.block(1, nx, xf0, xf1, sym=True)
-    elif L.scheme == "midpoint":
-        T.block(1, nx, xf0, xf1, sym=True)  # quirk Q4: always
+    elif L.scheme in ("midpoint", "euler", "euler_implicit"):
+        T.block(1, nx, xf0, xf1, sym=True)  # quirk Q4: always (midpoint.jl:286-291, euler.jl:345-350)
     else:
         if d.mayer or d.nb > 0:
             T.block(1, nx, xf0, xf1, sym=True)

@@ -42,6 +42,8 @@ enum SchemeId {
     GL3_CONST = 4,        // :gauss_legendre_3_constant_control  irk.jl:96-131
     GL2_STAGEWISE = 5,    // :gauss_legendre_2  irk_stagewise.jl
     GL3_STAGEWISE = 6,    // :gauss_legendre_3  irk_stagewise.jl
+    EULER_EXPLICIT = 7,   // :euler | :euler_explicit | :euler_forward   src/ode/euler.jl
+    EULER_IMPLICIT = 8,   // :euler_implicit | :euler_backward           src/ode/euler.jl
 };
 
 inline int scheme_from_name(const std::string& s) {
@@ -53,6 +55,8 @@ inline int scheme_from_name(const std::string& s) {
     if (s == "gauss_legendre_3_constant_control") return GL3_CONST;
     if (s == "gauss_legendre_2") return GL2_STAGEWISE;
     if (s == "gauss_legendre_3") return GL3_STAGEWISE;
+    if (s == "euler" || s == "euler_explicit" || s == "euler_forward") return EULER_EXPLICIT;   // DOCP_data.jl:315
+    if (s == "euler_implicit" || s == "euler_backward") return EULER_IMPLICIT;                  // DOCP_data.jl:318
     return -1;
 }
 
@@ -64,6 +68,8 @@ template <> struct SchemeTraits<GL2_CONST> { static constexpr int stage = 2; sta
 template <> struct SchemeTraits<GL3_CONST> { static constexpr int stage = 3; static constexpr bool irk = true, stagewise = false, final_control = false; };
 template <> struct SchemeTraits<GL2_STAGEWISE> { static constexpr int stage = 2; static constexpr bool irk = true, stagewise = true, final_control = false; };
 template <> struct SchemeTraits<GL3_STAGEWISE> { static constexpr int stage = 3; static constexpr bool irk = true, stagewise = true, final_control = false; };
+template <> struct SchemeTraits<EULER_EXPLICIT> { static constexpr int stage = 0; static constexpr bool irk = false, stagewise = false, final_control = false; };
+template <> struct SchemeTraits<EULER_IMPLICIT> { static constexpr int stage = 0; static constexpr bool irk = false, stagewise = false, final_control = false; };
 
 // Butcher tableaux, computed from the same expressions as irk.jl:41-43,78-80,116-122
 struct Butcher {
@@ -279,7 +285,11 @@ struct Docp {
     // generic: common.jl:140-155; stagewise: b-weighted average irk_stagewise.jl:197-205
     template <class Acc> void get_control(const Acc& a, int i, typename Acc::T* u) const {
         using T = typename Acc::T;
-        if constexpr (ST::stagewise) {
+        if constexpr (SCH == EULER_IMPLICIT) {
+            // euler.jl:66-69: u(]t_i, t_i+1]) = U_i, u(t_1) = U_1  =>  node i reads U_{i-1} (U_1 for i = 1)
+            if (i == 1) i = 2;
+            load(a, (i - 2) * step_block + nx, nu, u);
+        } else if constexpr (ST::stagewise) {
             if (i == N + 1) i = N;
             for (int k = 0; k < nu; ++k) u[k] = bt.b[0] * a(stagecontrol_off(i, 1) + k);
             for (int j = 2; j <= s; ++j)
@@ -318,6 +328,19 @@ struct Docp {
             load(a, control_off(i), nu, u);
             P::template dynamics<T>(f, ts, xs, u, v, p);
             T hi = (tip1 - ti) / 1.0;  // control_steps == 1
+            for (int k = 0; k < nx; ++k) c[k] = xip1[k] - (xi[k] + hi * f[k]);
+        } else if constexpr (SCH == EULER_EXPLICIT || SCH == EULER_IMPLICIT) {
+            // setWorkArray euler.jl:79-104 (f at node i, or at node i+1 for the implicit rule) +
+            // stepStateConstraints! euler.jl:140-159
+            T u[nu > 0 ? nu : 1], f[nx];
+            if constexpr (SCH == EULER_EXPLICIT) {
+                get_control(a, i, u);
+                P::template dynamics<T>(f, ti, xi, u, v, p);
+            } else {
+                get_control(a, i + 1, u);
+                P::template dynamics<T>(f, tip1, xip1, u, v, p);
+            }
+            T hi = tip1 - ti;
             for (int k = 0; k < nx; ++k) c[k] = xip1[k] - (xi[k] + hi * f[k]);
         } else if constexpr (SCH == TRAPEZE) {
             // setWorkArray trapeze.jl:50-71 + stepStateConstraints! trapeze.jl:118-142
@@ -416,6 +439,19 @@ struct Docp {
             for (int k = 0; k < nx; ++k) xs[k] = 0.5 * (xi[k] + xip1[k]);
             load(a, control_off(i), nu, u);
             return hi * P::template lagrange<T>(ts, xs, u, v, p);
+        } else if constexpr (SCH == EULER_EXPLICIT || SCH == EULER_IMPLICIT) {
+            // integral(): euler.jl:111-133
+            T hi = tip1 - ti;
+            T u[nu > 0 ? nu : 1];
+            if constexpr (SCH == EULER_EXPLICIT) {
+                get_control(a, i, u);
+                return hi * P::template lagrange<T>(ti, xi, u, v, p);
+            } else {
+                T xip1[nx];
+                load(a, state_off(i + 1), nx, xip1);
+                get_control(a, i + 1, u);
+                return hi * P::template lagrange<T>(tip1, xip1, u, v, p);
+            }
         } else {
             T hi = tip1 - ti;
             T u[nu > 0 ? nu : 1], xij[nx];
@@ -633,6 +669,18 @@ struct Docp {
                 L.add_block(dyn_start, dyn_end, xi_start, xip1_end);
                 L.add_block(c_offset + nx + 1, c_offset + cblock, xi_start, ui_end);
                 L.add_block(c_offset + 1, c_offset + cblock, v_start, v_end);
+            } else if constexpr (SCH == EULER_EXPLICIT || SCH == EULER_IMPLICIT) {
+                // euler.jl:166-262 (the Lagrange-cost lines only repeat entries of the dynamics block)
+                const int64_t path_start = c_offset + nx + 1, path_end = c_offset + cblock;
+                const int64_t xi_start = var_offset + 1, xi_end = var_offset + nx;
+                const int64_t ui_start = var_offset + nx + 1, ui_end = var_offset + nx + nu;
+                const int64_t xip1_end = var_offset + B + nx;
+                L.add_block(dyn_start, dyn_end, xi_start, xi_end);
+                L.add_block(dyn_start, dyn_end, ui_start, xip1_end);
+                L.add_block(dyn_start, dyn_end, v_start, v_end);
+                L.add_block(path_start, path_end, xi_start, xi_end);
+                L.add_block(path_start, path_end, ui_start, ui_end);
+                L.add_block(path_start, path_end, v_start, v_end);
             } else if constexpr (SCH == TRAPEZE) {
                 const int64_t path_start = c_offset + nx + 1, path_end = c_offset + cblock;
                 const int64_t xi_start = var_offset + 1, xi_end = var_offset + nx;
@@ -680,8 +728,9 @@ struct Docp {
             L.add_block(b_offset + 1, b_offset + nb, xf_start, xf_end);
             L.add_block(b_offset + 1, b_offset + nb, v_start, v_end);
         }
-        // irk_stagewise.jl:550-552 stray entry (quirk Q3)
-        if (ST::stagewise && P::has_lagrange && pattern_mode == 0) L.add(ncon, nx);
+        // irk_stagewise.jl:550-552, euler.jl:257-259: stray entry (quirk Q3)
+        if ((ST::stagewise || SCH == EULER_EXPLICIT || SCH == EULER_IMPLICIT) && P::has_lagrange && pattern_mode == 0)
+            L.add(ncon, nx);
         return L.build(ncon, nvar, false);
     }
 
@@ -701,6 +750,21 @@ struct Docp {
                 const int64_t xi_start = var_offset + 1, xip1_end = var_offset + B + nx;
                 L.add_block(xi_start, xip1_end, xi_start, xip1_end);
                 L.add_block(xi_start, xip1_end, v_start, v_end, true);
+            } else if constexpr (SCH == EULER_EXPLICIT || SCH == EULER_IMPLICIT) {
+                // euler.jl:269-355
+                const int64_t xi_start = var_offset + 1, xi_end = var_offset + nx;
+                const int64_t xip1_start = var_offset + B + 1, xip1_end = var_offset + B + nx;
+                const int64_t ui_start = var_offset + nx + 1, ui_end = var_offset + nx + nu;
+                L.add_block(ui_start, ui_end, ui_start, ui_end);
+                L.add_block(ui_start, ui_end, v_start, v_end, true);
+                if (SCH == EULER_IMPLICIT) {
+                    L.add_block(xip1_start, xip1_end, xip1_start, xip1_end);
+                    L.add_block(xip1_start, xip1_end, ui_start, ui_end, true);
+                    L.add_block(xip1_start, xip1_end, v_start, v_end, true);
+                }
+                L.add_block(xi_start, xi_end, xi_start, xi_end);
+                L.add_block(xi_start, xi_end, ui_start, ui_end, true);
+                L.add_block(xi_start, xi_end, v_start, v_end, true);
             } else if constexpr (SCH == TRAPEZE) {
                 const int64_t var_block = B * 2;
                 L.add_block(var_offset + 1, var_offset + var_block, var_offset + 1, var_offset + var_block);
@@ -727,8 +791,8 @@ struct Docp {
             }
             L.add_block(uf_start, uf_end, v_start, v_end, true);
             L.add_block(1, nx, xf_start, xf_end, true);
-        } else if constexpr (SCH == MIDPOINT) {
-            L.add_block(1, nx, xf_start, xf_end, true);  // always (quirk Q4)
+        } else if constexpr (SCH == MIDPOINT || SCH == EULER_EXPLICIT || SCH == EULER_IMPLICIT) {
+            L.add_block(1, nx, xf_start, xf_end, true);  // always (quirk Q4): midpoint.jl:286-291, euler.jl:345-350
         } else {
             if (P::has_mayer || nb > 0) L.add_block(1, nx, xf_start, xf_end, true);
         }

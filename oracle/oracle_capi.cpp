@@ -83,6 +83,8 @@ ModelBase* make_for_problem(int sch, int N, const double* tg, int ntg, const dou
         case GL3_CONST: return new Model<P, GL3_CONST>(N, tg, ntg, par, npar, pm);
         case GL2_STAGEWISE: return new Model<P, GL2_STAGEWISE>(N, tg, ntg, par, npar, pm);
         case GL3_STAGEWISE: return new Model<P, GL3_STAGEWISE>(N, tg, ntg, par, npar, pm);
+        case EULER_EXPLICIT: return new Model<P, EULER_EXPLICIT>(N, tg, ntg, par, npar, pm);
+        case EULER_IMPLICIT: return new Model<P, EULER_IMPLICIT>(N, tg, ntg, par, npar, pm);
     }
     return nullptr;
 }
