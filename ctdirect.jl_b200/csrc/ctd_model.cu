@@ -640,6 +640,8 @@ void Model::eval_dev(int flags, const double* x, const double* y, double sigma, 
     // warps per CTA: large CTAs for a single instance (a 1e5-step grid is one wave and CTA launch rate
     // matters), small CTAs for batches (many waves: resources are released per CTA, and the tiles of
     // an instance rarely fill a large CTA)
+    // (measured: N = 1000 x 4096 instances 78 % -> 94 % of the HBM peak with 3 warps per CTA, whereas a
+    // single 1e6-step grid is faster with 8)
     const int wpc = batch_ > 1 ? std::min(lc.wpc, 3) : lc.wpc;
     int threads = 32 * wpc;
     a.tiles = (N_ >= 3) ? (int)(((int64_t)N_ - 2 + lc.own - 1) / lc.own) : 0;

@@ -8,7 +8,8 @@ problem = sys.argv[1] if len(sys.argv) > 1 else "goddard"
 scheme = sys.argv[2] if len(sys.argv) > 2 else "midpoint"
 N = int(sys.argv[3]) if len(sys.argv) > 3 else 100000
 batch = int(sys.argv[4]) if len(sys.argv) > 4 else 1
-d = ctd.DOCP(problem, N, scheme, batch=batch)
+mode = sys.argv[5] if len(sys.argv) > 5 else "reference"
+d = ctd.DOCP(problem, N, scheme, batch=batch, pattern_mode=mode)
 dev = torch.device("cuda", 0)
 rng = np.random.default_rng(0)
 x0 = d.initial_guess()
@@ -54,4 +55,4 @@ for F in FLAGSETS:
         e1.record(stream)
         torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / K
-    print(f"{problem}/{scheme}/N={N}/B={batch} F={F:2d} {names[F]:14s} {us:9.2f} us  {nb/1e6:8.2f} MB  {nb/us/1e3:8.1f} GB/s  {nb/us/1e3/peak*100:5.1f}% of measured HBM", flush=True)
+    print(f"{problem}/{scheme}/{mode}/N={N}/B={batch} F={F:2d} {names[F]:14s} {us:9.2f} us  {nb/1e6:8.2f} MB  {nb/us/1e3:8.1f} GB/s  {nb/us/1e3/peak*100:5.1f}% of measured HBM", flush=True)
