@@ -20,6 +20,11 @@ class Desc(C.Structure):
     ]
 
 
+class Solution(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("time", "state", "control", "variable", "costate", "path_dual",
+                                          "boundary_dual")]
+
+
 class CtdError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"[ctdirect_b200 {code}] {msg}")
@@ -53,6 +58,8 @@ SIGNATURES = {
     "ctd_norms_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ctd_violation_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "ctd_norms": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ctd_unpack": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.POINTER(Solution)]),
+    "ctd_unpack_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.POINTER(Solution)]),
     "ctd_set_params": (C.c_int, [_H, _dp, C.c_int32]),
     "ctd_sync": (C.c_int, [_H]),
     "ctd_stream": (C.c_void_p, [_H]),

@@ -188,6 +188,22 @@ int ctd_norms(ctd_handle h, const double* x, double* obj, double* viol) {
     return guarded([&] { h->m->norms_host(x, obj, viol); });
 }
 
+int ctd_unpack(ctd_handle h, const double* x, const double* y, const ctd_solution* o) {
+    if (int e = check(h)) return e;
+    if (!o) return fail(-2, "ctd_unpack: NULL output descriptor");
+    return guarded([&] {
+        h->m->unpack_host(x, y, o->time, o->state, o->control, o->variable, o->costate, o->path_dual, o->boundary_dual);
+    });
+}
+
+int ctd_unpack_dev(ctd_handle h, const double* x, const double* y, const ctd_solution* o) {
+    if (int e = check(h)) return e;
+    if (!o) return fail(-2, "ctd_unpack_dev: NULL output descriptor");
+    return guarded([&] {
+        h->m->unpack_dev(x, y, o->time, o->state, o->control, o->variable, o->costate, o->path_dual, o->boundary_dual);
+    });
+}
+
 int ctd_set_params(ctd_handle h, const double* params, int32_t n) {
     if (int e = check(h)) return e;
     return guarded([&] { h->m->set_params(params, n); });

@@ -919,6 +919,86 @@ __global__ void __launch_bounds__(PCfg<E, F>::T) ctd_eval_kernel_parts(const Eva
     publish_reduction<E, F>(a, red, smem + PC::S_RED, &cta_ticket, inst, cta, lane, warp, hvals, grad, PC::P);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Solution unpacking: getter() of src/ode/common.jl:7-104 with the normalisations
+// of build_OCP_solution (src/DOCP_data.jl:514-633).  One thread per time node; outputs are
+// [node][component] (the memory of the getter's matrices), one instance after the other.
+struct UnpackArgs {
+    const double* x;
+    const double* y;          // may be nullptr: primal quantities only
+    double *time, *state, *control, *variable, *costate, *path_dual, *boundary_dual;   // any may be nullptr
+    const double* sgrid;
+    const double* params;
+    long long nvar, ncon;
+    int N;
+};
+
+template <class E>
+__global__ void __launch_bounds__(128) ctd_unpack_kernel(const UnpackArgs a) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x + 1;   // node 1..N+1
+    const long long inst = blockIdx.y;
+    const long long N = a.N;
+    if (i > N + 1) return;
+    const double* __restrict__ x = a.x + inst * a.nvar;
+    const double* __restrict__ y = a.y ? a.y + inst * a.ncon : nullptr;
+    const double* __restrict__ p = a.params + inst * (E::NPAR > 0 ? E::NPAR : 1);
+    double v[E::NV > 0 ? E::NV : 1];
+#pragma unroll
+    for (int k = 0; k < E::NV; ++k) v[k] = __ldg(x + a.nvar - E::NV + k);
+    const double t0 = E::T0_KIND == 0 ? E::T0_CONST : (E::T0_KIND == 1 ? v[E::T0_IDX > 0 ? E::T0_IDX : 0] : p[E::T0_IDX > 0 ? E::T0_IDX : 0]);
+    const double tf = E::TF_KIND == 0 ? E::TF_CONST : (E::TF_KIND == 1 ? v[E::TF_IDX > 0 ? E::TF_IDX : 0] : p[E::TF_IDX > 0 ? E::TF_IDX : 0]);
+    auto tgrid = [&](long long node) { return CTD_ADD(t0, CTD_MUL(__ldg(a.sgrid + node - 1), CTD_SUB(tf, t0))); };
+    if (a.time) a.time[inst * (N + 1) + i - 1] = tgrid(i);
+    if (a.state) {
+#pragma unroll
+        for (int k = 0; k < E::NX; ++k) a.state[(inst * (N + 1) + i - 1) * E::NX + k] = __ldg(x + (i - 1) * E::BLK + k);
+    }
+    if constexpr (E::NU > 0) {
+        if (a.control) {
+            double* out = a.control + (inst * (N + 1) + i - 1) * E::NU;
+            if constexpr (E::STAGEWISE) {
+                // b-weighted average of the stage controls, accumulated left to right (irk_stagewise.jl:197-205)
+                const long long ci = (i == N + 1) ? N : i;
+                const double bw[3] = {E::BB(0), E::BB(1), E::BB(2)};
+#pragma unroll
+                for (int k = 0; k < E::NU; ++k) {
+                    double u = CTD_MUL(bw[0], __ldg(x + (ci - 1) * E::BLK + E::NX + k));
+#pragma unroll
+                    for (int j = 1; j < E::STAGE; ++j) u = CTD_ADD(u, CTD_MUL(bw[j], __ldg(x + (ci - 1) * E::BLK + E::NX + j * E::NU + k)));
+                    out[k] = u;
+                }
+            } else {
+                long long off;
+                if (E::EULER_IMPLICIT) off = ((i == 1 ? 2 : i) - 2) * E::BLK + E::NX;      // euler.jl:66-69
+                else off = (((i == N + 1) && !E::FINAL_CONTROL ? N : i) - 1) * E::BLK + E::NX;   // common.jl:140-155
+#pragma unroll
+                for (int k = 0; k < E::NU; ++k) out[k] = __ldg(x + off + k);
+            }
+        }
+    }
+    if (i == 1 && a.variable) {
+#pragma unroll
+        for (int k = 0; k < E::NV; ++k) a.variable[inst * E::NV + k] = v[k];
+    }
+    if (!y) return;
+    if (a.costate && i <= N) {
+#pragma unroll
+        for (int k = 0; k < E::NX; ++k) a.costate[(inst * N + i - 1) * E::NX + k] = __ldg(y + (i - 1) * E::CB + k);
+    }
+    if constexpr (E::NP > 0) {
+        if (a.path_dual) {
+            const long long off = i <= N ? (i - 1) * E::CB + E::EQS : N * E::CB;
+            const double h = i <= N ? CTD_SUB(tgrid(i + 1), tgrid(i)) : CTD_SUB(tgrid(N + 1), tgrid(N));
+#pragma unroll
+            for (int r = 0; r < E::NP; ++r) a.path_dual[(inst * (N + 1) + i - 1) * E::NP + r] = __ldg(y + off + r) / h;
+        }
+    }
+    if (i == 1 && a.boundary_dual) {
+#pragma unroll
+        for (int r = 0; r < E::NB; ++r) a.boundary_dual[inst * E::NB + r] = __ldg(y + a.ncon - E::NB + r);
+    }
+}
+
 // the same body under two register budgets (see Cfg::LIGHT)
 template <class E, int F>
 __global__ void __maxnreg__(CTD_MAXNREG) ctd_eval_kernel_light(const EvalArgs a) { eval_body<E, F>(a); }

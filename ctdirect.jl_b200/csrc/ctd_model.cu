@@ -743,6 +743,48 @@ __global__ void __launch_bounds__(256) ctd_violation_kernel(const double* __rest
     }
 }
 
+void Model::unpack_dev(const double* x, const double* y, double* time, double* state, double* control, double* variable,
+                       double* costate, double* path_dual, double* boundary_dual) {
+    ensure_device();
+    if (!x) throw CtdError{-2, "x is NULL"};
+    UnpackArgs a;
+    a.x = x; a.y = y; a.time = time; a.state = state; a.control = control; a.variable = variable;
+    a.costate = costate; a.path_dual = path_dual; a.boundary_dual = boundary_dual;
+    a.sgrid = d_sgrid_; a.params = d_params_; a.nvar = nvar_; a.ncon = ncon_; a.N = N_;
+    const int e = reg_.launcher.unpack(a, batch_, stream_);
+    if (e != 0) throw CtdError{e, std::string("kernel launch failed: ") + cudaGetErrorString((cudaError_t)e)};
+    ++launches_;
+}
+
+void Model::unpack_host(const double* x, const double* y, double* time, double* state, double* control, double* variable,
+                        double* costate, double* path_dual, double* boundary_dual) {
+    ensure_device();
+    ensure_staging();
+    const ElemInfo& f = reg_.info;
+    const size_t b = (size_t)batch_, n1 = (size_t)N_ + 1;
+    const size_t sz[7] = {b * n1, b * n1 * f.nx, b * n1 * f.nu, b * f.nv, b * N_ * f.nx, b * n1 * f.np, b * f.nb};
+    double* host[7] = {time, state, control, variable, costate, path_dual, boundary_dual};
+    double* dev[7] = {nullptr};
+    size_t total = 0;
+    for (int k = 0; k < 7; ++k) if (host[k] && sz[k]) total += sz[k];
+    double* pool = nullptr;
+    if (total) CTD_CUDA(cudaMalloc(&pool, sizeof(double) * total));
+    size_t off = 0;
+    for (int k = 0; k < 7; ++k) if (host[k] && sz[k]) { dev[k] = pool + off; off += sz[k]; }
+    try {
+        CTD_CUDA(cudaMemcpyAsync(d_x_, x, sizeof(double) * b * nvar_, cudaMemcpyHostToDevice, stream_));
+        if (y) CTD_CUDA(cudaMemcpyAsync(d_y_, y, sizeof(double) * b * ncon_, cudaMemcpyHostToDevice, stream_));
+        unpack_dev(d_x_, y ? d_y_ : nullptr, dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], dev[6]);
+        for (int k = 0; k < 7; ++k)
+            if (dev[k]) CTD_CUDA(cudaMemcpyAsync(host[k], dev[k], sizeof(double) * sz[k], cudaMemcpyDeviceToHost, stream_));
+        CTD_CUDA(cudaStreamSynchronize(stream_));
+    } catch (...) {
+        cudaFree(pool);
+        throw;
+    }
+    cudaFree(pool);
+}
+
 void Model::ensure_con_bounds() {
     if (d_lcon_) return;
     std::vector<double> l(ncon_), u(ncon_);

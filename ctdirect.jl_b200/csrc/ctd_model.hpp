@@ -30,7 +30,8 @@ struct Launcher {
     // returns cudaError_t as int
     int (*launch)(const EvalArgs& a, int flags, int batch, size_t smem, cudaStream_t st, int parts, int threads) = nullptr;
     LaunchCfg (*cfg)(int flags) = nullptr;
-    int (*prepare)(int flags, size_t smem, int parts) = nullptr;  // opt in to > 48 KB dynamic shared memory
+    int (*prepare)(int flags, size_t smem, int parts) = nullptr;
+    int (*unpack)(const UnpackArgs& a, int batch, cudaStream_t st) = nullptr;  // opt in to > 48 KB dynamic shared memory
 };
 
 struct Registration {
@@ -92,6 +93,11 @@ class Model {
     void norms_dev(const double* x, double* obj, double* viol);
     void violation_dev(const double* c, double* viol);
     void norms_host(const double* x, double* obj, double* viol);
+    // solution unpacking (device pointers; any output may be NULL)
+    void unpack_dev(const double* x, const double* y, double* time, double* state, double* control, double* variable,
+                    double* costate, double* path_dual, double* boundary_dual);
+    void unpack_host(const double* x, const double* y, double* time, double* state, double* control, double* variable,
+                     double* costate, double* path_dual, double* boundary_dual);
     void set_params(const double* params, int n_params);
     void sync();
     cudaStream_t stream();

@@ -101,6 +101,13 @@ struct ElementLauncher {
 };
 
 template <class E>
+inline int launch_unpack(const UnpackArgs& a, int batch, cudaStream_t st) {
+    dim3 grid((unsigned)((a.N + 1 + 127) / 128), (unsigned)batch, 1);
+    ctd_unpack_kernel<E><<<grid, 128, 0, st>>>(a);
+    return (int)cudaGetLastError();
+}
+
+template <class E>
 struct ElementRegistrar {
     ElementRegistrar() {
         Registration r;
@@ -108,6 +115,7 @@ struct ElementRegistrar {
         r.launcher.launch = &ElementLauncher<E>::launch;
         r.launcher.cfg = &ElementLauncher<E>::cfg;
         r.launcher.prepare = &ElementLauncher<E>::prepare;
+        r.launcher.unpack = &launch_unpack<E>;
         register_element(r);
     }
 };

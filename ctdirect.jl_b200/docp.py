@@ -242,6 +242,32 @@ class DOCP:
         _lib.check(self._lib.ctd_violation_dev(self._h, _ptr(c), _ptr(viol)))
         return viol
 
+    def unpack(self, x, y=None, want=None):
+        """Solution arrays of build_OCP_solution (src/DOCP_data.jl:514-633) from an NLP point x and
+        multipliers y: dict with time, state, control, variable (+ costate, path_dual, boundary_dual when y
+        is given); arrays are [node, component] ([instance, node, component] for batches)."""
+        x = self._check_in(x, self.nvar, "x")
+        y = self._check_in(y, self.ncon, "y")
+        N, B = self.steps, self.batch
+        shapes = {"time": (N + 1,), "state": (N + 1, self.NLP_x), "control": (N + 1, self.NLP_u),
+                  "variable": (self.NLP_v,), "costate": (N, self.NLP_x), "path_dual": (N + 1, self.path_cons),
+                  "boundary_dual": (self.boundary_cons,)}
+        keys = [k for k in shapes if (want is None or k in want)
+                and (y is not None or k in ("time", "state", "control", "variable"))]
+        out, sol = {}, _lib.Solution()
+        for k in keys:
+            shp = shapes[k] if B == 1 else (B,) + shapes[k]
+            if _is_torch(x):
+                import torch
+                out[k] = torch.zeros(shp, dtype=torch.float64, device=x.device)
+            else:
+                out[k] = np.zeros(shp)
+            if int(np.prod(shp)) > 0:
+                setattr(sol, k, out[k].data_ptr() if _is_torch(x) else out[k].ctypes.data)
+        fn = self._lib.ctd_unpack_dev if _is_torch(x) else self._lib.ctd_unpack
+        _lib.check(fn(self._h, _ptr(x), _ptr(y), C.byref(sol)))
+        return out
+
     def set_params(self, params):
         par = np.ascontiguousarray(params, dtype=np.float64).ravel()
         _lib.check(self._lib.ctd_set_params(self._h, par.ctypes.data_as(_lib._dp), len(par)))

@@ -221,7 +221,8 @@ def emit_pair(ocp: OCP, scheme: str, pattern_mode: str = "reference") -> str:
     b = lambda x: "true" if x else "false"
     o.append(f"  static constexpr bool FREE_T0 = {b(ocp.free_t0)}, FREE_TF = {b(ocp.free_tf)}, LAGRANGE = {b(d.lagrange)}, "
              f"MAYER = {b(d.mayer)}, IS_MAX = {b(ocp.criterion == 'max')}, IRK = {b(L.irk)}, STAGEWISE = {b(L.stagewise)}, "
-             f"FINAL_CONTROL = {b(L.final_control)}, SYNTHETIC = {b(ocp.synthetic)};\n")
+             f"FINAL_CONTROL = {b(L.final_control)}, SYNTHETIC = {b(ocp.synthetic)}, "
+             f"EULER_IMPLICIT = {b(scheme == 'euler_implicit')};\n")
     tk = lambda spec: (0 if spec[0] == "const" else 1 if spec[0] == "var" else 2)
     o.append(f"  static constexpr int T0_KIND = {tk(ocp.t0)}, TF_KIND = {tk(ocp.tf)};  // 0 const, 1 v[idx], 2 p[idx]\n")
     o.append(f"  static constexpr int T0_IDX = {int(ocp.t0[1]) if ocp.t0[0] != 'const' else -1}, TF_IDX = {int(ocp.tf[1]) if ocp.tf[0] != 'const' else -1};\n")
@@ -258,6 +259,9 @@ def emit_pair(ocp: OCP, scheme: str, pattern_mode: str = "reference") -> str:
             consts.append(f"BB{j} = {float(Bw[j]).hex()}")
             consts.append(f"BC{j} = {float(Cw[j]).hex()}")
         o.append("  static constexpr double " + ", ".join(consts) + ";\n")
+    bw = [float(x).hex() for x in (butcher_values(s)[1] if s else [])] + ["0.0"] * (3 - s)
+    o.append("  __host__ __device__ static constexpr double BB(int j) {\n"
+             f"    constexpr double t[3] = {{{', '.join(bw)}}};\n    return t[j];\n  }}\n")
     # host-side metadata
     o.append("  static void meta(ctd::ProblemMeta& m) {\n")
     o.append("    m.default_params = {" + ", ".join(dlit(v) for _, v in ocp.params) + "};\n")

@@ -118,6 +118,22 @@ CTD_API int ctd_norms_dev(ctd_handle h, const double* x, double* obj, double* vi
 CTD_API int ctd_norms(ctd_handle h, const double* x, double* obj, double* viol);
 /* violation only, from constraint values c already on the device (e.g. produced by ctd_eval_dev) */
 CTD_API int ctd_violation_dev(ctd_handle h, const double* c, double* viol);
+/* Solution unpacking: getter(nlp_solution, docp; val) of src/ode/common.jl:7-104 with the normalisations
+ * of build_OCP_solution (src/DOCP_data.jl:514-633).  Arrays are [node][component] (the memory of the
+ * getter's matrices), one instance after the other; any member may be NULL.  y = NULL skips the duals.
+ * The box multipliers (state_l/u, control_l/u, variable_l/u) use the primal layout: pass multipliers_L
+ * or multipliers_U as x (with time = NULL). */
+typedef struct ctd_solution {
+    double* time;          /* (N+1)        time grid t0 + s (tf - t0), DOCP_data.jl:437-458          */
+    double* state;         /* (N+1) x nx   val = :state                                               */
+    double* control;       /* (N+1) x nu   val = :control (final control duplicated where aliased)    */
+    double* variable;      /* nv           val = :variable                                            */
+    double* costate;       /* N x nx       val = :costate: multipliers of the state equations         */
+    double* path_dual;     /* (N+1) x np   val = :mult_path_constraints divided by the step length    */
+    double* boundary_dual; /* nb           val = :mult_boundary_constraints                           */
+} ctd_solution;
+CTD_API int ctd_unpack(ctd_handle h, const double* x, const double* y, const ctd_solution* out);
+CTD_API int ctd_unpack_dev(ctd_handle h, const double* x, const double* y, const ctd_solution* out);
 /* replace the problem parameters (n = npar or batch*npar), e.g. new MPC scenarios */
 CTD_API int ctd_set_params(ctd_handle h, const double* params, int32_t n);
 CTD_API int ctd_sync(ctd_handle h);

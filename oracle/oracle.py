@@ -53,6 +53,7 @@ def _load():
     lib.orc_obj.argtypes = [C.c_void_p, _dp]
     lib.orc_cons.argtypes = [C.c_void_p, _dp, _dp]
     lib.orc_derivs.argtypes = [C.c_void_p, _dp, _dp, C.c_double, _dp, _dp, _dp, _ip]
+    lib.orc_unpack.argtypes = [C.c_void_p] + [_dp] * 9
     lib.orc_set_threads.restype = C.c_int
     lib.orc_set_threads.argtypes = [C.c_int]
     _lib = lib
@@ -145,6 +146,18 @@ class OracleModel:
                              dropped.ctypes.data_as(_ip))
         self.dropped = (int(dropped[0]), int(dropped[1]))
         return g, j, h
+
+    def unpack(self, x, y=None):
+        """Solution arrays of build_OCP_solution (src/DOCP_data.jl:514-633), [node][component]."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = None if y is None else np.ascontiguousarray(y, dtype=np.float64)
+        N = self.N
+        out = {"time": np.zeros(N + 1), "state": np.zeros((N + 1, self.nx)), "control": np.zeros((N + 1, self.nu)),
+               "variable": np.zeros(self.nv), "costate": np.zeros((N, self.nx)),
+               "path_dual": np.zeros((N + 1, self.np_)), "boundary_dual": np.zeros(self.nb)}
+        self._lib.orc_unpack(self._h, _p(x), _p(y), *[_p(out[k]) for k in
+                             ("time", "state", "control", "variable", "costate", "path_dual", "boundary_dual")])
+        return out
 
     def grad(self, x):
         return self.derivs(x, want=("grad",))[0]

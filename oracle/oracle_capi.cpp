@@ -27,6 +27,8 @@ struct ModelBase {
     virtual void cons(const double* x, double* c) = 0;
     virtual void derivs(const double* x, const double* y, double sigma, double* grad, double* jvals,
                         double* hvals, int64_t* dropped) = 0;
+    virtual void unpack(const double* x, const double* y, double* time, double* state, double* control,
+                        double* variable, double* costate, double* path_dual, double* boundary_dual) = 0;
 };
 
 template <class P, int SCH>
@@ -70,6 +72,35 @@ struct Model : ModelBase {
         o.grad = grad;
         d.derivatives(x, y, sigma, o);
         if (dropped) { dropped[0] = o.dropped_j; dropped[1] = o.dropped_h; }
+    }
+    // getter() of src/ode/common.jl:7-104 + the normalisations of build_OCP_solution
+    // (src/DOCP_data.jl:514-633): arrays are [node][component]; y may be NULL (then no duals)
+    void unpack(const double* x, const double* y, double* time, double* state, double* control, double* variable,
+                double* costate, double* path_dual, double* boundary_dual) override {
+        PlainAcc a{x};
+        const int N = d.N;
+        std::vector<double> T(N + 1);
+        for (int i = 1; i <= N + 1; ++i) T[i - 1] = d.time_at(a, i);
+        for (int i = 1; i <= N + 1; ++i) {
+            if (time) time[i - 1] = T[i - 1];
+            if (state) for (int k = 0; k < P::nx; ++k) state[(i - 1) * P::nx + k] = x[d.state_off(i) + k];
+            if (control && P::nu > 0) {
+                double u[P::nu > 0 ? P::nu : 1];
+                d.get_control(a, i, u);
+                for (int k = 0; k < P::nu; ++k) control[(i - 1) * P::nu + k] = u[k];
+            }
+        }
+        if (variable) for (int k = 0; k < P::nv; ++k) variable[k] = x[d.v_off() + k];
+        if (!y) return;
+        for (int i = 1; i <= N; ++i)
+            if (costate) for (int k = 0; k < P::nx; ++k) costate[(i - 1) * P::nx + k] = y[(i - 1) * d.cblock + k];
+        if (path_dual)
+            for (int i = 1; i <= N + 1; ++i) {
+                const int off = i <= N ? (i - 1) * d.cblock + d.eqs_block : N * d.cblock;
+                const double h = i <= N ? T[i] - T[i - 1] : T[N] - T[N - 1];   // DOCP_data.jl:596-602
+                for (int r = 0; r < P::np; ++r) path_dual[(i - 1) * P::np + r] = y[off + r] / h;
+            }
+        if (boundary_dual) for (int r = 0; r < P::nb; ++r) boundary_dual[r] = y[d.ncon - P::nb + r];
     }
 };
 
@@ -139,6 +170,10 @@ void orc_cons(void* h, const double* x, double* c) { static_cast<ModelBase*>(h)-
 void orc_derivs(void* h, const double* x, const double* y, double sigma, double* grad, double* jvals,
                 double* hvals, int64_t* dropped2) {
     static_cast<ModelBase*>(h)->derivs(x, y, sigma, grad, jvals, hvals, dropped2);
+}
+void orc_unpack(void* h, const double* x, const double* y, double* time, double* state, double* control,
+                double* variable, double* costate, double* path_dual, double* boundary_dual) {
+    static_cast<ModelBase*>(h)->unpack(x, y, time, state, control, variable, costate, path_dual, boundary_dual);
 }
 int orc_set_threads(int n) {
 #ifdef _OPENMP

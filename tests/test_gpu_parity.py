@@ -214,3 +214,35 @@ def test_stagewise_known_answer_on_gpu(ctd):
         np.testing.assert_allclose(c, lcon, atol=1e-12)
         np.testing.assert_allclose(c, ucon, atol=1e-12)
         assert abs(nlp.obj(xu) - 4.0 / 3.0) <= 1e-12
+
+
+def test_solution_unpacking(ctd, oracle_mod):
+    """getter / build_OCP_solution (src/ode/common.jl:7-104, src/DOCP_data.jl:514-633): copies are bit-exact,
+    the time grid and the path multipliers (divided by the step length) too (same non-contracted formulas)."""
+    rng = np.random.default_rng(8)
+    for problem, scheme in (("goddard_all", "trapeze"), ("goddard_all", "midpoint"), ("goddard", "gauss_legendre_3"),
+                            ("goddard_all", "gauss_legendre_2"), ("goddard", "euler_implicit"), ("goddard_all", "euler"),
+                            ("estimate_rotation_rate", "midpoint"), ("double_integrator_minenergy", "gauss_legendre_2_constant_control")):
+        o = oracle_mod.OracleModel(problem, scheme, 37)
+        d = ctd.DOCP(problem, 37, scheme)
+        x = o.x0() * (1 + 1e-2 * rng.uniform(-1, 1, o.nvar))
+        y = rng.standard_normal(o.ncon)
+        ref, got = o.unpack(x, y), d.unpack(x, y)
+        assert set(got) == set(ref)
+        for k in ref:
+            assert got[k].shape == ref[k].shape, (problem, scheme, k)
+            assert np.array_equal(got[k], ref[k]), (problem, scheme, k)
+        prim = d.unpack(x)                       # box multipliers use the same call without y
+        assert set(prim) == {"time", "state", "control", "variable"}
+    # batched, device tensors
+    import torch
+    B = 3
+    d = ctd.DOCP("goddard_all", 50, "midpoint", batch=B)
+    o = oracle_mod.OracleModel("goddard_all", "midpoint", 50)
+    x, y = synthetic_point(d, seed=5, batch=B)
+    got = d.unpack(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda())
+    d.synchronize()
+    for b in range(B):
+        ref = o.unpack(x[b], y[b])
+        for k in ref:
+            assert np.array_equal(got[k][b].cpu().numpy(), ref[k]), (b, k)

@@ -173,3 +173,28 @@ def _jt(m, x, y):
     out = np.zeros(m.nvar)
     np.add.at(out, cols - 1, j * y[rows - 1])
     return out
+
+
+def test_solution_unpacking_conventions(oracle_mod):
+    # src/ode/common.jl:7-104: costate = multipliers of the state equations; final control duplicated when
+    # u(tf) aliases U_N (common.jl:144-146); path multipliers divided by the step length (DOCP_data.jl:596-602)
+    m = oracle_mod.OracleModel("goddard_all", "midpoint", 4)
+    x = np.arange(m.nvar, dtype=float) + 1.0
+    y = -(np.arange(m.ncon, dtype=float) + 1.0)
+    s = m.unpack(x, y)
+    B, CB = m.step_block, m.cblock
+    assert np.array_equal(s["state"], np.array([x[i * B:i * B + 3] for i in range(5)]))
+    assert np.array_equal(s["control"][:4, 0], x[3::B][:4]) and s["control"][4, 0] == s["control"][3, 0]
+    assert s["variable"][0] == x[-1]
+    tf = x[-1]
+    np.testing.assert_allclose(s["time"], np.linspace(0, 1, 5) * tf, rtol=1e-15)
+    assert np.array_equal(s["costate"], np.array([y[i * CB:i * CB + 3] for i in range(4)]))
+    h = tf / 4
+    np.testing.assert_allclose(s["path_dual"][:4], np.array([y[i * CB + 3:i * CB + 6] for i in range(4)]) / h, rtol=1e-14)
+    np.testing.assert_allclose(s["path_dual"][4], y[4 * CB:4 * CB + 3] / h, rtol=1e-14)
+    assert np.array_equal(s["boundary_dual"], y[-4:])
+    # stagewise: the reported control is the b-weighted average of the stage controls (irk_stagewise.jl:197-205)
+    m = oracle_mod.OracleModel("stagewise_scalar", "gauss_legendre_2", 2)
+    x = np.arange(m.nvar, dtype=float)
+    s = m.unpack(x)
+    assert s["control"][0, 0] == 0.5 * x[1] + 0.5 * x[2] and s["control"][2, 0] == s["control"][1, 0]
