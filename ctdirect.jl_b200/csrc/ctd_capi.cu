@@ -157,6 +157,12 @@ int ctd_eval_dev(ctd_handle h, int what, const double* x, const double* y, doubl
     return guarded([&] { h->m->eval_dev(what, x, y, obj_weight, f, g, c, jvals, hvals); });
 }
 
+int ctd_eval_norms_dev(ctd_handle h, int what, const double* x, const double* y, double obj_weight, double* f,
+                       double* g, double* c, double* jvals, double* hvals, double* viol) {
+    if (int e = check(h)) return e;
+    return guarded([&] { h->m->eval_dev(what, x, y, obj_weight, f, g, c, jvals, hvals, viol); });
+}
+
 int ctd_obj(ctd_handle h, const double* x, double* f) {
     return ctd_eval(h, CTD_OBJ, x, nullptr, 1.0, f, nullptr, nullptr, nullptr, nullptr);
 }

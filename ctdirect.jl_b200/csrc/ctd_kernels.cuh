@@ -33,7 +33,7 @@ constexpr int MAX_NV = 4;
 constexpr int MAX_NVV = MAX_NV * (MAX_NV + 1) / 2;
 constexpr int MAX_TASKS = 3;
 
-enum : int { F_CONS = 1, F_JAC = 2, F_HESS = 4, F_GRAD = 8, F_OBJ = 16 };
+enum : int { F_CONS = 1, F_JAC = 2, F_HESS = 4, F_GRAD = 8, F_OBJ = 16, F_VIOL = 32 };
 
 struct EdgeTask {
     int step;      // 1-based step index
@@ -60,7 +60,8 @@ struct EvalArgs {
     long long nvar, ncon;
     long long jv_base[MAX_NV];    // position of the first value of column v_k in jvals
     long long hvv_pos[MAX_NVV];   // positions of the (v_a, v_b) entries in hvals (packed lower triangle)
-    double* partials;             // [batch][ctas][NRED]
+    double* viol;                 // [batch] max(lcon - c, c - ucon, 0) per instance, or nullptr
+    double* partials;             // [batch][ctas][NRED + 1]
     unsigned int* counters;       // [batch]
     // edge tables (identical for every instance)
     const int* edge_map;
@@ -76,11 +77,14 @@ struct EvalArgs {
 template <class E, int F>
 struct Cfg {
     static constexpr bool WC = (F & F_CONS) != 0, WJ = (F & F_JAC) != 0, WH = (F & F_HESS) != 0,
-                          WG = (F & F_GRAD) != 0, WO = (F & F_OBJ) != 0;
+                          WG = (F & F_GRAD) != 0, WO = (F & F_OBJ) != 0, WV = (F & F_VIOL) != 0;
+    static_assert(!WV || WC, "the violation norm is a by-product of the constraint rows");
     static constexpr int NV = E::NV;
     static constexpr int NVV = NV * (NV + 1) / 2;
     static constexpr int R_H = 0, R_G = R_H + (WH ? NVV : 0), R_O = R_G + (WG ? NV : 0);
     static constexpr int NRED = R_O + (WO ? 1 : 0);
+    // one more slot, combined with max instead of +: the constraint violation of the instance
+    static constexpr int R_V = NRED, NREDX = NRED + (WV ? 1 : 0);
     static constexpr int NJV = NV * E::JV_STRIDE;
     // phase A stages constraints, Jacobian and gradient; phase B the Hessian (same shared memory)
     static constexpr bool PHASE_A = WC || WJ || WG || WO, PHASE_B = WH;
@@ -124,7 +128,7 @@ struct Cfg {
     static constexpr int B_END = WH ? even((OWN + 1) * E::H_BLOCK) : 0;
     static constexpr int WARP_DOUBLES = ((A_END > B_END ? A_END : B_END) + 1) & ~1;
     static constexpr int S_RED = WPC * WARP_DOUBLES;
-    static constexpr int S_END = S_RED + WPC * (NRED > 0 ? NRED : 1) + 2;
+    static constexpr int S_END = S_RED + WPC * (NREDX > 0 ? NREDX : 1) + 2;
     static constexpr size_t TILE_SMEM = (size_t)S_END * sizeof(double);
     // edge map layout of one step task
     static constexpr int M_JO = 0, M_JN = M_JO + E::NJ_OWN, M_JV = M_JN + E::NJ_NEXT, M_HO = M_JV + E::NJ_V,
@@ -223,6 +227,10 @@ __device__ __forceinline__ long long gtime() {
 #define CTD_STAMP(k) do { } while (0)
 #endif
 
+// NaN-propagating max (a NaN constraint value must surface as a NaN violation)
+__device__ __forceinline__ double nanmax(double a, double b) { return (b > a || b != b) ? b : a; }
+__device__ __forceinline__ double row_violation(double lb, double ub, double v) { return nanmax(lb - v, v - ub); }
+
 __device__ __forceinline__ int phase_of(const double* g) {
     return (int)((reinterpret_cast<unsigned long long>(g) >> 3) & 1ull);
 }
@@ -244,7 +252,12 @@ struct TileSink {
     double gn_[E::NG_NEXT > 0 ? E::NG_NEXT : 1];
     double* red;
 
-    template <int R> __device__ __forceinline__ void c(double v) { if (PC) c_[R] = v; }
+    template <int R> __device__ __forceinline__ void c(double v) {
+        if (PC) {
+            c_[R] = v;
+            if constexpr (C::WV) { if (owner) red[C::R_V] = nanmax(red[C::R_V], row_violation(E::CON_LB(R), E::CON_UB(R), v)); }
+        }
+    }
     template <int N> __device__ __forceinline__ void jo(double v) { if (PJ) jo_[E::J_OWN(N, 2)] = v; }
     template <int N> __device__ __forceinline__ void jn(double v) { if (PJ) jn_[E::J_NEXT(N, 2)] = v; }
     template <int N> __device__ __forceinline__ void jv(double v) {
@@ -271,7 +284,12 @@ struct EdgeSink {
     __device__ __forceinline__ void put(int m, double v) {
         if (m >= 0) buf[m] = v;
     }
-    template <int R> __device__ __forceinline__ void c(double v) { if (crow) crow[R] = v; }
+    template <int R> __device__ __forceinline__ void c(double v) {
+        if (crow) {
+            crow[R] = v;
+            if constexpr (C::WV) red[C::R_V] = nanmax(red[C::R_V], row_violation(E::CON_LB(R), E::CON_UB(R), v));
+        }
+    }
     template <int N> __device__ __forceinline__ void jo(double v) { put(map[C::M_JO + N], v); }
     template <int N> __device__ __forceinline__ void jn(double v) { put(map[C::M_JN + N], v); }
     template <int N> __device__ __forceinline__ void jv(double v) { put(map[C::M_JV + N], v); }
@@ -284,14 +302,23 @@ struct EdgeSink {
 };
 
 // final path / boundary elements (edge CTA only): c<R>, j<N>, h<N>, g<N>
-template <class E, int F, int MJ, int MH, int MG>
+template <class E, int F, int MJ, int MH, int MG, bool BOUNDARY>
 struct EdgeElemSink {
     using C = Cfg<E, F>;
     double* buf;
     const int* map;
     double* crow;
     double* red;
-    template <int R> __device__ __forceinline__ void c(double v) { if (crow) crow[R] = v; }
+    template <int R> __device__ __forceinline__ void c(double v) {
+        if (crow) {
+            crow[R] = v;
+            if constexpr (C::WV) {   // rows of the boundary block, or path-constraint rows at the final time
+                const double lb = BOUNDARY ? E::BC_LB(R) : E::CON_LB(E::EQS + R);
+                const double ub = BOUNDARY ? E::BC_UB(R) : E::CON_UB(E::EQS + R);
+                red[C::R_V] = nanmax(red[C::R_V], row_violation(lb, ub, v));
+            }
+        }
+    }
     template <int N> __device__ __forceinline__ void j(double v) {
         const int m = map[MJ + N];
         if (m >= 0) buf[m] = v;
@@ -400,7 +427,7 @@ __device__ void edge_cta(const EvalArgs& a, const double* __restrict__ x, const 
                     for (int r = 0; r < E::NP; ++r) lam[r] = (C::WH && y) ? __ldg(y + N * E::CB + r) : 0.0;
                     TimeArgs<E::NV> Tm;
                     time_args<E>(a, z + E::FP_NLOC - E::NV, p, N + 1, Tm);
-                    EdgeElemSink<E, F, C::M_FP_J, C::M_FP_H, 0> s;
+                    EdgeElemSink<E, F, C::M_FP_J, C::M_FP_H, 0, false> s;
                     s.buf = buf + 2 * ne;
                     s.map = smap + a.fp_map_off;
                     s.crow = C::WC ? c + N * E::CB : nullptr;
@@ -418,7 +445,7 @@ __device__ void edge_cta(const EvalArgs& a, const double* __restrict__ x, const 
                 for (int k = 0; k < E::NV; ++k) z[2 * E::NX + k] = __ldg(x + a.nvar - E::NV + k);
 #pragma unroll
                 for (int r = 0; r < E::NB; ++r) lam[r] = (C::WH && y) ? __ldg(y + a.ncon - E::NB + r) : 0.0;
-                EdgeElemSink<E, F, C::M_BC_J, C::M_BC_H, C::M_BC_G> s;
+                EdgeElemSink<E, F, C::M_BC_J, C::M_BC_H, C::M_BC_G, true> s;
                 s.buf = buf + 3 * ne;
                 s.map = smap + a.bc_map_off;
                 s.crow = (C::WC && E::NB > 0) ? c + (a.ncon - E::NB) : nullptr;
@@ -545,32 +572,35 @@ __device__ __forceinline__ void publish_reduction(const EvalArgs& a, const doubl
                                                   unsigned int* cta_ticket_p, long long inst, int cta, int lane,
                                                   int warp, double* hvals, double* grad, const int NW) {
     using C = Cfg<E, F>;
-    if constexpr (C::NRED > 0) {
+    if constexpr (C::NREDX > 0) {
+        constexpr int NR = C::NREDX;
+        // slot R_V (the constraint violation) is combined with max, every other slot with +
+        auto comb = [](int k, double x, double y) { return (C::WV && k == C::R_V) ? nanmax(x, y) : x + y; };
         unsigned int& cta_ticket = *cta_ticket_p;
         const int nblk = a.ctas;
-        double wv[C::NRED];
+        double wv[NR];
 #pragma unroll
-        for (int k = 0; k < C::NRED; ++k) {
+        for (int k = 0; k < NR; ++k) {
             double v = red[k];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            for (int o = 16; o > 0; o >>= 1) v = comb(k, v, __shfl_xor_sync(0xffffffffu, v, o));
             wv[k] = v;
         }
         unsigned int flag = 0;
         if (lane == 0) {
 #pragma unroll
-            for (int k = 0; k < C::NRED; ++k) sred[warp * C::NRED + k] = wv[k];
+            for (int k = 0; k < NR; ++k) sred[warp * NR + k] = wv[k];
             __threadfence_block();
             flag = (atomicAdd(&cta_ticket, 1u) == (unsigned int)(NW - 1));
         }
         flag = __shfl_sync(0xffffffffu, flag, 0);
         if (flag) {
             __threadfence_block();
-            double* part = a.partials + (inst * nblk) * C::NRED;
-            if (lane < C::NRED) {
-                double v = 0.0;
-                for (int w = 0; w < NW; ++w) v += sred[w * C::NRED + lane];
-                part[(long long)cta * C::NRED + lane] = v;
+            double* part = a.partials + (inst * nblk) * NR;
+            if (lane < NR) {
+                double v = sred[lane];
+                for (int w = 1; w < NW; ++w) v = comb(lane, v, sred[w * NR + lane]);
+                part[(long long)cta * NR + lane] = v;
                 __threadfence();
             }
             __syncwarp();
@@ -579,30 +609,31 @@ __device__ __forceinline__ void publish_reduction(const EvalArgs& a, const doubl
             last = __shfl_sync(0xffffffffu, last, 0);
             if (last) {
                 __threadfence();
-                double acc[C::NRED];
+                double acc[NR];
 #pragma unroll
-                for (int k = 0; k < C::NRED; ++k) acc[k] = 0.0;
+                for (int k = 0; k < NR; ++k) acc[k] = 0.0;
                 // 16 independent loads per lane in flight (one memory round trip per 512 partials)
                 for (int base = 0; base < nblk; base += 32 * 16) {
 #pragma unroll
-                    for (int k = 0; k < C::NRED; ++k) {
+                    for (int k = 0; k < NR; ++k) {
                         double t[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const int b = base + j * 32 + lane;
-                            t[j] = b < nblk ? __ldcg(&part[(long long)b * C::NRED + k]) : 0.0;
+                            const int bb = base + j * 32 + lane;
+                            t[j] = bb < nblk ? __ldcg(&part[(long long)bb * NR + k]) : 0.0;
                         }
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) acc[k] += t[j];
+                        for (int j = 0; j < 16; ++j) acc[k] = comb(k, acc[k], t[j]);
                     }
                 }
 #pragma unroll
-                for (int k = 0; k < C::NRED; ++k) {
+                for (int k = 0; k < NR; ++k) {
                     double v = acc[k];
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    for (int o = 16; o > 0; o >>= 1) v = comb(k, v, __shfl_xor_sync(0xffffffffu, v, o));
                     if (lane == 0) {
-                        if (C::WH && k < C::R_G) { if (a.hvv_pos[k - C::R_H] >= 0) hvals[a.hvv_pos[k - C::R_H]] = v; }
+                        if (C::WV && k == C::R_V) { if (a.viol) a.viol[inst] = v; }
+                        else if (C::WH && k < C::R_G) { if (a.hvv_pos[k - C::R_H] >= 0) hvals[a.hvv_pos[k - C::R_H]] = v; }
                         else if (C::WG && k < C::R_O) grad[a.nvar - E::NV + (k - C::R_G)] = v;
                         else if (C::WO && a.obj) a.obj[inst] = v;
                     }
@@ -647,11 +678,11 @@ __device__ __forceinline__ void eval_body(const EvalArgs& a) {
     double* hvals = C::WH ? a.hvals + inst * a.h_stride : nullptr;
     double* grad = C::WG ? a.grad + inst * a.g_stride : nullptr;
 
-    double red[C::NRED > 0 ? C::NRED : 1];
+    double red[C::NREDX > 0 ? C::NREDX : 1];
 #pragma unroll
-    for (int k = 0; k < (C::NRED > 0 ? C::NRED : 1); ++k) red[k] = 0.0;
+    for (int k = 0; k < (C::NREDX > 0 ? C::NREDX : 1); ++k) red[k] = 0.0;
     __shared__ unsigned int cta_ticket;
-    if constexpr (C::NRED > 0) {
+    if constexpr (C::NREDX > 0) {
         if (tid == 0) cta_ticket = 0u;
         __syncthreads();
     }
@@ -737,7 +768,7 @@ struct PCfg {
     static constexpr int S_H = S_JV + (C::WJ ? C::NV * JV_ONE : 0);
     static constexpr int S_G = S_H + (C::WH ? even((OWN + 1) * E::H_BLOCK) : 0);
     static constexpr int S_RED = S_G + (C::WG ? even((OWN + 1) * E::BLK) : 0);
-    static constexpr int S_END = S_RED + P * (C::NRED > 0 ? C::NRED : 1) + 2;
+    static constexpr int S_END = S_RED + P * (C::NREDX > 0 ? C::NREDX : 1) + 2;
     static constexpr size_t TILE_SMEM = (size_t)S_END * sizeof(double);
     // every output of the element gets a running index; part = index * P / TOT
     static constexpr int O_C = 0;
@@ -765,7 +796,12 @@ struct PartSink {
     double gn_[E::NG_NEXT > 0 ? E::NG_NEXT : 1];
     double* red;
     static constexpr bool mine(int g) { return PC::part_of(g) == PART; }
-    template <int R> __device__ __forceinline__ void c(double v) { if constexpr (C::WC && mine(PC::O_C + R)) c_[R] = v; }
+    template <int R> __device__ __forceinline__ void c(double v) {
+        if constexpr (C::WC && mine(PC::O_C + R)) {
+            c_[R] = v;
+            if constexpr (C::WV) { if (owner) red[C::R_V] = nanmax(red[C::R_V], row_violation(E::CON_LB(R), E::CON_UB(R), v)); }
+        }
+    }
     template <int N> __device__ __forceinline__ void jo(double v) { if constexpr (C::WJ && mine(PC::O_JO + N)) jo_[E::J_OWN(N, 2)] = v; }
     template <int N> __device__ __forceinline__ void jn(double v) { if constexpr (C::WJ && mine(PC::O_JN + N)) jn_[E::J_NEXT(N, 2)] = v; }
     template <int N> __device__ __forceinline__ void jv(double v) {
@@ -851,11 +887,11 @@ __global__ void __launch_bounds__(PCfg<E, F>::T) ctd_eval_kernel_parts(const Eva
     double* jvals = C::WJ ? a.jvals + inst * a.j_stride : nullptr;
     double* hvals = C::WH ? a.hvals + inst * a.h_stride : nullptr;
     double* grad = C::WG ? a.grad + inst * a.g_stride : nullptr;
-    double red[C::NRED > 0 ? C::NRED : 1];
+    double red[C::NREDX > 0 ? C::NREDX : 1];
 #pragma unroll
-    for (int k = 0; k < (C::NRED > 0 ? C::NRED : 1); ++k) red[k] = 0.0;
+    for (int k = 0; k < (C::NREDX > 0 ? C::NREDX : 1); ++k) red[k] = 0.0;
     __shared__ unsigned int cta_ticket;
-    if constexpr (C::NRED > 0) {
+    if constexpr (C::NREDX > 0) {
         if (tid == 0) cta_ticket = 0u;
         __syncthreads();
     }

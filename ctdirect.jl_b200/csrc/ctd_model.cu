@@ -540,19 +540,21 @@ void Model::ensure_device() {
     CTD_CUDA(cudaSetDevice(device_));
     CTD_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     const LaunchCfg lc = reg_.launcher.cfg(F_CONS | F_JAC | F_HESS | F_GRAD | F_OBJ);
+    const int max_nred = lc.nred + 1;   // (+1: the violation slot of the flag sets that carry it)
     const int npar = std::max(reg_.info.npar, 1);
     CTD_CUDA(cudaMalloc(&d_edge_map_, sizeof(int) * std::max<size_t>(edge_map_.size(), 1)));
     CTD_CUDA(cudaMalloc(&d_edge_pos_, sizeof(long long) * std::max<size_t>(edge_pos_.size(), 1)));
     CTD_CUDA(cudaMalloc(&d_sgrid_, sizeof(double) * sgrid_.size()));
     CTD_CUDA(cudaMalloc(&d_params_, sizeof(double) * (size_t)batch_ * npar));
     int64_t max_ctas = 1;
-    for (int fl : {1, 2, 4, 16, 17, 24, 7, 31}) {
+    for (int fl : {1, 2, 4, 16, 17, 24, 7, 31, 49, 63}) {
         const LaunchCfg q = reg_.launcher.cfg(fl);
+        if (q.threads == 0) continue;
         const int64_t tiles = (N_ >= 3) ? ((int64_t)N_ - 2 + q.own - 1) / q.own : 0;
         max_ctas = std::max<int64_t>(max_ctas, tiles + 1);   // (one warp per CTA is the smallest launch configuration)
         if (q.p_threads > 0) max_ctas = std::max<int64_t>(max_ctas, ((N_ >= 3) ? ((int64_t)N_ - 2 + q.p_own - 1) / q.p_own : 0) + 1);
     }
-    CTD_CUDA(cudaMalloc(&d_partials_, sizeof(double) * (size_t)batch_ * max_ctas * std::max(lc.nred, 1)));
+    CTD_CUDA(cudaMalloc(&d_partials_, sizeof(double) * (size_t)batch_ * max_ctas * max_nred));
     CTD_CUDA(cudaMalloc(&d_counters_, sizeof(unsigned int) * batch_));
     CTD_CUDA(cudaMemsetAsync(d_counters_, 0, sizeof(unsigned int) * batch_, stream_));
     CTD_CUDA(cudaMemcpyAsync(d_edge_map_, edge_map_.data(), sizeof(int) * edge_map_.size(), cudaMemcpyHostToDevice, stream_));
@@ -626,8 +628,19 @@ EvalArgs Model::base_args() const {
 }
 
 void Model::eval_dev(int flags, const double* x, const double* y, double sigma, double* obj, double* grad, double* c,
-                     double* jvals, double* hvals) {
+                     double* jvals, double* hvals, double* viol) {
     ensure_device();
+    flags &= ~F_VIOL;
+    if (viol) {
+        if (!(flags & F_CONS)) throw CtdError{-2, "the violation norm needs the constraints (CTD_CONS)"};
+        if (reg_.launcher.cfg(flags | F_VIOL).threads > 0) {
+            flags |= F_VIOL;          // reduced inside the evaluation kernel
+        } else {                      // wide elements: evaluation, then the stand-alone norm kernel
+            eval_dev(flags, x, y, sigma, obj, grad, c, jvals, hvals, nullptr);
+            violation_dev(c, viol);
+            return;
+        }
+    }
     const LaunchCfg lc = reg_.launcher.cfg(flags);
     if (lc.threads == 0) throw CtdError{-2, "unsupported combination of outputs"};
     if (!x) throw CtdError{-2, "x is NULL"};
@@ -636,7 +649,7 @@ void Model::eval_dev(int flags, const double* x, const double* y, double sigma, 
     if ((flags & F_HESS) && (!hvals || !y)) throw CtdError{-2, "hvals / y is NULL"};
     if ((flags & F_GRAD) && !grad) throw CtdError{-2, "grad is NULL"};
     EvalArgs a = base_args();
-    a.x = x; a.y = y; a.sigma = sigma; a.obj = obj; a.grad = grad; a.c = c; a.jvals = jvals; a.hvals = hvals;
+    a.x = x; a.y = y; a.sigma = sigma; a.obj = obj; a.grad = grad; a.c = c; a.jvals = jvals; a.hvals = hvals; a.viol = viol;
     // warps per CTA: large CTAs for a single instance (a 1e5-step grid is one wave and CTA launch rate
     // matters), small CTAs for batches (many waves: resources are released per CTA, and the tiles of
     // an instance rarely fill a large CTA)
@@ -649,7 +662,7 @@ void Model::eval_dev(int flags, const double* x, const double* y, double sigma, 
     // wide elements on small grids: one tile per CTA, the tile's outputs split over the CTA's warps
     // (enough warps to occupy the GPU although the grid has few steps)
     int parts = 0;
-    size_t tile_smem = wpc * lc.warp_smem + sizeof(double) * (wpc * std::max(lc.nred, 1) + 2);
+    size_t tile_smem = wpc * lc.warp_smem + sizeof(double) * (wpc * (lc.nred + 1) + 2);
     if (lc.p_threads > 0) {
         const int64_t ptiles = (N_ >= 3) ? ((int64_t)N_ - 2 + lc.p_own - 1) / lc.p_own : 0;
         if (ptiles * batch_ * (lc.p_threads / 32) <= (int64_t)148 * 48) {
@@ -812,8 +825,9 @@ void Model::norms_dev(const double* x, double* obj, double* viol) {
     ensure_con_bounds();
     if (!viol) viol = d_viol_;
     if (!obj) obj = d_obj_;
-    eval_dev(F_CONS | F_OBJ, x, nullptr, 1.0, obj, nullptr, d_c_, nullptr, nullptr);
-    violation_dev(d_c_, viol);
+    // objective and violation norm come out of ONE launch (the violation is a max-reduction slot of the
+    // fused kernel); the constraint values are a by-product in the handle's buffer
+    eval_dev(F_CONS | F_OBJ, x, nullptr, 1.0, obj, nullptr, d_c_, nullptr, nullptr, viol);
 }
 
 void Model::norms_host(const double* x, double* obj, double* viol) {

@@ -85,8 +85,9 @@ class Model {
     void structure(const Csc& p, int64_t* rows, int64_t* cols) const;
 
     // device evaluation; pointers are DEVICE pointers, arrays are [batch][dim]
+    // `viol` (optional, needs F_CONS): per-instance max(lcon - c, c - ucon, 0), reduced in the same launch
     void eval_dev(int flags, const double* x, const double* y, double sigma, double* obj, double* grad, double* c,
-                  double* jvals, double* hvals);
+                  double* jvals, double* hvals, double* viol = nullptr);
     // host-pointer evaluation (copies through the handle's device buffers)
     void eval_host(int flags, const double* x, const double* y, double sigma, double* obj, double* grad, double* c,
                    double* jvals, double* hvals);

@@ -8,7 +8,13 @@ namespace ctd {
 
 // the output combinations that are compiled (one kernel each):
 //   cons | jac | hess | obj | cons+obj | grad+obj | cons+jac+hess | everything
-#define CTD_FOR_EACH_FLAGSET(X) X(1) X(2) X(4) X(16) X(17) X(24) X(7) X(31)
+#define CTD_FOR_EACH_FLAGSET(X) X(1) X(2) X(4) X(16) X(17) X(24) X(7) X(31) X(49) X(63)
+// 49 = cons+obj+violation, 63 = everything+violation: the per-instance violation norm reduced in the same
+// launch; only compiled for light elements (the batched MPC use case), others use ctd_violation_kernel
+constexpr bool viol_set(int f) { return (f & 32) != 0; }
+// the "parts" variant (wide elements on small grids) is only compiled for the derivative-heavy sets
+#define CTD_FOR_EACH_PARTS_FLAGSET(X) X(2) X(4) X(7) X(31)
+constexpr bool parts_compiled(int f) { return f == 2 || f == 4 || f == 7 || f == 31; }
 
 // launch with the programmatic-stream-serialization attribute (see pdl_entry() in ctd_kernels.cuh)
 template <class K>
@@ -36,12 +42,12 @@ struct ElementLauncher {
         c.own = C::OWN;
         c.wpc = C::WPC;
         c.warp_smem = (size_t)C::WARP_DOUBLES * sizeof(double);
-        c.nred = C::NRED;
+        c.nred = C::NREDX;
         c.tile_smem = C::TILE_SMEM;
         c.map_step = C::M_STEP + 1;
         c.map_fp = C::M_FP;
         c.map_bc = C::M_BC;
-        if constexpr (!C::LIGHT) {
+        if constexpr (!C::LIGHT && parts_compiled(F)) {
             using PC = PCfg<E, F>;
             c.p_threads = PC::T;
             c.p_own = PC::OWN;
@@ -51,7 +57,7 @@ struct ElementLauncher {
     }
     static LaunchCfg cfg(int flags) {
         switch (flags) {
-#define CTD_X(F) case F: return cfg_of<F>();
+#define CTD_X(F) case F: if constexpr (viol_set(F) && !Cfg<E, F>::LIGHT) return LaunchCfg(); else return cfg_of<F>();
             CTD_FOR_EACH_FLAGSET(CTD_X)
 #undef CTD_X
         }
@@ -62,7 +68,7 @@ struct ElementLauncher {
             switch (flags) {
 #define CTD_X(F) \
     case F: if constexpr (!Cfg<E, F>::LIGHT) return (int)cudaFuncSetAttribute(ctd_eval_kernel_parts<E, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); else return (int)cudaErrorInvalidValue;
-                CTD_FOR_EACH_FLAGSET(CTD_X)
+                CTD_FOR_EACH_PARTS_FLAGSET(CTD_X)
 #undef CTD_X
             }
             return (int)cudaErrorInvalidValue;
@@ -70,6 +76,7 @@ struct ElementLauncher {
         switch (flags) {
 #define CTD_X(F) \
     case F: if constexpr (Cfg<E, F>::LIGHT) return (int)cudaFuncSetAttribute(ctd_eval_kernel_light<E, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            else if constexpr (viol_set(F)) return (int)cudaErrorInvalidValue; \
             else return (int)cudaFuncSetAttribute(ctd_eval_kernel<E, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             CTD_FOR_EACH_FLAGSET(CTD_X)
 #undef CTD_X
@@ -82,7 +89,7 @@ struct ElementLauncher {
             switch (flags) {
 #define CTD_X(F) \
     case F: if constexpr (!Cfg<E, F>::LIGHT) launch_pdl(ctd_eval_kernel_parts<E, F>, grid, PCfg<E, F>::T, smem, st, a); break;
-                CTD_FOR_EACH_FLAGSET(CTD_X)
+                CTD_FOR_EACH_PARTS_FLAGSET(CTD_X)
 #undef CTD_X
                 default: return (int)cudaErrorInvalidValue;
             }
@@ -91,6 +98,7 @@ struct ElementLauncher {
         switch (flags) {
 #define CTD_X(F) \
     case F: if constexpr (Cfg<E, F>::LIGHT) launch_pdl(ctd_eval_kernel_light<E, F>, grid, threads, smem, st, a); \
+            else if constexpr (viol_set(F)) return (int)cudaErrorInvalidValue; \
             else launch_pdl(ctd_eval_kernel<E, F>, grid, threads, smem, st, a); break;
             CTD_FOR_EACH_FLAGSET(CTD_X)
 #undef CTD_X

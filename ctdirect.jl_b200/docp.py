@@ -194,6 +194,28 @@ class DOCP:
                       _ptr(res.get("grad")), _ptr(res.get("cons")), _ptr(res.get("jac")), _ptr(res.get("hess"))))
         return res
 
+    def evaluate_with_norms(self, what: int, x, y=None, obj_weight: float = 1.0, out=None, viol=None):
+        """`evaluate` on CUDA tensors plus the per-instance constraint violation, reduced in the same launch.
+        Returns (result dict, viol tensor)."""
+        import torch
+        x = self._check_in(x, self.nvar, "x")
+        y = self._check_in(y, self.ncon, "y")
+        if not _is_torch(x) or not (what & CONS):
+            raise TypeError("evaluate_with_norms needs CUDA tensors and CONS among the outputs")
+        out = dict(out or {})
+        res = {}
+        for bit, key, n in ((OBJ, "obj", 1), (GRAD, "grad", self.nvar), (CONS, "cons", self.ncon),
+                            (JAC, "jac", self.nnzj), (HESS, "hess", self.nnzh)):
+            if what & bit:
+                buf = out.get(key)
+                res[key] = self._check_in(buf, n, key) if buf is not None else self._empty_like(x, n)
+        if viol is None:
+            viol = torch.empty(self.batch, dtype=torch.float64, device=x.device)
+        _lib.check(self._lib.ctd_eval_norms_dev(self._h, int(what), _ptr(x), _ptr(y), float(obj_weight),
+                                                _ptr(res.get("obj")), _ptr(res.get("grad")), _ptr(res.get("cons")),
+                                                _ptr(res.get("jac")), _ptr(res.get("hess")), _ptr(viol)))
+        return res, viol
+
     def bind(self, what: int, x, y=None, obj_weight: float = 1.0, out=None):
         """Validate the buffers once and return a zero-argument callable that issues the same evaluation
         again (solver loops call the same buffers every iteration; this keeps the per-call host cost at

@@ -259,6 +259,16 @@ def emit_pair(ocp: OCP, scheme: str, pattern_mode: str = "reference") -> str:
             consts.append(f"BB{j} = {float(Bw[j]).hex()}")
             consts.append(f"BC{j} = {float(Cw[j]).hex()}")
         o.append("  static constexpr double " + ", ".join(consts) + ";\n")
+    # bounds of the constraint rows of one step (0 for the state / stage equations, the path-constraint
+    # bounds after them) and of the boundary rows: DOCP_functions.jl:163-191
+    def _dtab(fname, vals):
+        vals = list(vals) or [0.0]
+        return (f"  __host__ __device__ static constexpr double {fname}(int r) {{\n"
+                f"    constexpr double t[{len(vals)}] = {{{', '.join(dlit(v) for v in vals)}}};\n    return t[r];\n  }}\n")
+    o.append(_dtab("CON_LB", [0.0] * L.eqs_block + list(ocp.path_lb)))
+    o.append(_dtab("CON_UB", [0.0] * L.eqs_block + list(ocp.path_ub)))
+    o.append(_dtab("BC_LB", ocp.bc_lb))
+    o.append(_dtab("BC_UB", ocp.bc_ub))
     bw = [float(x).hex() for x in (butcher_values(s)[1] if s else [])] + ["0.0"] * (3 - s)
     o.append("  __host__ __device__ static constexpr double BB(int j) {\n"
              f"    constexpr double t[3] = {{{', '.join(bw)}}};\n    return t[j];\n  }}\n")

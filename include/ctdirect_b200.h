@@ -112,6 +112,10 @@ CTD_API int ctd_eval(ctd_handle h, int what, const double* x, const double* y, d
 /* device-pointer twins (asynchronous on the handle's stream) */
 CTD_API int ctd_eval_dev(ctd_handle h, int what, const double* x, const double* y, double obj_weight, double* f,
                  double* g, double* c, double* jvals, double* hvals);
+/* ctd_eval_dev plus the per-instance constraint violation max_k max(lcon_k - c_k, c_k - ucon_k, 0) reduced in
+ * the same launch (`what` must include CTD_CONS; viol has `batch` entries) */
+CTD_API int ctd_eval_norms_dev(ctd_handle h, int what, const double* x, const double* y, double obj_weight, double* f,
+                       double* g, double* c, double* jvals, double* hvals, double* viol);
 /* per-instance objective and constraint violation  max_k max(lcon_k - c_k, c_k - ucon_k, 0)  (the two
  * numbers a batched MPC driver gathers across GPUs); obj and viol have `batch` entries (device) */
 CTD_API int ctd_norms_dev(ctd_handle h, const double* x, double* obj, double* viol);
