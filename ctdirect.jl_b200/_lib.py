@@ -54,6 +54,7 @@ SIGNATURES = {
     "ctd_jac_coord": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "ctd_hess_coord": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
     "ctd_eval": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_double] + [C.c_void_p] * 5),
+    "ctd_eval_async": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_double] + [C.c_void_p] * 5),
     "ctd_eval_dev": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_double] + [C.c_void_p] * 5),
     "ctd_eval_norms_dev": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_double] + [C.c_void_p] * 6),
     "ctd_norms_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),

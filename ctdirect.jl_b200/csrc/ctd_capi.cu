@@ -151,6 +151,12 @@ int ctd_eval(ctd_handle h, int what, const double* x, const double* y, double ob
     return guarded([&] { h->m->eval_host(what, x, y, obj_weight, f, g, c, jvals, hvals); });
 }
 
+int ctd_eval_async(ctd_handle h, int what, const double* x, const double* y, double obj_weight, double* f, double* g,
+                   double* c, double* jvals, double* hvals) {
+    if (int e = check(h)) return e;
+    return guarded([&] { h->m->eval_host(what, x, y, obj_weight, f, g, c, jvals, hvals, false); });
+}
+
 int ctd_eval_dev(ctd_handle h, int what, const double* x, const double* y, double obj_weight, double* f,
                  double* g, double* c, double* jvals, double* hvals) {
     if (int e = check(h)) return e;

@@ -710,7 +710,7 @@ void Model::eval_dev(int flags, const double* x, const double* y, double sigma, 
 }
 
 void Model::eval_host(int flags, const double* x, const double* y, double sigma, double* obj, double* grad, double* c,
-                      double* jvals, double* hvals) {
+                      double* jvals, double* hvals, bool wait) {
     ensure_device();
     ensure_staging();
     const size_t b = (size_t)batch_;
@@ -726,7 +726,7 @@ void Model::eval_host(int flags, const double* x, const double* y, double sigma,
     if ((flags & F_HESS) && hvals) CTD_CUDA(cudaMemcpyAsync(hvals, d_h_, sizeof(double) * b * nnzh(), cudaMemcpyDeviceToHost, stream_));
     if ((flags & F_GRAD) && grad) CTD_CUDA(cudaMemcpyAsync(grad, d_g_, sizeof(double) * b * nvar_, cudaMemcpyDeviceToHost, stream_));
     if ((flags & F_OBJ) && obj) CTD_CUDA(cudaMemcpyAsync(obj, d_obj_, sizeof(double) * b, cudaMemcpyDeviceToHost, stream_));
-    CTD_CUDA(cudaStreamSynchronize(stream_));
+    if (wait) CTD_CUDA(cudaStreamSynchronize(stream_));
 }
 
 // --------------------------------------------------------------------------------------------

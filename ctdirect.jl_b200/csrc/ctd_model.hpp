@@ -90,7 +90,7 @@ class Model {
                   double* jvals, double* hvals, double* viol = nullptr);
     // host-pointer evaluation (copies through the handle's device buffers)
     void eval_host(int flags, const double* x, const double* y, double sigma, double* obj, double* grad, double* c,
-                   double* jvals, double* hvals);
+                   double* jvals, double* hvals, bool wait = true);
     void norms_dev(const double* x, double* obj, double* viol);
     void violation_dev(const double* c, double* viol);
     void norms_host(const double* x, double* obj, double* viol);

@@ -216,10 +216,11 @@ class DOCP:
                                                 _ptr(res.get("jac")), _ptr(res.get("hess")), _ptr(viol)))
         return res, viol
 
-    def bind(self, what: int, x, y=None, obj_weight: float = 1.0, out=None):
+    def bind(self, what: int, x, y=None, obj_weight: float = 1.0, out=None, wait: bool = True):
         """Validate the buffers once and return a zero-argument callable that issues the same evaluation
         again (solver loops call the same buffers every iteration; this keeps the per-call host cost at
-        one ctypes call).  Returns (callable, result dict)."""
+        one ctypes call).  Returns (callable, result dict).  With host arrays, wait=False only enqueues the
+        copies and the kernel (ctd_eval_async): call synchronize() before reading the results."""
         x = self._check_in(x, self.nvar, "x")
         y = self._check_in(y, self.ncon, "y")
         dev = _is_torch(x)
@@ -230,7 +231,7 @@ class DOCP:
             if what & bit:
                 buf = out.get(key)
                 res[key] = self._check_in(buf, n, key) if buf is not None else self._empty_like(x, n)
-        fn = self._lib.ctd_eval_dev if dev else self._lib.ctd_eval
+        fn = self._lib.ctd_eval_dev if dev else (self._lib.ctd_eval if wait else self._lib.ctd_eval_async)
         args = (self._h, int(what), _ptr(x), _ptr(y), C.c_double(float(obj_weight)), _ptr(res.get("obj")),
                 _ptr(res.get("grad")), _ptr(res.get("cons")), _ptr(res.get("jac")), _ptr(res.get("hess")))
         keep = (x, y, res)

@@ -109,6 +109,12 @@ CTD_API int ctd_hess_coord(ctd_handle h, const double* x, const double* y, doubl
 CTD_API int ctd_eval(ctd_handle h, int what, const double* x, const double* y, double obj_weight, double* f, double* g,
              double* c, double* jvals, double* hvals);
 
+/* ctd_eval without the final wait: copies and kernel are only ENQUEUED on the handle's stream; the host
+ * buffers (pinned memory, for the copies to be asynchronous) must stay untouched until ctd_sync(h).  Several
+ * handles used round-robin overlap the H2D, kernel and D2H stages of consecutive evaluations. */
+CTD_API int ctd_eval_async(ctd_handle h, int what, const double* x, const double* y, double obj_weight, double* f,
+                   double* g, double* c, double* jvals, double* hvals);
+
 /* device-pointer twins (asynchronous on the handle's stream) */
 CTD_API int ctd_eval_dev(ctd_handle h, int what, const double* x, const double* y, double obj_weight, double* f,
                  double* g, double* c, double* jvals, double* hvals);
