@@ -727,14 +727,15 @@ __device__ __forceinline__ void eval_body(const EvalArgs& a) {
             tile_phase<E, F, false, false, true, false, false>(a, ws, z, lam, Tm, p, red, lane, nown, i0, active, c,
                                                                 jvals, hvals, grad);
         }
-#if CTD_TMA_STORE
         CTD_STAMP(4);
-        if (lane == 0) bulk_wait_read();   // shared memory must outlive the copies that read it
-#endif
-        CTD_STAMP(5);
     }
 
+    // the partial sums are published while the copy engine is still draining the last phase
     publish_reduction<E, F>(a, red, smem + nw * C::WARP_DOUBLES, &cta_ticket, inst, cta, lane, warp, hvals, grad, nw);
+    CTD_STAMP(5);
+#if CTD_TMA_STORE
+    if (cta != 0 && lane == 0) bulk_wait_read();   // shared memory must outlive the copies that read it
+#endif
     CTD_STAMP(6);
 }
 

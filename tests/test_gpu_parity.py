@@ -246,3 +246,35 @@ def test_solution_unpacking(ctd, oracle_mod):
         ref = o.unpack(x[b], y[b])
         for k in ref:
             assert np.array_equal(got[k][b].cpu().numpy(), ref[k]), (b, k)
+
+
+def test_every_output_entry_is_written_and_nothing_else(ctd):
+    """Own bounds check (compute-sanitizer is not available on the GPU pool): outputs live inside guarded
+    buffers pre-filled with a sentinel; after an evaluation no sentinel is left inside and the guards are intact."""
+    import torch
+    SENT = -7.25e300
+    G = 64
+    cases = [("goddard", "midpoint", 1000, 1, "reference"), ("goddard", "midpoint", 1000, 7, "reference"),
+             ("goddard", "midpoint", 33, 5, "optimized"), ("goddard_all", "trapeze", 311, 1, "reference"),
+             ("goddard", "gauss_legendre_3", 95, 1, "reference"), ("goddard", "gauss_legendre_3", 2100, 1, "optimized"),
+             ("robot", "trapeze", 64, 2, "reference"), ("double_integrator_minenergy", "euler", 3, 1, "reference"),
+             ("goddard", "midpoint", 2, 1, "reference"), ("goddard", "midpoint", 1, 3, "reference")]
+    for p, s, N, B, m in cases:
+        d = ctd.DOCP(p, N, s, batch=B, pattern_mode=m)
+        x, y = synthetic_point(d, seed=21, batch=B)
+        xd = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+        yd = torch.from_numpy(np.ascontiguousarray(y)).cuda()
+        sizes = {"obj": B, "grad": B * d.nvar, "cons": B * d.ncon, "jac": B * d.nnzj, "hess": B * d.nnzh}
+        for F in (ctd.CONS, ctd.JAC, ctd.HESS, ctd.GRAD | ctd.OBJ, ctd.CONS | ctd.JAC | ctd.HESS,
+                  ctd.CONS | ctd.JAC | ctd.HESS | ctd.GRAD | ctd.OBJ):
+            keys = [k for bit, k in ((ctd.OBJ, "obj"), (ctd.GRAD, "grad"), (ctd.CONS, "cons"), (ctd.JAC, "jac"), (ctd.HESS, "hess")) if F & bit]
+            big = {k: torch.full((sizes[k] + 2 * G,), SENT, dtype=torch.float64, device="cuda") for k in keys}
+            out = {k: big[k][G:G + sizes[k]].view((B, -1) if (B > 1 and k != "obj") else (-1,)) for k in keys}
+            d.evaluate(F, xd, yd, 0.9, out=out)
+            d.synchronize()
+            for k in keys:
+                b = big[k].cpu().numpy()
+                tag = f"{p}/{s}/{m}/N={N}/B={B}/F={F}/{k}"
+                assert np.all(b[:G] == SENT) and np.all(b[G + sizes[k]:] == SENT), tag + ": wrote outside the array"
+                assert not np.any(b[G:G + sizes[k]] == SENT), tag + ": entries left unwritten"
+                assert np.all(np.isfinite(b[G:G + sizes[k]])), tag
