@@ -62,6 +62,8 @@ SIGNATURES = {
     "ctd_norms": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ctd_unpack": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.POINTER(Solution)]),
     "ctd_unpack_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.POINTER(Solution)]),
+    "ctd_pack": (C.c_int, [_H] + [C.c_void_p] * 5),
+    "ctd_pack_dev": (C.c_int, [_H] + [C.c_void_p] * 5),
     "ctd_set_params": (C.c_int, [_H, _dp, C.c_int32]),
     "ctd_sync": (C.c_int, [_H]),
     "ctd_stream": (C.c_void_p, [_H]),

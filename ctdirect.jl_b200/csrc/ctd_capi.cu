@@ -216,6 +216,18 @@ int ctd_unpack_dev(ctd_handle h, const double* x, const double* y, const ctd_sol
     });
 }
 
+int ctd_pack(ctd_handle h, const double* state, const double* control, const double* variable,
+             const double* stage_control, double* x) {
+    if (int e = check(h)) return e;
+    return guarded([&] { h->m->pack_host(state, control, variable, stage_control, x); });
+}
+
+int ctd_pack_dev(ctd_handle h, const double* state, const double* control, const double* variable,
+                 const double* stage_control, double* x) {
+    if (int e = check(h)) return e;
+    return guarded([&] { h->m->pack_dev(state, control, variable, stage_control, x); });
+}
+
 int ctd_set_params(ctd_handle h, const double* params, int32_t n) {
     if (int e = check(h)) return e;
     return guarded([&] { h->m->set_params(params, n); });

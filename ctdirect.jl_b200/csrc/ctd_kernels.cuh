@@ -1036,6 +1036,52 @@ __global__ void __launch_bounds__(128) ctd_unpack_kernel(const UnpackArgs a) {
     }
 }
 
+// Initial guess / warm start (the inverse of unpacking): __initial_guess of src/DOCP_variables.jl:122-145 and
+// irk_stagewise.jl:302-335 from SAMPLED state / control / variable data -- 0.1 everywhere, then the variables,
+// the states at the nodes and the controls through the setters of src/ode/common.jl:184-225.
+struct PackArgs {
+    const double *state, *control, *variable, *stage_control;   // any may be nullptr (the 0.1 default stays)
+    double* x;
+    long long nvar;
+    int N;
+};
+
+template <class E>
+__global__ void __launch_bounds__(128) ctd_pack_kernel(const PackArgs a) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x + 1;   // node 1..N+1
+    const long long inst = blockIdx.y;
+    const long long N = a.N;
+    if (i > N + 1) return;
+    double* x = a.x + inst * a.nvar;
+    const int blk = (i <= N) ? E::BLK : (int)(a.nvar - E::NV - N * E::BLK);     // last block: x_f (+ u_f for trapeze)
+    double* xb = x + (i - 1) * E::BLK;
+    for (int k = 0; k < blk; ++k) xb[k] = 0.1;
+    if (a.state) {
+#pragma unroll
+        for (int k = 0; k < E::NX; ++k) xb[k] = a.state[(inst * (N + 1) + i - 1) * E::NX + k];
+    }
+    if constexpr (E::NU > 0) {
+        if constexpr (E::STAGEWISE) {
+            if (i <= N) {
+#pragma unroll
+                for (int j = 0; j < E::STAGE; ++j)
+#pragma unroll
+                    for (int k = 0; k < E::NU; ++k) {
+                        if (a.stage_control) xb[E::NX + j * E::NU + k] = a.stage_control[((inst * N + i - 1) * E::STAGE + j) * E::NU + k];
+                        else if (a.control) xb[E::NX + j * E::NU + k] = a.control[(inst * (N + 1) + i - 1) * E::NU + k];
+                    }
+            }
+        } else if (a.control && (i <= N || E::FINAL_CONTROL)) {
+#pragma unroll
+            for (int k = 0; k < E::NU; ++k) xb[E::NX + k] = a.control[(inst * (N + 1) + i - 1) * E::NU + k];
+        }
+    }
+    if (i == 1) {
+#pragma unroll
+        for (int k = 0; k < E::NV; ++k) x[a.nvar - E::NV + k] = a.variable ? a.variable[inst * E::NV + k] : 0.1;
+    }
+}
+
 // the same body under two register budgets (see Cfg::LIGHT)
 template <class E, int F>
 __global__ void __maxnreg__(CTD_MAXNREG) ctd_eval_kernel_light(const EvalArgs a) { eval_body<E, F>(a); }

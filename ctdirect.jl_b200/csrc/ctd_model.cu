@@ -798,6 +798,49 @@ void Model::unpack_host(const double* x, const double* y, double* time, double* 
     cudaFree(pool);
 }
 
+void Model::pack_dev(const double* state, const double* control, const double* variable, const double* stage_control,
+                     double* x) {
+    ensure_device();
+    if (!x) throw CtdError{-2, "x is NULL"};
+    PackArgs a;
+    a.state = state; a.control = control; a.variable = variable; a.stage_control = stage_control;
+    a.x = x; a.nvar = nvar_; a.N = N_;
+    const int e = reg_.launcher.pack(a, batch_, stream_);
+    if (e != 0) throw CtdError{e, std::string("kernel launch failed: ") + cudaGetErrorString((cudaError_t)e)};
+    ++launches_;
+}
+
+void Model::pack_host(const double* state, const double* control, const double* variable, const double* stage_control,
+                      double* x) {
+    ensure_device();
+    ensure_staging();
+    const ElemInfo& f = reg_.info;
+    const size_t b = (size_t)batch_, n1 = (size_t)N_ + 1;
+    const size_t sz[4] = {b * n1 * f.nx, b * n1 * f.nu, b * f.nv, b * N_ * f.stage * f.nu};
+    const double* host[4] = {state, control, variable, stage_control};
+    double* dev[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t total = 0;
+    for (int k = 0; k < 4; ++k) if (host[k] && sz[k]) total += sz[k];
+    double* pool = nullptr;
+    if (total) CTD_CUDA(cudaMalloc(&pool, sizeof(double) * total));
+    size_t off = 0;
+    try {
+        for (int k = 0; k < 4; ++k)
+            if (host[k] && sz[k]) {
+                dev[k] = pool + off;
+                off += sz[k];
+                CTD_CUDA(cudaMemcpyAsync(dev[k], host[k], sizeof(double) * sz[k], cudaMemcpyHostToDevice, stream_));
+            }
+        pack_dev(dev[0], dev[1], dev[2], dev[3], d_x_);
+        CTD_CUDA(cudaMemcpyAsync(x, d_x_, sizeof(double) * b * nvar_, cudaMemcpyDeviceToHost, stream_));
+        CTD_CUDA(cudaStreamSynchronize(stream_));
+    } catch (...) {
+        cudaFree(pool);
+        throw;
+    }
+    cudaFree(pool);
+}
+
 void Model::ensure_con_bounds() {
     if (d_lcon_) return;
     std::vector<double> l(ncon_), u(ncon_);

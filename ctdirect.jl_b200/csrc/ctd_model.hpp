@@ -31,7 +31,8 @@ struct Launcher {
     int (*launch)(const EvalArgs& a, int flags, int batch, size_t smem, cudaStream_t st, int parts, int threads) = nullptr;
     LaunchCfg (*cfg)(int flags) = nullptr;
     int (*prepare)(int flags, size_t smem, int parts) = nullptr;
-    int (*unpack)(const UnpackArgs& a, int batch, cudaStream_t st) = nullptr;  // opt in to > 48 KB dynamic shared memory
+    int (*unpack)(const UnpackArgs& a, int batch, cudaStream_t st) = nullptr;
+    int (*pack)(const PackArgs& a, int batch, cudaStream_t st) = nullptr;  // opt in to > 48 KB dynamic shared memory
 };
 
 struct Registration {
@@ -99,6 +100,9 @@ class Model {
                     double* costate, double* path_dual, double* boundary_dual);
     void unpack_host(const double* x, const double* y, double* time, double* state, double* control, double* variable,
                      double* costate, double* path_dual, double* boundary_dual);
+    // initial guess / warm start from sampled data (device or host pointers; inputs may be NULL)
+    void pack_dev(const double* state, const double* control, const double* variable, const double* stage_control, double* x);
+    void pack_host(const double* state, const double* control, const double* variable, const double* stage_control, double* x);
     void set_params(const double* params, int n_params);
     void sync();
     cudaStream_t stream();

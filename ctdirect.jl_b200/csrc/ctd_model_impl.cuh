@@ -116,6 +116,13 @@ inline int launch_unpack(const UnpackArgs& a, int batch, cudaStream_t st) {
 }
 
 template <class E>
+inline int launch_pack(const PackArgs& a, int batch, cudaStream_t st) {
+    dim3 grid((unsigned)((a.N + 1 + 127) / 128), (unsigned)batch, 1);
+    ctd_pack_kernel<E><<<grid, 128, 0, st>>>(a);
+    return (int)cudaGetLastError();
+}
+
+template <class E>
 struct ElementRegistrar {
     ElementRegistrar() {
         Registration r;
@@ -124,6 +131,7 @@ struct ElementRegistrar {
         r.launcher.cfg = &ElementLauncher<E>::cfg;
         r.launcher.prepare = &ElementLauncher<E>::prepare;
         r.launcher.unpack = &launch_unpack<E>;
+        r.launcher.pack = &launch_pack<E>;
         register_element(r);
     }
 };

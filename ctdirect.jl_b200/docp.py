@@ -291,6 +291,33 @@ class DOCP:
         _lib.check(fn(self._h, _ptr(x), _ptr(y), C.byref(sol)))
         return out
 
+    def pack(self, state=None, control=None, variable=None, stage_control=None):
+        """NLP vector of __initial_guess (src/DOCP_variables.jl:122-145) from sampled data: state [N+1, nx],
+        control [N+1, nu], variable [nv] (stagewise schemes: stage_control [N, s, nu]); None keeps the 0.1
+        default.  numpy in -> numpy out, CUDA tensors in -> CUDA tensor out."""
+        N, B = self.steps, self.batch
+        given = [a for a in (state, control, variable, stage_control) if a is not None]
+        dev = any(_is_torch(a) for a in given)
+        sizes = {"state": (N + 1) * self.NLP_x, "control": (N + 1) * self.NLP_u, "variable": self.NLP_v,
+                 "stage_control": N * self.stage * self.NLP_u}
+        args = []
+        for name, a in (("state", state), ("control", control), ("variable", variable), ("stage_control", stage_control)):
+            if a is None or sizes[name] == 0:
+                args.append(None)
+                continue
+            if dev != _is_torch(a):
+                raise TypeError("all inputs must be host arrays or all CUDA tensors")
+            args.append(self._check_in(a, sizes[name], name))
+        if dev:
+            import torch
+            x = torch.empty(self._shape(self.nvar), dtype=torch.float64, device=given[0].device)
+            fn = self._lib.ctd_pack_dev
+        else:
+            x = np.empty(self._shape(self.nvar))
+            fn = self._lib.ctd_pack
+        _lib.check(fn(self._h, *[_ptr(a) for a in args], _ptr(x)))
+        return x
+
     def set_params(self, params):
         par = np.ascontiguousarray(params, dtype=np.float64).ravel()
         _lib.check(self._lib.ctd_set_params(self._h, par.ctypes.data_as(_lib._dp), len(par)))

@@ -144,6 +144,15 @@ typedef struct ctd_solution {
 } ctd_solution;
 CTD_API int ctd_unpack(ctd_handle h, const double* x, const double* y, const ctd_solution* out);
 CTD_API int ctd_unpack_dev(ctd_handle h, const double* x, const double* y, const ctd_solution* out);
+/* Initial guess / warm start, the inverse of ctd_unpack: __initial_guess (src/DOCP_variables.jl:122-145,
+ * irk_stagewise.jl:302-335) from SAMPLED data -- x = 0.1 everywhere, then variable, state[(N+1) x nx] at the
+ * nodes and control[(N+1) x nu] through the setters of src/ode/common.jl:184-225 (final control only where
+ * the scheme has one).  Stagewise schemes take stage_control[N x s x nu] (one control per stage) or, if it is
+ * NULL, the node control for every stage of the step.  Any input may be NULL (its 0.1 default stays). */
+CTD_API int ctd_pack(ctd_handle h, const double* state, const double* control, const double* variable,
+             const double* stage_control, double* x);
+CTD_API int ctd_pack_dev(ctd_handle h, const double* state, const double* control, const double* variable,
+                 const double* stage_control, double* x);
 /* replace the problem parameters (n = npar or batch*npar), e.g. new MPC scenarios */
 CTD_API int ctd_set_params(ctd_handle h, const double* params, int32_t n);
 CTD_API int ctd_sync(ctd_handle h);

@@ -54,6 +54,7 @@ def _load():
     lib.orc_cons.argtypes = [C.c_void_p, _dp, _dp]
     lib.orc_derivs.argtypes = [C.c_void_p, _dp, _dp, C.c_double, _dp, _dp, _dp, _ip]
     lib.orc_unpack.argtypes = [C.c_void_p] + [_dp] * 9
+    lib.orc_pack.argtypes = [C.c_void_p] + [_dp] * 5
     lib.orc_set_threads.restype = C.c_int
     lib.orc_set_threads.argtypes = [C.c_int]
     _lib = lib
@@ -158,6 +159,14 @@ class OracleModel:
         self._lib.orc_unpack(self._h, _p(x), _p(y), *[_p(out[k]) for k in
                              ("time", "state", "control", "variable", "costate", "path_dual", "boundary_dual")])
         return out
+
+    def pack(self, state=None, control=None, variable=None, stage_control=None):
+        """NLP vector of __initial_guess (DOCP_variables.jl:122-145) from sampled state / control / variable."""
+        c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        state, control, variable, stage_control = c(state), c(control), c(variable), c(stage_control)
+        x = np.zeros(self.nvar)
+        self._lib.orc_pack(self._h, _p(state), _p(control), _p(variable), _p(stage_control), _p(x))
+        return x
 
     def grad(self, x):
         return self.derivs(x, want=("grad",))[0]

@@ -29,6 +29,8 @@ struct ModelBase {
                         double* hvals, int64_t* dropped) = 0;
     virtual void unpack(const double* x, const double* y, double* time, double* state, double* control,
                         double* variable, double* costate, double* path_dual, double* boundary_dual) = 0;
+    virtual void pack(const double* state, const double* control, const double* variable,
+                      const double* stage_control, double* x) = 0;
 };
 
 template <class P, int SCH>
@@ -102,6 +104,31 @@ struct Model : ModelBase {
             }
         if (boundary_dual) for (int r = 0; r < P::nb; ++r) boundary_dual[r] = y[d.ncon - P::nb + r];
     }
+    // __initial_guess (DOCP_variables.jl:122-145, irk_stagewise.jl:302-335) from SAMPLED data: 0.1 everywhere,
+    // then the variables, the states at the nodes and the controls (set_*_at_time_step!, common.jl:184-225;
+    // the final control only where the scheme has one).  Stagewise schemes take one control per stage
+    // (stage_control, [step][stage][k]) or, without it, the node control for every stage of the step.
+    void pack(const double* state, const double* control, const double* variable, const double* stage_control,
+              double* x) override {
+        using ST = typename Docp<P, SCH>::ST;
+        const int N = d.N;
+        for (int k = 0; k < d.nvar; ++k) x[k] = 0.1;
+        if (variable) for (int k = 0; k < P::nv; ++k) x[d.v_off() + k] = variable[k];
+        for (int i = 1; i <= N + 1; ++i) {
+            if (state) for (int k = 0; k < P::nx; ++k) x[d.state_off(i) + k] = state[(i - 1) * P::nx + k];
+            if (P::nu == 0) continue;
+            if (ST::stagewise) {
+                if (i > N) continue;
+                for (int j = 1; j <= ST::stage; ++j)
+                    for (int k = 0; k < P::nu; ++k) {
+                        if (stage_control) x[d.stagecontrol_off(i, j) + k] = stage_control[((i - 1) * ST::stage + (j - 1)) * P::nu + k];
+                        else if (control) x[d.stagecontrol_off(i, j) + k] = control[(i - 1) * P::nu + k];
+                    }
+            } else if (control && (i <= N || ST::final_control)) {
+                for (int k = 0; k < P::nu; ++k) x[(i - 1) * d.step_block + P::nx + k] = control[(i - 1) * P::nu + k];
+            }
+        }
+    }
 };
 
 template <class P>
@@ -174,6 +201,10 @@ void orc_derivs(void* h, const double* x, const double* y, double sigma, double*
 void orc_unpack(void* h, const double* x, const double* y, double* time, double* state, double* control,
                 double* variable, double* costate, double* path_dual, double* boundary_dual) {
     static_cast<ModelBase*>(h)->unpack(x, y, time, state, control, variable, costate, path_dual, boundary_dual);
+}
+void orc_pack(void* h, const double* state, const double* control, const double* variable,
+              const double* stage_control, double* x) {
+    static_cast<ModelBase*>(h)->pack(state, control, variable, stage_control, x);
 }
 int orc_set_threads(int n) {
 #ifdef _OPENMP

@@ -278,3 +278,35 @@ def test_every_output_entry_is_written_and_nothing_else(ctd):
                 assert np.all(b[:G] == SENT) and np.all(b[G + sizes[k]:] == SENT), tag + ": wrote outside the array"
                 assert not np.any(b[G:G + sizes[k]] == SENT), tag + ": entries left unwritten"
                 assert np.all(np.isfinite(b[G:G + sizes[k]])), tag
+
+
+def test_initial_guess_packing_roundtrip(ctd, oracle_mod):
+    """__initial_guess from sampled data (src/DOCP_variables.jl:122-145, irk_stagewise.jl:302-335): bit-exact
+    against the oracle's restatement of the setters; pack(unpack(x)) reproduces the node variables."""
+    rng = np.random.default_rng(13)
+    for problem, scheme in (("goddard_all", "trapeze"), ("goddard", "midpoint"), ("goddard", "gauss_legendre_3"),
+                            ("goddard", "gauss_legendre_2_constant_control"), ("estimate_rotation_rate", "euler"),
+                            ("double_integrator_minenergy", "gauss_legendre_2")):
+        N = 23
+        o = oracle_mod.OracleModel(problem, scheme, N)
+        d = ctd.DOCP(problem, N, scheme)
+        st = rng.standard_normal((N + 1, o.nx))
+        ct = rng.standard_normal((N + 1, o.nu)) if o.nu else None
+        va = rng.standard_normal(o.nv) if o.nv else None
+        assert np.array_equal(d.pack(st, ct, va), o.pack(st, ct, va)), (problem, scheme)
+        assert np.array_equal(d.pack(), np.full(o.nvar, 0.1))                     # default guess 0.1 everywhere
+        assert np.array_equal(d.pack(variable=va), o.pack(variable=va))
+        if d.stage and "constant" not in scheme and o.nu:
+            sc = rng.standard_normal((N, d.stage, o.nu))
+            assert np.array_equal(d.pack(st, None, va, sc), o.pack(st, None, va, sc)), (problem, scheme)
+        x = d.pack(st, ct, va)
+        u = d.unpack(x)
+        assert np.array_equal(u["state"], st)
+        if va is not None:
+            assert np.array_equal(u["variable"], va)
+    import torch
+    d = ctd.DOCP("goddard", 10, "midpoint", batch=2)
+    st = torch.randn(2, 11, 3, dtype=torch.float64, device="cuda")
+    x = d.pack(state=st)
+    d.synchronize()
+    assert x.shape == (2, d.nvar) and torch.equal(x[:, 0:3], st[:, 0]) and float(x[0, 3]) == 0.1
