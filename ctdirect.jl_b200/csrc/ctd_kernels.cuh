@@ -91,8 +91,9 @@ struct Cfg {
     static constexpr int PER_STEP_A = (WC ? E::CB : 0) + (WJ ? E::J_BLOCK + NJV : 0) + (WG ? E::BLK : 0);
     static constexpr int PER_STEP_B = WH ? E::H_BLOCK : 0;
     static constexpr int PER_STEP = PER_STEP_A > PER_STEP_B ? PER_STEP_A : PER_STEP_B;
-    // warps per CTA: 4 when a CTA's staged tiles stay small (many CTAs per SM), fewer for wide
-    // elements (e.g. 3-stage IRK of a 6-state problem)
+    // WPC = the LARGEST number of warps per CTA a launch may use (the host picks blockDim per launch,
+    // see Model::eval_dev): 8 while a CTA's staged tiles stay below 72 KB, fewer for wide elements
+    // (e.g. 3-stage IRK of a 6-state problem)
     static constexpr int SMEM_MAX = 200 * 1024;
 #ifndef CTD_WPC
 #define CTD_WPC 8
@@ -101,11 +102,9 @@ struct Cfg {
     static constexpr int WPC = (WARP_BYTES * CTD_WPC <= 72 * 1024) ? CTD_WPC
                                : (WARP_BYTES * 4 <= 100 * 1024) ? 4 : (WARP_BYTES * 2 <= 100 * 1024) ? 2 : 1;
     static constexpr int T = WPC * 32;
-    // light elements: cap registers at 88/thread so that 22 warps (682 owned steps) are resident per SM,
-    // i.e. a grid of 1e5 steps is ONE wave on 148 SMs; wide elements keep the full register file
-    // light elements (midpoint / trapeze of small systems): registers are capped so that 24 warps (744
-    // owned steps) are resident per SM and a grid of 1e5 steps is ONE wave on 148 SMs; wide elements
-    // keep the full register file
+    // light elements (midpoint / trapeze / Euler of small systems): registers are capped at 80 so that 24
+    // warps (744 owned steps) are resident per SM and a grid of 1e5 steps is ONE wave on 148 SMs; wide
+    // elements keep the full register file
 #ifndef CTD_MAXNREG
 #define CTD_MAXNREG 80
 #endif
@@ -142,11 +141,7 @@ struct Cfg {
 __device__ __forceinline__ double grid_point(const EvalArgs& a, long long j /*0-based node*/) {
     // DOCP_data.jl:176-214: the normalized grid (collect(LinRange(0,1,N+1)) by default) is built once on
     // the host; it is shared by all instances and evaluations, so it stays L2-resident
-#ifdef CTD_USE_DIV
-    return (double)j / (double)a.N;
-#else
     return __ldg(a.sgrid + j);
-#endif
 }
 
 template <class E>
@@ -171,31 +166,13 @@ __device__ __forceinline__ void time_args(const EvalArgs& a, const double* v, co
     }
 }
 
-// contiguous shared -> global copy; s and g have the same 16-byte phase
-__device__ __forceinline__ void store_range(double* __restrict__ g, const double* __restrict__ s, int n, int tid,
-                                            int nthreads) {
-    const int head = (int)((reinterpret_cast<unsigned long long>(g) >> 3) & 1ull) < n
-                         ? (int)((reinterpret_cast<unsigned long long>(g) >> 3) & 1ull) : n;
-    if (tid == 0 && head) g[0] = s[0];
-    const int n2 = (n - head) >> 1;
-    const double2* __restrict__ s2 = reinterpret_cast<const double2*>(s + head);
-    double2* __restrict__ g2 = reinterpret_cast<double2*>(g + head);
-    for (int k = tid; k < n2; k += nthreads) g2[k] = s2[k];
-    const int done = head + 2 * n2;
-    if (done < n && tid == nthreads - 1) g[done] = s[done];
-}
-
 // ---- TMA bulk store (cp.async.bulk, shared::cta -> global): one elected lane hands a staged range to
 // the copy engine, the warp's issue slots stay free for the next phase.
-#ifndef CTD_TMA_STORE
-#define CTD_TMA_STORE 1
-#endif
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // contiguous shared -> global copy of n doubles; s and g have the same 16-byte phase.  Called by the
 // whole warp after fence_proxy_async_smem() + __syncwarp(); lane 0 issues the bulk copy of the
 // 16-byte-aligned body, the (at most one) leading and trailing doubles are stored directly.
@@ -531,7 +508,6 @@ __device__ __forceinline__ void tile_phase(const EvalArgs& a, double* __restrict
         }
         __syncwarp();
     }
-#if CTD_TMA_STORE
     fence_proxy_async_smem();
     __syncwarp();
     if (nown > 0) {
@@ -547,21 +523,6 @@ __device__ __forceinline__ void tile_phase(const EvalArgs& a, double* __restrict
         if constexpr (PG) bulk_store_range(gG, sG, nown * E::BLK, lane);
         if (lane == 0) bulk_commit();
     }
-#else
-    if (nown > 0) {
-        if constexpr (PC) store_range(gC, sC, nown * E::CB, lane, 32);
-        if constexpr (PJ) {
-            store_range(gJ, sJ, nown * E::J_BLOCK, lane, 32);
-            if constexpr (C::NV > 0) {
-#pragma unroll
-                for (int k = 0; k < C::NV; ++k) store_range(gJV[k], sJV[k], nown * E::JV_STRIDE, lane, 32);
-            }
-        }
-        if constexpr (PH) store_range(gH, sH, nown * E::H_BLOCK, lane, 32);
-        if constexpr (PG) store_range(gG, sG, nown * E::BLK, lane, 32);
-    }
-    __syncwarp();
-#endif
 }
 
 // Deterministic reduction of the global sums ((v,v) Hessian entries, d cost / d v, cost) over the grid.
@@ -717,12 +678,10 @@ __device__ __forceinline__ void eval_body(const EvalArgs& a) {
                                                                   jvals, hvals, grad);
         CTD_STAMP(2);
         if constexpr (C::PHASE_B) {
-#if CTD_TMA_STORE
             if constexpr (C::PHASE_A) {   // phase B reuses the region: the copy engine must have read it
                 if (lane == 0) bulk_wait_read();
                 __syncwarp();
             }
-#endif
             CTD_STAMP(3);
             tile_phase<E, F, false, false, true, false, false>(a, ws, z, lam, Tm, p, red, lane, nown, i0, active, c,
                                                                 jvals, hvals, grad);
@@ -733,9 +692,7 @@ __device__ __forceinline__ void eval_body(const EvalArgs& a) {
     // the partial sums are published while the copy engine is still draining the last phase
     publish_reduction<E, F>(a, red, smem + nw * C::WARP_DOUBLES, &cta_ticket, inst, cta, lane, warp, hvals, grad, nw);
     CTD_STAMP(5);
-#if CTD_TMA_STORE
     if (cta != 0 && lane == 0) bulk_wait_read();   // shared memory must outlive the copies that read it
-#endif
     CTD_STAMP(6);
 }
 

@@ -97,7 +97,6 @@ Model::Model(const Registration& reg, int grid_size, const double* time_grid, in
     if (!time_grid) {
         if (grid_size < 1) throw CtdError{-2, "grid_size must be >= 1"};
         N_ = grid_size;
-        uniform_ = true;
         sgrid_.resize(N_ + 1);
         for (int j = 0; j <= N_; ++j) sgrid_[j] = (double)j / (double)N_;  // collect(LinRange(0, 1, N+1))
     } else {
@@ -106,7 +105,6 @@ Model::Model(const Registration& reg, int grid_size, const double* time_grid, in
             if (!(time_grid[j] < time_grid[j + 1]))
                 throw CtdError{-3, "given time grid is not strictly increasing. Aborting..."};  // DOCP_data.jl:187
         N_ = n_time_grid - 1;
-        uniform_ = false;
         sgrid_.assign(time_grid, time_grid + n_time_grid);
         if (time_grid[0] != 0.0 || time_grid[N_] != 1.0) {  // normalisation DOCP_data.jl:191-196
             const double a = time_grid[0], b = time_grid[N_];

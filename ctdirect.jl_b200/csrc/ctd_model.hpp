@@ -119,7 +119,6 @@ class Model {
 
     Registration reg_;
     int N_ = 0, batch_ = 1, device_ = 0;
-    bool uniform_ = true;
     std::vector<double> sgrid_, params_;
     int64_t nvar_ = 0, ncon_ = 0;
     Csc jac_, hess_;
