@@ -92,6 +92,7 @@ Model::Model(const Registration& reg, int grid_size, const double* time_grid, in
     : reg_(reg), batch_(batch), device_(device) {
     const ElemInfo& f = reg_.info;
     if (batch < 1) throw CtdError{-2, "batch must be >= 1"};
+    if (batch > 65535) throw CtdError{-2, "batch must be <= 65535 (instances are the y dimension of the grid)"};
     if (f.nv > MAX_NV) throw CtdError{-2, "too many optimisation variables v for this build"};
     // DOCPtime: DOCP_data.jl:176-214
     if (!time_grid) {
@@ -136,6 +137,7 @@ Model::Model(const Registration& reg, int grid_size, const double* time_grid, in
 Model::~Model() {
     if (dev_ready_) {
         cudaSetDevice(device_);
+        if (stream_) cudaStreamSynchronize(stream_);   // nothing of this handle may still be in flight
         cudaFree(d_edge_map_); cudaFree(d_edge_pos_); cudaFree(d_sgrid_); cudaFree(d_params_);
         cudaFree(d_partials_); cudaFree(d_counters_);
         cudaFree(d_x_); cudaFree(d_y_); cudaFree(d_c_); cudaFree(d_j_); cudaFree(d_h_); cudaFree(d_g_); cudaFree(d_obj_);
