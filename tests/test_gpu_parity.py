@@ -310,3 +310,30 @@ def test_initial_guess_packing_roundtrip(ctd, oracle_mod):
     x = d.pack(state=st)
     d.synchronize()
     assert x.shape == (2, d.nvar) and torch.equal(x[:, 0:3], st[:, 0]) and float(x[0, 3]) == 0.1
+
+
+def test_wide_elements_on_large_grids_and_batches(ctd, oracle_mod):
+    """Wide elements use the parts kernel on small grids; large grids and batches go through the one-warp-per-
+    tile kernel with the full register file.  Both paths against the oracle."""
+    o = oracle_mod.OracleModel("goddard", "gauss_legendre_2", 120_000)
+    d = ctd.DOCP("goddard", 120_000, "gauss_legendre_2")
+    x, y = synthetic_point(o, seed=31)
+    _compare_all(ctd, o, d, x, y, 0.8, "goddard/gauss_legendre_2/N=120000")
+    B, N = 60, 400
+    rng = np.random.default_rng(3)
+    par = np.tile(np.array([310.0, 500.0, 2.0, 3.5]), (B, 1))
+    par[:, 3] = rng.uniform(1.0, 3.5, B)
+    d = ctd.DOCP("goddard", N, "gauss_legendre_3_constant_control", params=par, batch=B)
+    x, y = synthetic_point(d, seed=32, batch=B)
+    r = d.evaluate(ctd.CONS | ctd.JAC | ctd.HESS | ctd.GRAD | ctd.OBJ, x, y, 1.0)
+    obj, viol = d.norms(x)
+    _, _, lcon, ucon = d.bounds()
+    for b in (0, 17, 59):
+        o = oracle_mod.OracleModel("goddard", "gauss_legendre_3_constant_control", N, params=par[b])
+        g, j, h = o.derivs(x[b], y[b], 1.0)
+        c = o.cons(x[b])
+        assert_close(r["cons"][b], c, scale=max(1.0, np.abs(x[b]).max()), what=f"b={b} cons")
+        assert_close(r["jac"][b], j, scale=1e-3 * np.abs(j).max(), what=f"b={b} jac")
+        assert_close(r["hess"][b], h, scale=1e-3 * np.abs(h).max(), what=f"b={b} hess")
+        assert_close(viol[b], max(0.0, float(np.max(np.maximum(lcon - c, c - ucon)))), scale=max(1.0, np.abs(x[b]).max()),
+                     what=f"b={b} violation (stand-alone norm kernel for wide elements)")
