@@ -19,7 +19,7 @@ edge = t[:WPC]; tiles = t[WPC:]
 tiles = tiles[tiles[:, 0] > 0]
 t0 = min(tiles[:, 0].min(), edge[edge[:, 0] > 0][:, 0].min())
 print("warps traced", len(tiles), " kernel span (first start -> last end) us:", (tiles[:, 6].max() - t0) / 1e3)
-names = ["start", "loads_done", "phaseA_done", "B_start(after wait)", "B_done", "bulk_read_done", "end"]
+names = ["start", "loads_done", "phaseA_done", "B_start(after wait)", "B_done", "published", "end"]
 for k in range(7):
     v = (tiles[:, k] - t0) / 1e3
     print(f"  {names[k]:20s} min {v.min():7.2f} p50 {np.median(v):7.2f} p90 {np.percentile(v,90):7.2f} max {v.max():7.2f}")
