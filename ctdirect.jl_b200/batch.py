@@ -61,3 +61,77 @@ class ShardedScenarios:
         """Local evaluation of (objective, violation) followed by the all-gather: global vectors."""
         obj, viol = self.docp.norms(x)
         return gather_norms(obj, viol, self.n_instances, group)
+
+
+class NormsPipeline:
+    """Overlaps the all-gather of batched evaluation k with the kernel of evaluation k+1.
+
+    At 8 GPUs the local evaluation of 512 instances takes about 48 us and the NCCL all-gather of the
+    2*B doubles about 25 us of pure latency; issued back to back on one stream they add up.  Here the
+    collective runs on its own stream behind an event, `depth` result slots deep: `submit` enqueues
+    evaluation k (its objective / violation vectors land directly in the slot that is gathered) and the
+    gather of that slot; `result(slot)` makes the caller's stream wait for that gather and returns the
+    (world, 2, n_local) tensor.  With CPU tensors (gloo, tests) there are no streams and every step is
+    serial; the results are identical.
+
+    `evaluate(slot, obj, viol)` is the user's evaluation: it must write the local objective and violation
+    vectors into the two given rows (e.g. `DOCP.evaluate_with_norms(..., out={"obj": obj}, viol=viol)`)."""
+
+    def __init__(self, n_local: int, device, group=None, depth: int = 2, eval_stream=None):
+        import torch
+        import torch.distributed as dist
+        self.group = group
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.depth = depth
+        self.cuda = torch.device(device).type == "cuda"
+        self.local = [torch.zeros((2, n_local), dtype=torch.float64, device=device) for _ in range(depth)]
+        self.gathered = [torch.zeros((self.world * 2, n_local), dtype=torch.float64, device=device) for _ in range(depth)]
+        self.k = 0
+        if self.cuda:
+            self.eval_stream = eval_stream if eval_stream is not None else torch.cuda.current_stream(device)
+            self.comm_stream = torch.cuda.Stream(device=device)
+            self.ev_done = [torch.cuda.Event() for _ in range(depth)]
+            self.ev_gathered = [torch.cuda.Event() for _ in range(depth)]
+            self.used = [False] * depth
+
+    def submit(self, evaluate) -> int:
+        """Enqueue one evaluation and the all-gather of its norms; returns the slot holding the result."""
+        import torch
+        import torch.distributed as dist
+        s = self.k % self.depth
+        self.k += 1
+        if not self.cuda:
+            evaluate(s, self.local[s][0], self.local[s][1])
+            if self.world > 1:
+                dist.all_gather_into_tensor(self.gathered[s], self.local[s], group=self.group)
+            else:
+                self.gathered[s].copy_(self.local[s])
+            return s
+        if self.used[s]:   # the slot's previous gather must have read the local vectors
+            self.eval_stream.wait_event(self.ev_gathered[s])
+        with torch.cuda.stream(self.eval_stream):
+            evaluate(s, self.local[s][0], self.local[s][1])
+        self.ev_done[s].record(self.eval_stream)
+        self.comm_stream.wait_event(self.ev_done[s])
+        with torch.cuda.stream(self.comm_stream):
+            if self.world > 1:
+                dist.all_gather_into_tensor(self.gathered[s], self.local[s], group=self.group)
+            else:
+                self.gathered[s].copy_(self.local[s], non_blocking=True)
+        self.ev_gathered[s].record(self.comm_stream)
+        self.used[s] = True
+        return s
+
+    def result(self, slot: int, stream=None):
+        """The gathered norms of `slot` as a (world, 2, n_local) tensor; `stream` (default: the evaluation
+        stream) is made to wait for the collective."""
+        if self.cuda and self.used[slot]:
+            (stream if stream is not None else self.eval_stream).wait_event(self.ev_gathered[slot])
+        return self.gathered[slot].view(self.world, 2, -1)
+
+    def drain(self):
+        """Make the evaluation stream wait for every outstanding gather."""
+        if self.cuda:
+            for s in range(self.depth):
+                if self.used[s]:
+                    self.eval_stream.wait_event(self.ev_gathered[s])

@@ -248,34 +248,32 @@ struct TileSink {
     template <int N> __device__ __forceinline__ void gv(double v) { if (PG) red[C::R_G + E::G_V(N, 2)] += owner ? v : 0.0; }
 };
 
-// Sink of an edge job: every value goes to its own entry of one layer of the edge buffer (plain
-// stores: inside a layer no two values share an entry), through the host-built map.
+// Sink of an edge step job: like a tile, every value is staged at its compile-time slot of the task's
+// staging block (one STS each, no map lookups or branches in the derivative code); the whole CTA then
+// places the staged values into the edge buffer through the host-built map (edge_cta below).
 // map codes: >= 0 edge-buffer index, -1 not in the pattern (dropped), <= -2 reduction slot -(m+2).
 template <class E, int F>
 struct EdgeSink {
     using C = Cfg<E, F>;
-    double* buf;
-    const int* map;
+    double* st;       // staging block of this task: C::M_STEP doubles, laid out like the task's map
+    bool sums;        // this task contributes to the global sums (it is not a halo re-evaluation)
     double* crow;     // destination of the constraint rows (global) or nullptr
     double* red;
-    __device__ __forceinline__ void put(int m, double v) {
-        if (m >= 0) buf[m] = v;
-    }
     template <int R> __device__ __forceinline__ void c(double v) {
         if (crow) {
             crow[R] = v;
             if constexpr (C::WV) red[C::R_V] = nanmax(red[C::R_V], row_violation(E::CON_LB(R), E::CON_UB(R), v));
         }
     }
-    template <int N> __device__ __forceinline__ void jo(double v) { put(map[C::M_JO + N], v); }
-    template <int N> __device__ __forceinline__ void jn(double v) { put(map[C::M_JN + N], v); }
-    template <int N> __device__ __forceinline__ void jv(double v) { put(map[C::M_JV + N], v); }
-    template <int N> __device__ __forceinline__ void ho(double v) { put(map[C::M_HO + N], v); }
-    template <int N> __device__ __forceinline__ void hn(double v) { put(map[C::M_HN + N], v); }
-    template <int K> __device__ __forceinline__ void hv(double v) { if (map[C::M_STEP]) red[C::R_H + K] += v; }
-    template <int N> __device__ __forceinline__ void go(double v) { put(map[C::M_GO + N], v); }
-    template <int N> __device__ __forceinline__ void gn(double v) { put(map[C::M_GN + N], v); }
-    template <int N> __device__ __forceinline__ void gv(double v) { if (map[C::M_STEP]) red[C::R_G + E::G_V(N, 2)] += v; }
+    template <int N> __device__ __forceinline__ void jo(double v) { st[C::M_JO + N] = v; }
+    template <int N> __device__ __forceinline__ void jn(double v) { st[C::M_JN + N] = v; }
+    template <int N> __device__ __forceinline__ void jv(double v) { st[C::M_JV + N] = v; }
+    template <int N> __device__ __forceinline__ void ho(double v) { st[C::M_HO + N] = v; }
+    template <int N> __device__ __forceinline__ void hn(double v) { st[C::M_HN + N] = v; }
+    template <int K> __device__ __forceinline__ void hv(double v) { if (sums) red[C::R_H + K] += v; }
+    template <int N> __device__ __forceinline__ void go(double v) { st[C::M_GO + N] = v; }
+    template <int N> __device__ __forceinline__ void gn(double v) { st[C::M_GN + N] = v; }
+    template <int N> __device__ __forceinline__ void gv(double v) { if (sums) red[C::R_G + E::G_V(N, 2)] += v; }
 };
 
 // final path / boundary elements (edge CTA only): c<R>, j<N>, h<N>, g<N>
@@ -333,7 +331,7 @@ constexpr int EDGE_LAYERS = 4;   // step tasks 0/2, step task 1, final path, bou
 template <class E, int F, bool PA, bool PB>
 __device__ __forceinline__ void edge_step_job(const EvalArgs& a, const EdgeTask& tk, const double* __restrict__ x,
                                               const double* __restrict__ y, const double* __restrict__ p, double* c,
-                                              double* layer, const int* smap, double* red) {
+                                              double* stage, const int* smap, double* red) {
     using C = Cfg<E, F>;
     constexpr bool JC = PA && C::WC, JJ = PA && C::WJ, JH = PB && C::WH, JG = PA && C::WG, JO = PA && C::WO;
     double z[E::NZ], lam[E::CB];
@@ -343,8 +341,8 @@ __device__ __forceinline__ void edge_step_job(const EvalArgs& a, const EdgeTask&
     TimeArgs<E::NV> Tm;
     time_args<E>(a, z + E::NOWN + E::NNEXT, p, tk.step, Tm);
     EdgeSink<E, F> s;
-    s.buf = layer;
-    s.map = smap + tk.map_off;
+    s.st = stage;
+    s.sums = smap[tk.map_off + C::M_STEP] != 0;
     s.crow = (JC && tk.own) ? c + (long long)(tk.step - 1) * E::CB : nullptr;
     s.red = red;
     if constexpr (JC || JJ || JH) E::template step<JC, JJ, JH>(z, Tm, p, lam, a.sigma, s);
@@ -363,6 +361,8 @@ __device__ void edge_cta(const EvalArgs& a, const double* __restrict__ x, const 
     // the position maps are staged in shared memory first (one coalesced pass): the sinks look up one
     // map entry per value, and those lookups must not be dependent global loads
     int* smap = reinterpret_cast<int*>(buf + EDGE_LAYERS * ne);
+    // staging blocks of the step tasks (behind the maps): see EdgeSink
+    double* stage = buf + EDGE_LAYERS * ne + (a.nmap + 1) / 2;
     for (int k = tid; k < a.nmap; k += T) smap[k] = __ldg(a.edge_map + k);
     for (int k = tid; k < EDGE_LAYERS * ne; k += T) buf[k] = 0.0;
     __syncthreads();
@@ -375,12 +375,12 @@ __device__ void edge_cta(const EvalArgs& a, const double* __restrict__ x, const 
         const int lane_ = tid & 31, warp_ = tid >> 5;
         if (lane_ < a.ntask) {
             const EdgeTask tk = a.task[lane_];
-            double* layer = buf + (lane_ & 1) * ne;
+            double* st = stage + lane_ * C::M_STEP;
             if constexpr (TWO) {
-                if (warp_ == W_A) edge_step_job<E, F, true, false>(a, tk, x, y, p, c, layer, smap, red);
-                if (warp_ == W_B) edge_step_job<E, F, false, true>(a, tk, x, y, p, c, layer, smap, red);
+                if (warp_ == W_A) edge_step_job<E, F, true, false>(a, tk, x, y, p, c, st, smap, red);
+                if (warp_ == W_B) edge_step_job<E, F, false, true>(a, tk, x, y, p, c, st, smap, red);
             } else {
-                if (warp_ == W_A) edge_step_job<E, F, C::PHASE_A, C::PHASE_B>(a, tk, x, y, p, c, layer, smap, red);
+                if (warp_ == W_A) edge_step_job<E, F, C::PHASE_A, C::PHASE_B>(a, tk, x, y, p, c, st, smap, red);
             }
         }
         if (lane_ == 0) {
@@ -432,6 +432,23 @@ __device__ void edge_cta(const EvalArgs& a, const double* __restrict__ x, const 
                 if constexpr (C::WO) red[C::R_O] += E::mayer(z, p);
             }
         }
+    }
+    __syncthreads();
+    // ---- place the staged values of the step tasks (tasks 0/2 -> layer 0, task 1 -> layer 1: inside a
+    //      layer no two values share an entry, so these are plain stores)
+    for (int t = 0; t < a.ntask; ++t) {
+        const int* mp = smap + a.task[t].map_off;
+        const double* st = stage + t * C::M_STEP;
+        double* layer = buf + (t & 1) * ne;
+        auto place = [&](int lo, int hi) {
+            for (int k = lo + tid; k < hi; k += T) {
+                const int m = mp[k];
+                if (m >= 0) layer[m] = st[k];
+            }
+        };
+        if constexpr (C::WJ) place(C::M_JO, C::M_HO);
+        if constexpr (C::WH) place(C::M_HO, C::M_GO);
+        if constexpr (C::WG) place(C::M_GO, C::M_STEP);
     }
     __syncthreads();
     // ---- scatter the edge buffer (layers summed in a fixed order)
@@ -707,6 +724,12 @@ __device__ __forceinline__ void eval_body(const EvalArgs& a) {
 #ifndef CTD_PARTS
 #define CTD_PARTS 2
 #endif
+#ifndef CTD_PART_HW
+#define CTD_PART_HW 1
+#endif
+#ifndef CTD_PART_OWN
+#define CTD_PART_OWN 31
+#endif
 
 template <class E, int F>
 struct PCfg {
@@ -716,7 +739,7 @@ struct PCfg {
     static constexpr int PER_STEP = (C::WC ? E::CB : 0) + (C::WJ ? E::J_BLOCK + C::NJV : 0) + (C::WH ? E::H_BLOCK : 0) +
                                     (C::WG ? E::BLK : 0);
     static constexpr int FIT = PER_STEP > 0 ? (C::SMEM_MAX - 2048) / (PER_STEP * 8) - 1 : 31;
-    static constexpr int OWN = (31 < FIT) ? 31 : FIT;
+    static constexpr int OWN = (CTD_PART_OWN < FIT) ? CTD_PART_OWN : FIT;
     static_assert(OWN >= 1, "element too wide for one SM's shared memory");
     static constexpr int even(int n) { return (n + 3) & ~1; }
     static constexpr int S_C = 0;
@@ -740,7 +763,10 @@ struct PCfg {
     static constexpr int O_GN = O_GO + (C::WG ? E::NG_OWN : 0);
     static constexpr int O_GV = O_GN + (C::WG ? E::NG_NEXT : 0);
     static constexpr int TOT = O_GV + (C::WG ? E::NG_V : 0);
-    static constexpr int part_of(int g) { return TOT > 0 ? (int)((long long)g * P / TOT) : 0; }
+    // a Hessian value costs about CTD_PART_HW times the instructions of a Jacobian value: the split is by
+    // weighted index so that the parts take about the same time
+    static constexpr long long wpos(int g) { return g < O_HO ? g : (g < O_GO ? O_HO + (long long)(g - O_HO) * CTD_PART_HW : O_HO + (long long)(O_GO - O_HO) * CTD_PART_HW + (g - O_GO)); }
+    static constexpr int part_of(int g) { return TOT > 0 ? (int)(wpos(g) * P / wpos(TOT)) : 0; }
 };
 
 template <class E, int F, int PART>
@@ -853,8 +879,10 @@ __global__ void __launch_bounds__(PCfg<E, F>::T) ctd_eval_kernel_parts(const Eva
         if (tid == 0) cta_ticket = 0u;
         __syncthreads();
     }
+    CTD_STAMP(0);
     if (cta == 0) {
         edge_cta<E, F>(a, x, y, p, c, jvals, hvals, grad, smem, red, PC::P);
+        CTD_STAMP(4);
     } else {
         const long long i0 = 2 + (long long)(cta - 1) * PC::OWN;
         const long long left = (long long)a.N - 1 - i0 + 1;
@@ -890,9 +918,15 @@ __global__ void __launch_bounds__(PCfg<E, F>::T) ctd_eval_kernel_parts(const Eva
             for (int r = 0; r < E::CB; ++r) lam[r] = (C::WH && y) ? __ldg(y + (i - 1) * E::CB + r) : 0.0;
             time_args<E>(a, z + E::NOWN + E::NNEXT, p, i, Tm);
         }
+#ifdef CTD_TRACE
+        if (active && Tm.hh == -1.2345) CTD_STAMP(7);   // forces the loads to have arrived
+        CTD_STAMP(1);
+#endif
         PartDispatch<E, F, 0>::run(warp, a, z, lam, Tm, p, red, active, owner, ob, nb, sC, sJ, sJV, sH, sG);
+        CTD_STAMP(2);
         fence_proxy_async_smem();
         __syncthreads();
+        CTD_STAMP(3);
         if (warp == 0 && nown > 0) {
             if constexpr (C::WC) bulk_store_range(gC, sC, nown * E::CB, lane);
             if constexpr (C::WJ) {
@@ -909,8 +943,11 @@ __global__ void __launch_bounds__(PCfg<E, F>::T) ctd_eval_kernel_parts(const Eva
                 bulk_wait_read();   // shared memory must outlive the copies that read it
             }
         }
+        CTD_STAMP(4);
     }
     publish_reduction<E, F>(a, red, smem + PC::S_RED, &cta_ticket, inst, cta, lane, warp, hvals, grad, PC::P);
+    CTD_STAMP(5);
+    CTD_STAMP(6);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -667,7 +667,11 @@ void Model::eval_dev(int flags, const double* x, const double* y, double sigma, 
         const int64_t ptiles = (N_ >= 3) ? ((int64_t)N_ - 2 + lc.p_own - 1) / lc.p_own : 0;
         // (measured: robot/trapeze with 3226 tiles is 40 % faster through the one-warp-per-tile kernel, the
         //  3-stage IRK at 645 tiles 2.5x faster through the parts kernel)
-        if (ptiles * batch_ * (lc.p_threads / 32) <= (int64_t)148 * 16) {
+        bool use_parts = ptiles * batch_ * (lc.p_threads / 32) <= (int64_t)148 * 16;
+#ifdef CTD_TRACE
+        if (getenv("CTD_NO_PARTS")) use_parts = false;   // debug builds: the timeline exists only in the one-warp kernel
+#endif
+        if (use_parts) {
             parts = 1;
             threads = lc.p_threads;
             a.tiles = (int)ptiles;
@@ -677,7 +681,9 @@ void Model::eval_dev(int flags, const double* x, const double* y, double sigma, 
     }
     // the edge CTA uses the same dynamic shared memory as its value buffer (its reduction scratch at
     // S_RED is only touched after the buffer has been scattered)
-    const size_t edge_smem = sizeof(double) * (EDGE_LAYERS * ((size_t)ne_j_ + ne_h_ + ne_g_) + 2) + sizeof(int) * (edge_map_.size() + 2);
+    // (layers, position maps, then one staging block per step task)
+    const size_t edge_smem = sizeof(double) * (EDGE_LAYERS * ((size_t)ne_j_ + ne_h_ + ne_g_) + 2) + sizeof(int) * (edge_map_.size() + 2) +
+                             sizeof(double) * (size_t)ntask_ * (size_t)lc.map_step;
     const size_t smem = std::max(tile_smem, edge_smem);
     const int pkey = flags + 256 * parts;
     auto it = prepared_.find(pkey);
@@ -689,7 +695,7 @@ void Model::eval_dev(int flags, const double* x, const double* y, double sigma, 
 #ifdef CTD_TRACE
     // debug builds only: per-warp timestamps of the launch, dumped as raw int64 to $CTD_TRACE_FILE
     long long* d_trace = nullptr;
-    const size_t ntrace = (size_t)a.ctas * lc.wpc * 8;
+    const size_t ntrace = (size_t)a.ctas * std::max(lc.wpc, std::max(threads, lc.p_threads) / 32) * 8;
     const char* trace_file = getenv("CTD_TRACE_FILE");
     if (trace_file) {
         CTD_CUDA(cudaMalloc(&d_trace, ntrace * sizeof(long long)));

@@ -243,6 +243,35 @@ class DOCP:
 
         return call, res
 
+    def bind_with_norms(self, what: int, x, y=None, obj_weight: float = 1.0, out=None, viol=None):
+        """`bind` for `evaluate_with_norms` (CUDA tensors): buffers validated once, one ctypes call per
+        evaluation afterwards.  Returns (callable, result dict, viol tensor)."""
+        import torch
+        x = self._check_in(x, self.nvar, "x")
+        y = self._check_in(y, self.ncon, "y")
+        if not _is_torch(x) or not (what & CONS):
+            raise TypeError("bind_with_norms needs CUDA tensors and CONS among the outputs")
+        out = dict(out or {})
+        res = {}
+        for bit, key, n in ((OBJ, "obj", 1), (GRAD, "grad", self.nvar), (CONS, "cons", self.ncon),
+                            (JAC, "jac", self.nnzj), (HESS, "hess", self.nnzh)):
+            if what & bit:
+                buf = out.get(key)
+                res[key] = self._check_in(buf, n, key) if buf is not None else self._empty_like(x, n)
+        if viol is None:
+            viol = torch.empty(self.batch, dtype=torch.float64, device=x.device)
+        fn = self._lib.ctd_eval_norms_dev
+        args = (self._h, int(what), _ptr(x), _ptr(y), C.c_double(float(obj_weight)), _ptr(res.get("obj")),
+                _ptr(res.get("grad")), _ptr(res.get("cons")), _ptr(res.get("jac")), _ptr(res.get("hess")), _ptr(viol))
+        keep = (x, y, res, viol)
+
+        def call(_fn=fn, _args=args, _keep=keep):
+            code = _fn(*_args)
+            if code != 0:
+                _lib.check(code)
+
+        return call, res, viol
+
     def norms(self, x):
         """Per-instance (objective, max constraint violation): what a batched MPC driver gathers."""
         x = self._check_in(x, self.nvar, "x")

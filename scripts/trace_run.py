@@ -1,10 +1,14 @@
-"""Debug: per-warp timeline of one launch (needs a -DCTD_TRACE build). usage: trace_run.py FLAGS WPC"""
+"""Debug: per-warp timeline of one launch (needs a -DCTD_TRACE build).
+usage: trace_run.py FLAGS WPC [problem scheme N]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 F = int(sys.argv[1]); WPC = int(sys.argv[2])
 import ctdirect_b200 as ctd
-d = ctd.DOCP("goddard", 100000, "midpoint")
+PROB = sys.argv[3] if len(sys.argv) > 3 else "goddard"
+SCH = sys.argv[4] if len(sys.argv) > 4 else "midpoint"
+NN = int(sys.argv[5]) if len(sys.argv) > 5 else 100000
+d = ctd.DOCP(PROB, NN, SCH)
 dev = torch.device("cuda", 0)
 rng = np.random.default_rng(0)
 x = torch.from_numpy(d.initial_guess() * (1 + 1e-3 * rng.uniform(-1, 1, d.nvar))).to(dev)

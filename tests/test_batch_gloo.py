@@ -62,3 +62,50 @@ def test_gather_norms_single_process():
     from ctdirect_b200.batch import gather_norms
     o, v = gather_norms(torch.tensor([1.0, 2.0], dtype=torch.float64), torch.tensor([0.5, 0.0], dtype=torch.float64), 2)
     assert o.tolist() == [1.0, 2.0] and v.tolist() == [0.5, 0.0]
+
+
+def _pipe_worker(rank, world, port, n_local, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ctdirect_b200.batch import NormsPipeline
+        pipe = NormsPipeline(n_local, "cpu", depth=2)
+        got = []
+        for k in range(5):
+            def ev(slot, obj, viol, k=k):
+                obj.copy_(torch.arange(n_local, dtype=torch.float64) + 100.0 * rank + 1000.0 * k)
+                viol.fill_(float(k - rank))
+            s = pipe.submit(ev)
+            got.append(pipe.result(s).clone().numpy())
+        pipe.drain()
+        q.put((rank, got))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_norms_pipeline_gloo_world2():
+    """The pipelined gather (serial on CPU tensors) returns every evaluation's norms of every rank, in order."""
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    n_local = 3
+    procs = [ctx.Process(target=_pipe_worker, args=(r, 2, port, n_local, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=60) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, got in res:
+        for k, g in enumerate(got):
+            assert g.shape == (2, 2, n_local)
+            for r in range(2):
+                np.testing.assert_array_equal(g[r, 0], np.arange(n_local) + 100.0 * r + 1000.0 * k)
+                np.testing.assert_array_equal(g[r, 1], np.full(n_local, float(k - r)))
