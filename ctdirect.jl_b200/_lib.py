@@ -68,6 +68,11 @@ SIGNATURES = {
     "ctd_sync": (C.c_int, [_H]),
     "ctd_stream": (C.c_void_p, [_H]),
     "ctd_launch_count": (C.c_int64, [_H]),
+    "ctd_nccl_unique_id": (C.c_int, [C.c_char_p]),
+    "ctd_nccl_version": (C.c_int, []),
+    "ctd_comm_init": (C.c_int, [_H, C.c_char_p, C.c_int32, C.c_int32]),
+    "ctd_gather_norms_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int32]),
+    "ctd_comm_wait": (C.c_int, [_H, C.c_int32]),
 }
 
 

@@ -135,3 +135,62 @@ class NormsPipeline:
             for s in range(self.depth):
                 if self.used[s]:
                     self.eval_stream.wait_event(self.ev_gathered[s])
+
+
+def broadcast_unique_id(group=None) -> bytes:
+    """Create the NCCL id of the library's communicator on rank 0 and hand it to every rank through the
+    existing torch.distributed group (any backend)."""
+    import torch.distributed as dist
+    from .docp import DOCP
+    box = [DOCP.nccl_unique_id() if dist.get_rank(group) == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    return box[0]
+
+
+class NativeNormsPipeline:
+    """`NormsPipeline` on the library's own communicator: the evaluation and the all-gather are two C calls
+    per step (ctd_eval_norms_dev, ctd_gather_norms_dev), the collective runs on a high-priority stream owned
+    by the handle, and slot events replace the Python-side stream bookkeeping.  Shards must have the same
+    size on every rank.
+
+        pipe = NativeNormsPipeline(docp, rank, world, unique_id)
+        slot = pipe.submit(what, x, y, out)        # evaluation k and its gather (overlaps evaluation k+1)
+        norms = pipe.result(slot)                  # (world, 2, batch) tensor, valid on the handle's stream
+    """
+
+    def __init__(self, docp, rank: int, world: int, unique_id: bytes, depth: int = 2):
+        import torch
+        if not (1 <= depth <= 4):
+            raise ValueError("depth must be 1..4 (CTD_COMM_SLOTS)")
+        self.docp, self.world, self.depth, self.k = docp, world, depth, 0
+        docp.comm_init(unique_id, rank, world)
+        dev = torch.device("cuda", docp.device)
+        self.local = [torch.zeros((2, docp.batch), dtype=torch.float64, device=dev) for _ in range(depth)]
+        self.gathered = [torch.zeros((world, 2, docp.batch), dtype=torch.float64, device=dev) for _ in range(depth)]
+        self._bound = {}
+
+    def submit(self, what: int, x, y=None, out=None, obj_weight: float = 1.0, serial: bool = False) -> int:
+        s = self.k % self.depth
+        self.k += 1
+        key = (s, what, x.data_ptr(), 0 if y is None else y.data_ptr(), obj_weight,
+               tuple(sorted((k, v.data_ptr()) for k, v in (out or {}).items() if k != "obj")))
+        call = self._bound.get(key)
+        if call is None:   # buffers are validated once per distinct set
+            o = dict(out or {})
+            o["obj"] = self.local[s][0]
+            call = self.docp.bind_with_norms(what, x, y, obj_weight, out=o, viol=self.local[s][1])[0]
+            self._bound[key] = call
+        self.docp.comm_wait(s)          # the gather that last used this slot has read local[s]
+        call()
+        self.docp.gather_norms(self.local[s], self.gathered[s], s)
+        if serial:
+            self.docp.comm_wait(s)
+        return s
+
+    def result(self, slot: int):
+        self.docp.comm_wait(slot)
+        return self.gathered[slot]
+
+    def drain(self):
+        for s in range(self.depth):
+            self.docp.comm_wait(s)

@@ -40,7 +40,7 @@ def _common_deps():
 
 
 def _sources(only=None):
-    srcs = [os.path.join(CSRC, "ctd_model.cu"), os.path.join(CSRC, "ctd_capi.cu")]
+    srcs = [os.path.join(CSRC, "ctd_model.cu"), os.path.join(CSRC, "ctd_capi.cu"), os.path.join(CSRC, "ctd_comm.cu")]
     manifest = os.path.join(GEN, "MANIFEST.txt")
     if not os.path.exists(manifest):
         raise RuntimeError("csrc/generated/MANIFEST.txt missing: run python -m ctdirect_b200.gen.generate")
@@ -85,7 +85,7 @@ def build(force: bool = False, only=None, jobs: int | None = None, verbose: bool
                 f.result()
     if tasks or not os.path.exists(LIB) or force:
         cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
-               "-o", LIB, *objs]
+               "-o", LIB, *objs, "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

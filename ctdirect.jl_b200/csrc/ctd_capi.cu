@@ -8,6 +8,8 @@
 
 using namespace ctd;
 
+static_assert(CTD_COMM_SLOTS == kCommSlots && CTD_NCCL_ID_BYTES == kNcclIdBytes, "header and model disagree");
+
 struct ctd_model_s {
     Model* m;
 };
@@ -248,6 +250,32 @@ void* ctd_stream(ctd_handle h) {
 int64_t ctd_launch_count(ctd_handle h) {
     if (check(h)) return -1;
     return h->m->launches();
+}
+
+int ctd_nccl_unique_id(char id[CTD_NCCL_ID_BYTES]) {
+    if (!id) return fail(-2, "ctd_nccl_unique_id: NULL argument");
+    return guarded([&] { nccl_unique_id(id); });
+}
+
+int ctd_nccl_version(void) {
+    int v = 0;
+    const int e = guarded([&] { v = nccl_version(); });
+    return e ? (e > 0 ? -e : e) : v;
+}
+
+int ctd_comm_init(ctd_handle h, const char id[CTD_NCCL_ID_BYTES], int32_t rank, int32_t world) {
+    if (int e = check(h)) return e;
+    return guarded([&] { h->m->comm_init(id, rank, world); });
+}
+
+int ctd_gather_norms_dev(ctd_handle h, const double* local, double* gathered, int32_t slot) {
+    if (int e = check(h)) return e;
+    return guarded([&] { h->m->gather_norms_dev(local, gathered, slot); });
+}
+
+int ctd_comm_wait(ctd_handle h, int32_t slot) {
+    if (int e = check(h)) return e;
+    return guarded([&] { h->m->comm_wait(slot); });
 }
 
 }  // extern "C"

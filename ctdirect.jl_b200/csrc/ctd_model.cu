@@ -137,6 +137,7 @@ Model::Model(const Registration& reg, int grid_size, const double* time_grid, in
 Model::~Model() {
     if (dev_ready_) {
         cudaSetDevice(device_);
+        comm_destroy();
         if (stream_) cudaStreamSynchronize(stream_);   // nothing of this handle may still be in flight
         cudaFree(d_edge_map_); cudaFree(d_edge_pos_); cudaFree(d_sgrid_); cudaFree(d_params_);
         cudaFree(d_partials_); cudaFree(d_counters_);

@@ -63,6 +63,9 @@ class BlockPattern {
     std::vector<Rect> rects_;
 };
 
+constexpr int kCommSlots = 4;      // result slots of the pipelined gather
+constexpr int kNcclIdBytes = 128;  // sizeof(ncclUniqueId)
+
 class Model {
   public:
     Model(const Registration& reg, int grid_size, const double* time_grid, int n_time_grid, const double* params,
@@ -107,6 +110,12 @@ class Model {
     void sync();
     cudaStream_t stream();
     int64_t launches() const { return launches_; }
+    // multi-GPU norm gather (ctd_comm.cu)
+    void comm_init(const char* nccl_id, int rank, int world);
+    void comm_destroy();
+    void gather_norms_dev(const double* local, double* gathered, int slot);
+    void comm_wait(int slot);
+    int comm_world() const { return comm_world_; }
 
   private:
     void build_patterns();
@@ -140,7 +149,16 @@ class Model {
            *d_obj_ = nullptr, *d_lcon_ = nullptr, *d_ucon_ = nullptr, *d_viol_ = nullptr;
     std::map<int, size_t> prepared_;  // flags (+ 256 for the parts variant) -> dynamic smem size
     int64_t launches_ = 0;
+    // communicator state (only after comm_init)
+    void* comm_ = nullptr;
+    int comm_rank_ = 0, comm_world_ = 0;
+    cudaStream_t comm_stream_ = nullptr;
+    cudaEvent_t ev_issue_ = nullptr, ev_gathered_[kCommSlots] = {};
+    bool slot_used_[kCommSlots] = {};
 };
+
+void nccl_unique_id(char* id);   // kNcclIdBytes bytes
+int nccl_version();
 
 struct CtdError {
     int code;

@@ -354,6 +354,31 @@ class DOCP:
     def synchronize(self):
         _lib.check(self._lib.ctd_sync(self._h))
 
+    # ---- multi-GPU norm gather through the library's own NCCL communicator (ctd_comm_* of the C ABI) ----
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        """128 bytes created by ONE rank; hand them to every rank before `comm_init`."""
+        lib = _lib.load()
+        buf = C.create_string_buffer(128)
+        _lib.check(lib.ctd_nccl_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        """Join the communicator of the batch (every rank calls this with the same id)."""
+        if len(unique_id) != 128:
+            raise ValueError("unique_id must be the 128 bytes of nccl_unique_id()")
+        _lib.check(self._lib.ctd_comm_init(self._h, C.c_char_p(unique_id), int(rank), int(world)))
+        self.comm_world = int(world)
+
+    def gather_norms(self, local, gathered, slot: int = 0):
+        """Enqueue the all-gather of `local` (2 x batch CUDA tensor: objective row, violation row) into
+        `gathered` (world x 2 x batch) behind everything issued on this handle so far; slot < 4."""
+        _lib.check(self._lib.ctd_gather_norms_dev(self._h, _ptr(local), _ptr(gathered), int(slot)))
+
+    def comm_wait(self, slot: int = 0):
+        """Make this handle's stream wait until the gather that last used `slot` has landed."""
+        _lib.check(self._lib.ctd_comm_wait(self._h, int(slot)))
+
     @property
     def cuda_stream(self) -> int:
         return int(self._lib.ctd_stream(self._h) or 0)

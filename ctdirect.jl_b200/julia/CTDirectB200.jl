@@ -138,4 +138,23 @@ function b200_model_builder(problem::AbstractString, docp)
     end
 end
 
+# ---- batched scenarios on several GPUs: the library's own NCCL communicator (include/ctdirect_b200.h) ----
+"128 bytes created by ONE rank; broadcast them to every rank (MPI, Distributed, a file) before `comm_init!`."
+function nccl_unique_id()
+    id = Vector{UInt8}(undef, 128)
+    check(ccall((:ctd_nccl_unique_id, LIB), Cint, (Ptr{UInt8},), id))
+    return id
+end
+
+comm_init!(handle::Ptr{Cvoid}, id::Vector{UInt8}, rank::Integer, world::Integer) =
+    check(ccall((:ctd_comm_init, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int32, Int32), handle, id, rank, world))
+
+"All-gather of the 2*batch doubles at device pointer `localp` into `gatheredp` (world*2*batch), slot in 0:3."
+gather_norms!(handle::Ptr{Cvoid}, localp, gatheredp, slot::Integer) =
+    check(ccall((:ctd_gather_norms_dev, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32), handle, localp, gatheredp, slot))
+
+"Make the handle's stream wait until the gather that last used `slot` has landed."
+comm_wait!(handle::Ptr{Cvoid}, slot::Integer) =
+    check(ccall((:ctd_comm_wait, LIB), Cint, (Ptr{Cvoid}, Int32), handle, slot))
+
 end # module

@@ -161,6 +161,28 @@ CTD_API void* ctd_stream(ctd_handle h);
 /* number of kernel launches issued through this handle so far */
 CTD_API int64_t ctd_launch_count(ctd_handle h);
 
+/* ---- multi-GPU norm gather (the reference has no batching, every scenario is its own DOCP,
+ * src/DOCP_data.jl:293).  One process per GPU; each rank owns a batched handle for its shard of the
+ * instances (all shards the same size).  The only exchange is the all-gather of the per-instance
+ * (objective, violation) pairs over NCCL, issued by the library on a stream of its own.
+ *   rank 0: ctd_nccl_unique_id(id); the caller hands the 128 bytes to every rank (MPI, a file, a TCP store...)
+ *   every rank: ctd_comm_init(h, id, rank, world)
+ *   per evaluation k, slot s = k % CTD_COMM_SLOTS:
+ *     ctd_comm_wait(h, s)                      -- the gather that last used slot s has landed (frees local_s)
+ *     ctd_eval_norms_dev(h, ..., f = local_s, ..., viol = local_s + batch)
+ *     ctd_gather_norms_dev(h, local_s, gathered_s, s)
+ *   before reading gathered_s on the handle's stream: ctd_comm_wait(h, s) (then ctd_sync for the host).
+ * local_s: 2*batch doubles [objective | violation]; gathered_s: world*2*batch doubles, rank-major.
+ * Waiting right after every gather serialises kernel and collective; waiting only before the slot is
+ * reused overlaps the gather of evaluation k with the kernel of evaluation k+1. */
+#define CTD_COMM_SLOTS 4
+#define CTD_NCCL_ID_BYTES 128
+CTD_API int ctd_nccl_unique_id(char id[CTD_NCCL_ID_BYTES]);
+CTD_API int ctd_nccl_version(void);   /* e.g. 22809, or a negative error code when NCCL cannot be loaded */
+CTD_API int ctd_comm_init(ctd_handle h, const char id[CTD_NCCL_ID_BYTES], int32_t rank, int32_t world);
+CTD_API int ctd_gather_norms_dev(ctd_handle h, const double* local, double* gathered, int32_t slot);
+CTD_API int ctd_comm_wait(ctd_handle h, int32_t slot);
+
 #ifdef __cplusplus
 }
 #endif

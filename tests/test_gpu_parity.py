@@ -337,3 +337,34 @@ def test_wide_elements_on_large_grids_and_batches(ctd, oracle_mod):
         assert_close(r["hess"][b], h, scale=1e-3 * np.abs(h).max(), what=f"b={b} hess")
         assert_close(viol[b], max(0.0, float(np.max(np.maximum(lcon - c, c - ucon)))), scale=max(1.0, np.abs(x[b]).max()),
                      what=f"b={b} violation (stand-alone norm kernel for wide elements)")
+
+
+@pytest.mark.gpu
+def test_native_norm_gather_single_rank(ctd):
+    """The library's own NCCL communicator (ctd_comm_init / ctd_gather_norms_dev / ctd_comm_wait) with one
+    rank: the gathered (objective, violation) rows of every pipelined evaluation equal ctd_norms."""
+    import torch
+    from ctdirect_b200.batch import NativeNormsPipeline
+    B, N = 6, 200
+    rng = np.random.default_rng(5)
+    par = np.tile(np.array([310.0, 500.0, 2.0, 3.5]), (B, 1))
+    par[:, 3] = rng.uniform(1.0, 3.5, B)
+    d = ctd.DOCP("goddard", N, "midpoint", params=par, batch=B)
+    assert ctd._lib.load().ctd_nccl_version() > 20000
+    pipe = NativeNormsPipeline(d, 0, 1, ctd.DOCP.nccl_unique_id(), depth=2)
+    dev = torch.device("cuda", 0)
+    pts = []
+    for k in range(5):
+        x, y = synthetic_point(d, seed=100 + k, batch=B)
+        pts.append((torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev)))
+    ALL = ctd.CONS | ctd.JAC | ctd.HESS | ctd.GRAD | ctd.OBJ
+    for k, (tx, ty) in enumerate(pts):
+        s = pipe.submit(ALL, tx, ty, serial=(k == 0))
+        g = pipe.result(s)
+        d.synchronize()
+        obj, viol = d.norms(tx)
+        assert g.shape == (1, 2, B)
+        assert_close(g[0, 0].cpu().numpy(), obj.cpu().numpy(), scale=1.0, what=f"evaluation {k}: gathered objective")
+        assert_close(g[0, 1].cpu().numpy(), viol.cpu().numpy(), scale=1.0, what=f"evaluation {k}: gathered violation")
+    pipe.drain()
+    d.synchronize()
