@@ -108,7 +108,16 @@ struct Cfg {
 #ifndef CTD_MAXNREG
 #define CTD_MAXNREG 80
 #endif
-    static constexpr bool LIGHT = PER_STEP <= 64;
+    // (few staged values per step is not enough: the robot arm with the detected pattern stages 30 doubles
+    //  per step but its derivative code spills 168 bytes under an 80-register cap, the 2-stage IRK of Goddard
+    //  with the detected pattern 256 bytes)
+#ifndef CTD_LIGHT_MAXDIM
+#define CTD_LIGHT_MAXDIM 6
+#endif
+#ifndef CTD_LIGHT_MAXSTAGE
+#define CTD_LIGHT_MAXSTAGE 1
+#endif
+    static constexpr bool LIGHT = PER_STEP <= 64 && (E::NX + E::NU) <= CTD_LIGHT_MAXDIM && E::STAGE <= CTD_LIGHT_MAXSTAGE;
     static constexpr int FIT = PER_STEP > 0 ? (SMEM_MAX / WPC - 512) / (PER_STEP * 8) - 1 : 31;
     static constexpr int OWN = (31 < FIT) ? 31 : FIT;  // owned steps per warp tile
     static_assert(OWN >= 1, "element too wide for one SM's shared memory");
@@ -731,27 +740,45 @@ __device__ __forceinline__ void eval_body(const EvalArgs& a) {
 #define CTD_PART_OWN 31
 #endif
 
+#ifndef CTD_PARTS_TWO_PHASE
+#define CTD_PARTS_TWO_PHASE 1
+#endif
+
 template <class E, int F>
 struct PCfg {
     using C = Cfg<E, F>;
     static constexpr int P = CTD_PARTS;
     static constexpr int T = 32 * P;
-    static constexpr int PER_STEP = (C::WC ? E::CB : 0) + (C::WJ ? E::J_BLOCK + C::NJV : 0) + (C::WH ? E::H_BLOCK : 0) +
-                                    (C::WG ? E::BLK : 0);
+    // two phases like the one-warp kernel (A: constraints + Jacobian + gradient, B: Hessian, same shared
+    // memory) when both are requested: a 3-stage IRK step stages 290 doubles, 186 at a time with two phases
+    static constexpr bool TWO = CTD_PARTS_TWO_PHASE && C::WJ && C::WH;
+    static constexpr int PER_A = (C::WC ? E::CB : 0) + (C::WJ ? E::J_BLOCK + C::NJV : 0) + (C::WG ? E::BLK : 0);
+    static constexpr int PER_B = C::WH ? E::H_BLOCK : 0;
+    static constexpr int PER_STEP = TWO ? (PER_A > PER_B ? PER_A : PER_B) : PER_A + PER_B;
     static constexpr int FIT = PER_STEP > 0 ? (C::SMEM_MAX - 2048) / (PER_STEP * 8) - 1 : 31;
-    static constexpr int OWN = (CTD_PART_OWN < FIT) ? CTD_PART_OWN : FIT;
+    // tiles of 24..30 steps when that lets 5 CTAs share an SM (44 KB each) instead of 4
+    static constexpr int FIT5 = PER_STEP > 0 ? (44 * 1024) / (PER_STEP * 8) - 1 : 31;
+    static constexpr bool FIVE = TWO && FIT5 >= 24 && FIT5 < CTD_PART_OWN;
+    static constexpr int OWN_T = FIVE ? FIT5 : CTD_PART_OWN;
+    static constexpr int OWN = (OWN_T < FIT) ? OWN_T : FIT;
+    static constexpr int MINB = FIVE ? 5 : 1;
     static_assert(OWN >= 1, "element too wide for one SM's shared memory");
     static constexpr int even(int n) { return (n + 3) & ~1; }
     static constexpr int S_C = 0;
     static constexpr int S_J = S_C + (C::WC ? even((OWN + 1) * E::CB) : 0);
     static constexpr int S_JV = S_J + (C::WJ ? even((OWN + 1) * E::J_BLOCK) : 0);
     static constexpr int JV_ONE = even((OWN + 1) * E::JV_STRIDE);
-    static constexpr int S_H = S_JV + (C::WJ ? C::NV * JV_ONE : 0);
-    static constexpr int S_G = S_H + (C::WH ? even((OWN + 1) * E::H_BLOCK) : 0);
-    static constexpr int S_RED = S_G + (C::WG ? even((OWN + 1) * E::BLK) : 0);
+    static constexpr int A_END0 = S_JV + (C::WJ ? C::NV * JV_ONE : 0);
+    static constexpr int H_LEN = C::WH ? even((OWN + 1) * E::H_BLOCK) : 0;
+    static constexpr int G_LEN = C::WG ? even((OWN + 1) * E::BLK) : 0;
+    // one phase: c | J | Jv | H | g     two phases: A = c | J | Jv | g, B = H (from 0)
+    static constexpr int S_H = TWO ? 0 : A_END0;
+    static constexpr int S_G = TWO ? A_END0 : A_END0 + H_LEN;
+    static constexpr int S_RED0 = TWO ? ((A_END0 + G_LEN) > H_LEN ? (A_END0 + G_LEN) : H_LEN) : A_END0 + H_LEN + G_LEN;
+    static constexpr int S_RED = (S_RED0 + 1) & ~1;
     static constexpr int S_END = S_RED + P * (C::NREDX > 0 ? C::NREDX : 1) + 2;
     static constexpr size_t TILE_SMEM = (size_t)S_END * sizeof(double);
-    // every output of the element gets a running index; part = index * P / TOT
+    // every output of the element gets a running index
     static constexpr int O_C = 0;
     static constexpr int O_JO = O_C + (C::WC ? E::CB : 0);
     static constexpr int O_JN = O_JO + (C::WJ ? E::NJ_OWN : 0);
@@ -763,16 +790,25 @@ struct PCfg {
     static constexpr int O_GN = O_GO + (C::WG ? E::NG_OWN : 0);
     static constexpr int O_GV = O_GN + (C::WG ? E::NG_NEXT : 0);
     static constexpr int TOT = O_GV + (C::WG ? E::NG_V : 0);
-    // a Hessian value costs about CTD_PART_HW times the instructions of a Jacobian value: the split is by
-    // weighted index so that the parts take about the same time
+    // a Hessian value costs about CTD_PART_HW times the instructions of a Jacobian value: the one-phase
+    // split is by weighted index so that the parts take about the same time
     static constexpr long long wpos(int g) { return g < O_HO ? g : (g < O_GO ? O_HO + (long long)(g - O_HO) * CTD_PART_HW : O_HO + (long long)(O_GO - O_HO) * CTD_PART_HW + (g - O_GO)); }
-    static constexpr int part_of(int g) { return TOT > 0 ? (int)(wpos(g) * P / wpos(TOT)) : 0; }
+    // two phases: the outputs of each phase are split evenly on their own
+    static constexpr int NA = O_HO + (TOT - O_GO), NB = O_GO - O_HO;
+    static constexpr int part_of(int g) {
+        if (TOT == 0) return 0;
+        if (!TWO) return (int)(wpos(g) * P / wpos(TOT));
+        const bool hess = g >= O_HO && g < O_GO;
+        return hess ? (int)((long long)(g - O_HO) * P / NB) : (int)((long long)(g < O_HO ? g : O_HO + (g - O_GO)) * P / NA);
+    }
 };
 
-template <class E, int F, int PART>
+// PA / PB: which outputs this pass produces (both in the one-phase kernel)
+template <class E, int F, int PART, bool PA, bool PB>
 struct PartSink {
     using C = Cfg<E, F>;
     using PC = PCfg<E, F>;
+    static constexpr bool WC = PA && C::WC, WJ = PA && C::WJ, WG = PA && C::WG, WH = PB && C::WH;
     double *c_, *jo_, *jn_, *ho_, *go_;
     double* jv_[E::NV > 0 ? E::NV : 1];
     bool owner;
@@ -781,35 +817,36 @@ struct PartSink {
     double* red;
     static constexpr bool mine(int g) { return PC::part_of(g) == PART; }
     template <int R> __device__ __forceinline__ void c(double v) {
-        if constexpr (C::WC && mine(PC::O_C + R)) {
+        if constexpr (WC && mine(PC::O_C + R)) {
             c_[R] = v;
             if constexpr (C::WV) { if (owner) red[C::R_V] = nanmax(red[C::R_V], row_violation(E::CON_LB(R), E::CON_UB(R), v)); }
         }
     }
-    template <int N> __device__ __forceinline__ void jo(double v) { if constexpr (C::WJ && mine(PC::O_JO + N)) jo_[E::J_OWN(N, 2)] = v; }
-    template <int N> __device__ __forceinline__ void jn(double v) { if constexpr (C::WJ && mine(PC::O_JN + N)) jn_[E::J_NEXT(N, 2)] = v; }
+    template <int N> __device__ __forceinline__ void jo(double v) { if constexpr (WJ && mine(PC::O_JO + N)) jo_[E::J_OWN(N, 2)] = v; }
+    template <int N> __device__ __forceinline__ void jn(double v) { if constexpr (WJ && mine(PC::O_JN + N)) jn_[E::J_NEXT(N, 2)] = v; }
     template <int N> __device__ __forceinline__ void jv(double v) {
-        if constexpr (C::WJ && mine(PC::O_JV + N)) jv_[E::J_V(N, 1)][E::J_V(N, 2)] = v;
+        if constexpr (WJ && mine(PC::O_JV + N)) jv_[E::J_V(N, 1)][E::J_V(N, 2)] = v;
     }
-    template <int N> __device__ __forceinline__ void ho(double v) { if constexpr (C::WH && mine(PC::O_HO + N)) ho_[E::H_OWN(N, 2)] = v; }
-    template <int N> __device__ __forceinline__ void hn(double v) { if constexpr (C::WH && mine(PC::O_HN + N)) hn_[N] = v; }
+    template <int N> __device__ __forceinline__ void ho(double v) { if constexpr (WH && mine(PC::O_HO + N)) ho_[E::H_OWN(N, 2)] = v; }
+    template <int N> __device__ __forceinline__ void hn(double v) { if constexpr (WH && mine(PC::O_HN + N)) hn_[N] = v; }
     template <int K> __device__ __forceinline__ void hv(double v) {
-        if constexpr (C::WH && mine(PC::O_HV + K)) red[C::R_H + K] += owner ? v : 0.0;
+        if constexpr (WH && mine(PC::O_HV + K)) red[C::R_H + K] += owner ? v : 0.0;
     }
-    template <int N> __device__ __forceinline__ void go(double v) { if constexpr (C::WG && mine(PC::O_GO + N)) go_[E::G_OWN(N, 2)] = v; }
-    template <int N> __device__ __forceinline__ void gn(double v) { if constexpr (C::WG && mine(PC::O_GN + N)) gn_[N] = v; }
+    template <int N> __device__ __forceinline__ void go(double v) { if constexpr (WG && mine(PC::O_GO + N)) go_[E::G_OWN(N, 2)] = v; }
+    template <int N> __device__ __forceinline__ void gn(double v) { if constexpr (WG && mine(PC::O_GN + N)) gn_[N] = v; }
     template <int N> __device__ __forceinline__ void gv(double v) {
-        if constexpr (C::WG && mine(PC::O_GV + N)) red[C::R_G + E::G_V(N, 2)] += owner ? v : 0.0;
+        if constexpr (WG && mine(PC::O_GV + N)) red[C::R_G + E::G_V(N, 2)] += owner ? v : 0.0;
     }
 };
 
-template <class E, int F, int PART>
+template <class E, int F, int PART, bool PA, bool PB>
 __device__ __forceinline__ void run_part(const EvalArgs& a, const double* z, const double* lam, const TimeArgs<E::NV>& Tm,
                                          const double* __restrict__ p, double* red, bool active, bool owner, int ob, int nb,
                                          double* sC, double* sJ, double* const* sJV, double* sH, double* sG) {
     using C = Cfg<E, F>;
     using PC = PCfg<E, F>;
-    PartSink<E, F, PART> s;
+    using S = PartSink<E, F, PART, PA, PB>;
+    S s;
     s.red = red;
     s.owner = owner;
     s.c_ = sC + ob * E::CB;
@@ -817,45 +854,45 @@ __device__ __forceinline__ void run_part(const EvalArgs& a, const double* z, con
     s.jn_ = sJ + nb * E::J_BLOCK;
     s.ho_ = sH + ob * E::H_BLOCK;
     s.go_ = sG + ob * E::BLK;
-    if constexpr (C::WJ && C::NV > 0) {
+    if constexpr (S::WJ && C::NV > 0) {
 #pragma unroll
         for (int k = 0; k < C::NV; ++k) s.jv_[k] = sJV[k] + ob * E::JV_STRIDE;
     }
     if (active) {
-        if constexpr (C::WG && !E::LAGRANGE && PART == 0) {
+        if constexpr (S::WG && !E::LAGRANGE && PART == 0) {
 #pragma unroll
             for (int k = 0; k < E::BLK; ++k) s.go_[k] = 0.0;
         }
-        if constexpr (C::WC || C::WJ || C::WH) E::template step<C::WC, C::WJ, C::WH>(z, Tm, p, lam, a.sigma, s);
-        if constexpr (C::WG) E::grad_step(z, Tm, p, s);
-        if constexpr (C::WO && PART == 0) { if (owner) red[C::R_O] += E::cost_step(z, Tm, p); }
+        if constexpr (S::WC || S::WJ || S::WH) E::template step<S::WC, S::WJ, S::WH>(z, Tm, p, lam, a.sigma, s);
+        if constexpr (S::WG) E::grad_step(z, Tm, p, s);
+        if constexpr (PA && C::WO && PART == 0) { if (owner) red[C::R_O] += E::cost_step(z, Tm, p); }
     }
     __syncthreads();   // all owners have stored: the neighbours' contributions can be added
     if (active) {
-        if constexpr (C::WH) {
+        if constexpr (S::WH) {
 #pragma unroll
             for (int n = 0; n < E::NH_NEXT; ++n)
-                if (PartSink<E, F, PART>::mine(PC::O_HN + n)) sH[nb * E::H_BLOCK + E::H_NEXT(n, 2)] += s.hn_[n];
+                if (S::mine(PC::O_HN + n)) sH[nb * E::H_BLOCK + E::H_NEXT(n, 2)] += s.hn_[n];
         }
-        if constexpr (C::WG) {
+        if constexpr (S::WG) {
 #pragma unroll
             for (int n = 0; n < E::NG_NEXT; ++n)
-                if (PartSink<E, F, PART>::mine(PC::O_GN + n)) sG[nb * E::BLK + E::G_NEXT(n, 2)] += s.gn_[n];
+                if (S::mine(PC::O_GN + n)) sG[nb * E::BLK + E::G_NEXT(n, 2)] += s.gn_[n];
         }
     }
 }
 
-template <class E, int F, int PART>
+template <class E, int F, int PART, bool PA, bool PB>
 struct PartDispatch {
     template <class... A>
     __device__ __forceinline__ static void run(int warp, A&&... args) {
-        if (warp == PART) run_part<E, F, PART>(args...);
-        else if constexpr (PART + 1 < PCfg<E, F>::P) PartDispatch<E, F, PART + 1>::run(warp, args...);
+        if (warp == PART) run_part<E, F, PART, PA, PB>(args...);
+        else if constexpr (PART + 1 < PCfg<E, F>::P) PartDispatch<E, F, PART + 1, PA, PB>::run(warp, args...);
     }
 };
 
 template <class E, int F>
-__global__ void __launch_bounds__(PCfg<E, F>::T) ctd_eval_kernel_parts(const EvalArgs a) {
+__global__ void __launch_bounds__(PCfg<E, F>::T, PCfg<E, F>::MINB) ctd_eval_kernel_parts(const EvalArgs a) {
     using C = Cfg<E, F>;
     using PC = PCfg<E, F>;
     pdl_entry();
@@ -922,27 +959,49 @@ __global__ void __launch_bounds__(PCfg<E, F>::T) ctd_eval_kernel_parts(const Eva
         if (active && Tm.hh == -1.2345) CTD_STAMP(7);   // forces the loads to have arrived
         CTD_STAMP(1);
 #endif
-        PartDispatch<E, F, 0>::run(warp, a, z, lam, Tm, p, red, active, owner, ob, nb, sC, sJ, sJV, sH, sG);
-        CTD_STAMP(2);
-        fence_proxy_async_smem();
-        __syncthreads();
-        CTD_STAMP(3);
-        if (warp == 0 && nown > 0) {
-            if constexpr (C::WC) bulk_store_range(gC, sC, nown * E::CB, lane);
-            if constexpr (C::WJ) {
-                bulk_store_range(gJ, sJ, nown * E::J_BLOCK, lane);
-                if constexpr (C::NV > 0) {
+        // hands the staged ranges of phase A and / or B to the copy engine (warp 0)
+        auto store = [&](bool pa, bool pb) {
+            if (warp == 0 && nown > 0) {
+                if (pa) {
+                    if constexpr (C::WC) bulk_store_range(gC, sC, nown * E::CB, lane);
+                    if constexpr (C::WJ) {
+                        bulk_store_range(gJ, sJ, nown * E::J_BLOCK, lane);
+                        if constexpr (C::NV > 0) {
 #pragma unroll
-                    for (int k = 0; k < C::NV; ++k) bulk_store_range(gJV[k], sJV[k], nown * E::JV_STRIDE, lane);
+                            for (int k = 0; k < C::NV; ++k) bulk_store_range(gJV[k], sJV[k], nown * E::JV_STRIDE, lane);
+                        }
+                    }
+                    if constexpr (C::WG) bulk_store_range(gG, sG, nown * E::BLK, lane);
                 }
+                if (pb) {
+                    if constexpr (C::WH) bulk_store_range(gH, sH, nown * E::H_BLOCK, lane);
+                }
+                if (lane == 0) bulk_commit();
             }
-            if constexpr (C::WH) bulk_store_range(gH, sH, nown * E::H_BLOCK, lane);
-            if constexpr (C::WG) bulk_store_range(gG, sG, nown * E::BLK, lane);
-            if (lane == 0) {
-                bulk_commit();
-                bulk_wait_read();   // shared memory must outlive the copies that read it
-            }
+        };
+        if constexpr (!PC::TWO) {
+            PartDispatch<E, F, 0, true, true>::run(warp, a, z, lam, Tm, p, red, active, owner, ob, nb, sC, sJ, sJV, sH, sG);
+            CTD_STAMP(2);
+            fence_proxy_async_smem();
+            __syncthreads();
+            CTD_STAMP(3);
+            store(true, true);
+        } else {
+            PartDispatch<E, F, 0, true, false>::run(warp, a, z, lam, Tm, p, red, active, owner, ob, nb, sC, sJ, sJV, sH, sG);
+            fence_proxy_async_smem();
+            __syncthreads();
+            store(true, false);
+            CTD_STAMP(2);
+            // phase B reuses the region: the copy engine must have read it
+            if (warp == 0 && lane == 0 && nown > 0) bulk_wait_read();
+            __syncthreads();
+            CTD_STAMP(3);
+            PartDispatch<E, F, 0, false, true>::run(warp, a, z, lam, Tm, p, red, active, owner, ob, nb, sC, sJ, sJV, sH, sG);
+            fence_proxy_async_smem();
+            __syncthreads();
+            store(false, true);
         }
+        if (warp == 0 && lane == 0 && nown > 0) bulk_wait_read();   // shared memory must outlive the copies that read it
         CTD_STAMP(4);
     }
     publish_reduction<E, F>(a, red, smem + PC::S_RED, &cta_ticket, inst, cta, lane, warp, hvals, grad, PC::P);
