@@ -129,6 +129,12 @@ def cpu_fused_eval_time(orc_mod, n_threads, budget_s, min_reps=2):
     return el / reps, reps, used
 
 
+def workload_text(nvar, ncon, nnzj, nnzh):
+    """`config.workload`, identical in both arms."""
+    return (f"{PROBLEM}/{SCHEME}/grid_size={GRID}: fused cons+jac+hess, :manual pattern, "
+            f"nvar={nvar} ncon={ncon} nnzj={nnzj} nnzh={nnzh}; one instance per GPU")
+
+
 def run_reference(args, rank):
     """--impl reference: the CPU port of the reference's algorithm on the host cores (rank 0 only)."""
     if rank != 0:
@@ -154,7 +160,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "evals/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * el / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{PROBLEM}/{SCHEME}/grid_size={GRID} fused cons+jac+hess, :manual pattern",
+        "config": {"workload": workload_text(o.nvar, o.ncon, o.nnzj, o.nnzh),
                    "note": "CPU port of the reference algorithm (oracle/): the reference is Julia + ADNLPModels and "
                            "cannot run in this image; derivatives by element-wise second-order forward AD, OpenMP"},
         "cpu_baseline": {"value": val, "unit": "evals/s", "cores": used, "kind": "port",
@@ -508,8 +514,8 @@ def main():
             "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{PROBLEM}/{SCHEME}/grid_size={GRID}: fused cons+jac+hess (one launch), :manual "
-                                   f"pattern, nvar={nvar} ncon={ncon} nnzj={nnzj} nnzh={nnzh}; one instance per GPU",
+            "config": {"workload": workload_text(nvar, ncon, nnzj, nnzh),
+                       "launches": "one kernel launch per evaluation",
                        "l2": f"rotating {nsets} input/output buffer sets ({nsets * alg_bytes / 1e6:.0f} MB > 126 MB L2)",
                        "streams": f"{NSTREAMS} independent evaluations in flight per GPU (one handle + CUDA stream each); "
                                   "single_stream / roofline give the one-stream figures",
