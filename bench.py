@@ -222,6 +222,10 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU port")
+    numa = None
+    if world > 1 and not os.environ.get("CTD_BENCH_NO_NUMA"):   # one process per GPU: sit on the GPU's NUMA node before any pinned buffer is allocated
+        from ctdirect_b200.batch import bind_to_gpu_numa_node
+        numa = bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -520,7 +524,7 @@ def main():
                        "streams": f"{NSTREAMS} independent evaluations in flight per GPU (one handle + CUDA stream each); "
                                   "single_stream / roofline give the one-stream figures",
                        "timing": f"CUDA events on the handles' streams, max over streams and ranks; median of {REPEATS} timed regions of exactly --steps evaluations each (all regions in region_ms)"},
-            "single_stream": single_stream, "region_ms": regions,
+            "single_stream": single_stream, "region_ms": regions, "numa": numa,
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "batched": batched,
         }

@@ -194,3 +194,42 @@ class NativeNormsPipeline:
     def drain(self):
         for s in range(self.depth):
             self.docp.comm_wait(s)
+
+
+def bind_to_gpu_numa_node(device_index: int) -> dict:
+    """Pin the calling process to the CPUs of the NUMA node its GPU hangs off, so that the pinned host
+    buffers it allocates afterwards (first touch) and the threads that feed the GPU sit next to the GPU's PCIe
+    root port.  With one process per GPU on a two-socket box this keeps host<->device copies off the
+    inter-socket link.  Returns what was done; never raises (a box without sysfs / NVML is left alone)."""
+    import os
+    info = {"device": device_index, "numa_node": None, "cpus": None}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = device_index
+        if visible:
+            ids = [v.strip() for v in visible.split(",") if v.strip()]
+            if device_index < len(ids) and ids[device_index].isdigit():
+                phys = int(ids[device_index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        path = f"/sys/bus/pci/devices/{dom[-4:].lower()}:{rest.lower()}/numa_node"
+        node = int(open(path).read().strip())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        cpulist = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["cpus"] = len(allowed)
+    except Exception as ex:  # best effort
+        info["error"] = str(ex)[:120]
+    return info
