@@ -3,6 +3,8 @@
 Tolerance (BASELINE.json north_star): indices bit-exact, values within 1e-12 relative.  `assert_close`
 uses |a-b| <= 1e-12 * max(|a|, |b|, scale) where `scale` is the magnitude of the quantities that were
 combined to form the entry (stated at each call)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -368,3 +370,69 @@ def test_native_norm_gather_single_rank(ctd):
         assert_close(g[0, 1].cpu().numpy(), viol.cpu().numpy(), scale=1.0, what=f"evaluation {k}: gathered violation")
     pipe.drain()
     d.synchronize()
+
+
+def _native_gather_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)   # only carries the 128-byte NCCL id
+    try:
+        import ctdirect_b200 as ctd
+        from ctdirect_b200.batch import NativeNormsPipeline, broadcast_unique_id, shard_range
+        B, N = 8, 120
+        rng = np.random.default_rng(3)
+        par = np.tile(np.array([310.0, 500.0, 2.0, 3.5]), (B, 1))
+        par[:, 3] = rng.uniform(1.0, 3.5, B)
+        lo, hi = shard_range(B, world, rank)
+        d = ctd.DOCP("goddard", N, "midpoint", params=par[lo:hi], batch=hi - lo, device=rank)
+        pipe = NativeNormsPipeline(d, rank, world, broadcast_unique_id(), depth=2)
+        dev = torch.device("cuda", rank)
+        x_all = np.tile(d.initial_guess(), (B, 1)) * (1 + 1e-3 * rng.uniform(-1, 1, (B, d.nvar)))
+        res = []
+        for k in range(3):
+            xk = torch.from_numpy(np.ascontiguousarray(x_all[lo:hi] * (1 + 1e-4 * k))).to(dev)
+            s = pipe.submit(ctd.CONS | ctd.OBJ, xk)
+            g = pipe.result(s)
+            d.synchronize()
+            res.append(g.cpu().numpy().copy())
+        pipe.drain()
+        d.synchronize()
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_native_norm_gather_two_ranks(ctd):
+    """Two processes, two GPUs: every rank ends up with the (objective, violation) rows of both shards, equal to
+    a single-process evaluation of the whole batch.  Skipped on a one-GPU box."""
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    procs = [mpc.Process(target=_native_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p_ in procs:
+        p_.start()
+    out = dict(q.get(timeout=180) for _ in range(2))
+    for p_ in procs:
+        p_.join(timeout=60)
+        assert p_.exitcode == 0
+    B, N = 8, 120
+    rng = np.random.default_rng(3)
+    par = np.tile(np.array([310.0, 500.0, 2.0, 3.5]), (B, 1))
+    par[:, 3] = rng.uniform(1.0, 3.5, B)
+    d = ctd.DOCP("goddard", N, "midpoint", params=par, batch=B)
+    x_all = np.tile(d.initial_guess(), (B, 1)) * (1 + 1e-3 * rng.uniform(-1, 1, (B, d.nvar)))
+    for k in range(3):
+        obj, viol = d.norms(np.ascontiguousarray(x_all * (1 + 1e-4 * k)))
+        for rank in (0, 1):
+            g = out[rank][k]                    # (world, 2, 4)
+            assert_close(g[:, 0, :].reshape(-1), obj, scale=1.0, what=f"rank {rank} evaluation {k}: objectives")
+            assert_close(g[:, 1, :].reshape(-1), viol, scale=1.0, what=f"rank {rank} evaluation {k}: violations")
