@@ -67,7 +67,11 @@ SIGNATURES = {
     "ctd_set_params": (C.c_int, [_H, _dp, C.c_int32]),
     "ctd_sync": (C.c_int, [_H]),
     "ctd_stream": (C.c_void_p, [_H]),
+    "ctd_set_stream": (C.c_int, [_H, C.c_void_p]),
     "ctd_launch_count": (C.c_int64, [_H]),
+    "ctd_kkt_nnz": (C.c_int64, [_H]),
+    "ctd_kkt_structure": (C.c_int, [_H, _ip, _ip]),
+    "ctd_kkt_assemble_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ctd_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "ctd_nccl_version": (C.c_int, []),
     "ctd_comm_init": (C.c_int, [_H, C.c_char_p, C.c_int32, C.c_int32]),

@@ -40,7 +40,7 @@ def _common_deps():
 
 
 def _sources(only=None):
-    srcs = [os.path.join(CSRC, "ctd_model.cu"), os.path.join(CSRC, "ctd_capi.cu"), os.path.join(CSRC, "ctd_comm.cu")]
+    srcs = [os.path.join(CSRC, "ctd_model.cu"), os.path.join(CSRC, "ctd_capi.cu"), os.path.join(CSRC, "ctd_comm.cu"), os.path.join(CSRC, "ctd_kkt.cu")]
     manifest = os.path.join(GEN, "MANIFEST.txt")
     if not os.path.exists(manifest):
         raise RuntimeError("csrc/generated/MANIFEST.txt missing: run python -m ctdirect_b200.gen.generate")

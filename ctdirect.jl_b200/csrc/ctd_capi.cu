@@ -247,9 +247,32 @@ void* ctd_stream(ctd_handle h) {
     return s;
 }
 
+int ctd_set_stream(ctd_handle h, void* stream) {
+    if (int e = check(h)) return e;
+    return guarded([&] { h->m->set_stream((cudaStream_t)stream); });
+}
+
 int64_t ctd_launch_count(ctd_handle h) {
     if (check(h)) return -1;
     return h->m->launches();
+}
+
+int64_t ctd_kkt_nnz(ctd_handle h) {
+    if (check(h)) return -1;
+    int64_t n = -1;
+    guarded([&] { n = h->m->kkt_nnz(); });
+    return n;
+}
+
+int ctd_kkt_structure(ctd_handle h, int64_t* colptr, int64_t* rows) {
+    if (int e = check(h)) return e;
+    return guarded([&] { h->m->kkt_structure(colptr, rows); });
+}
+
+int ctd_kkt_assemble_dev(ctd_handle h, const double* hvals, const double* jvals, const double* dx, const double* dc,
+                         double* kvals) {
+    if (int e = check(h)) return e;
+    return guarded([&] { h->m->kkt_assemble_dev(hvals, jvals, dx, dc, kvals); });
 }
 
 int ctd_nccl_unique_id(char id[CTD_NCCL_ID_BYTES]) {

@@ -138,12 +138,13 @@ Model::~Model() {
     if (dev_ready_) {
         cudaSetDevice(device_);
         comm_destroy();
+        kkt_free();
         if (stream_) cudaStreamSynchronize(stream_);   // nothing of this handle may still be in flight
         cudaFree(d_edge_map_); cudaFree(d_edge_pos_); cudaFree(d_sgrid_); cudaFree(d_params_);
         cudaFree(d_partials_); cudaFree(d_counters_);
         cudaFree(d_x_); cudaFree(d_y_); cudaFree(d_c_); cudaFree(d_j_); cudaFree(d_h_); cudaFree(d_g_); cudaFree(d_obj_);
         cudaFree(d_lcon_); cudaFree(d_ucon_); cudaFree(d_viol_);
-        if (stream_) cudaStreamDestroy(stream_);
+        if (own_stream_) cudaStreamDestroy(own_stream_);
     }
 }
 
@@ -539,7 +540,8 @@ void Model::ensure_device() {
         throw CtdError{(int)(e == cudaSuccess ? cudaErrorNoDevice : e),
                        "no CUDA device: this library has no CPU fallback (evaluation needs a B200)"};
     CTD_CUDA(cudaSetDevice(device_));
-    CTD_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    CTD_CUDA(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking));
+    if (!stream_) stream_ = own_stream_;
     const LaunchCfg lc = reg_.launcher.cfg(F_CONS | F_JAC | F_HESS | F_GRAD | F_OBJ);
     const int max_nred = lc.nred + 1;   // (+1: the violation slot of the flag sets that carry it)
     const int npar = std::max(reg_.info.npar, 1);
@@ -597,6 +599,14 @@ void Model::set_params(const double* params, int n_params) {
 cudaStream_t Model::stream() {
     ensure_device();
     return stream_;
+}
+
+void Model::set_stream(cudaStream_t s) {
+    ensure_device();
+    // work already enqueued on the previous stream is not ordered with the new one: finish it first
+    CTD_CUDA(cudaSetDevice(device_));
+    CTD_CUDA(cudaStreamSynchronize(stream_));
+    stream_ = s ? s : own_stream_;
 }
 
 void Model::sync() {

@@ -109,7 +109,13 @@ class Model {
     void set_params(const double* params, int n_params);
     void sync();
     cudaStream_t stream();
+    // run this handle's work on a caller-owned stream (nullptr: back to the handle's own stream)
+    void set_stream(cudaStream_t s);
     int64_t launches() const { return launches_; }
+    // KKT assembly (ctd_kkt.cu)
+    int64_t kkt_nnz();
+    void kkt_structure(int64_t* colptr, int64_t* rows);
+    void kkt_assemble_dev(const double* hvals, const double* jvals, const double* dx, const double* dc, double* kvals);
     // multi-GPU norm gather (ctd_comm.cu)
     void comm_init(const char* nccl_id, int rank, int world);
     void comm_destroy();
@@ -140,7 +146,7 @@ class Model {
     int64_t jv_base_[MAX_NV], hvv_pos_[MAX_NVV];
     // device state (created on first evaluation)
     bool dev_ready_ = false, staging_ready_ = false;
-    cudaStream_t stream_ = nullptr;
+    cudaStream_t stream_ = nullptr, own_stream_ = nullptr;
     int* d_edge_map_ = nullptr;
     long long* d_edge_pos_ = nullptr;
     double *d_sgrid_ = nullptr, *d_params_ = nullptr, *d_partials_ = nullptr;
@@ -149,6 +155,12 @@ class Model {
            *d_obj_ = nullptr, *d_lcon_ = nullptr, *d_ucon_ = nullptr, *d_viol_ = nullptr;
     std::map<int, size_t> prepared_;  // flags (+ 256 for the parts variant) -> dynamic smem size
     int64_t launches_ = 0;
+    // KKT structure and position maps (built on first use)
+    void build_kkt();
+    void kkt_free();
+    bool kkt_built_ = false;
+    std::vector<int64_t> kkt_colptr_, kkt_rows_, kkt_pos_h_, kkt_pos_j_, kkt_hdiag_;
+    long long *d_kkt_pos_h_ = nullptr, *d_kkt_pos_j_ = nullptr, *d_kkt_hdiag_ = nullptr, *d_kkt_colptr_ = nullptr;
     // communicator state (only after comm_init)
     void* comm_ = nullptr;
     int comm_rank_ = 0, comm_world_ = 0;

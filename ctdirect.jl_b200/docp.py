@@ -144,6 +144,30 @@ class DOCP:
         _lib.check(self._lib.ctd_hess_structure(self._h, r.ctypes.data_as(_lib._ip), c.ctypes.data_as(_lib._ip)))
         return r, c
 
+    # ---- KKT assembly (ctd_kkt_* of the C ABI) ------------------------------------------------------
+    @property
+    def nnzk(self) -> int:
+        return int(self._lib.ctd_kkt_nnz(self._h))
+
+    def kkt_structure(self):
+        """(colptr, rows), 1-based, of the lower triangle of [[H + diag(dx), .], [J, -diag(dc)]] in CSC order."""
+        colptr = np.empty(self.nvar + self.ncon + 1, dtype=np.int64)
+        rows = np.empty(self.nnzk, dtype=np.int64)
+        _lib.check(self._lib.ctd_kkt_structure(self._h, colptr.ctypes.data_as(_lib._ip), rows.ctypes.data_as(_lib._ip)))
+        return colptr, rows
+
+    def kkt_assemble(self, hvals, jvals, dx=None, dc=None, out=None):
+        """Move the value arrays of an evaluation (CUDA tensors) to KKT order in one launch."""
+        hvals = self._check_in(hvals, self.nnzh, "hvals")
+        jvals = self._check_in(jvals, self.nnzj, "jvals")
+        dx = self._check_in(dx, self.nvar, "dx")
+        dc = self._check_in(dc, self.ncon, "dc")
+        if not _is_torch(hvals):
+            raise TypeError("kkt_assemble needs CUDA tensors")
+        out = self._check_in(out, self.nnzk, "out") if out is not None else self._empty_like(hvals, self.nnzk)
+        _lib.check(self._lib.ctd_kkt_assemble_dev(self._h, _ptr(hvals), _ptr(jvals), _ptr(dx), _ptr(dc), _ptr(out)))
+        return out
+
     # ---- evaluation --------------------------------------------------------------------------------
     def _shape(self, n):
         if n == 1:
@@ -378,6 +402,13 @@ class DOCP:
     def comm_wait(self, slot: int = 0):
         """Make this handle's stream wait until the gather that last used `slot` has landed."""
         _lib.check(self._lib.ctd_comm_wait(self._h, int(slot)))
+
+    def set_stream(self, stream=None):
+        """Run this handle's work on a caller-owned CUDA stream (a `torch.cuda.Stream`, a raw cudaStream_t as int,
+        or None for the handle's own stream): evaluations then follow the caller's stream order and can be
+        captured into the caller's CUDA graphs."""
+        ptr = getattr(stream, "cuda_stream", stream)
+        _lib.check(self._lib.ctd_set_stream(self._h, C.c_void_p(int(ptr)) if ptr else None))
 
     @property
     def cuda_stream(self) -> int:

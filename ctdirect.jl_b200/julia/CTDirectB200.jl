@@ -138,6 +138,27 @@ function b200_model_builder(problem::AbstractString, docp)
     end
 end
 
+"""
+CSC lower triangle of `[H + diag(dx)  .; J  -diag(dc)]` (what MadNLP's sparse KKT system hands to cuDSS):
+`(colptr, rowval)`, 1-based, ready for `SparseMatrixCSC(n, n, colptr, rowval, nzval)`.
+"""
+function kkt_structure(nlp::B200DOCPModel)
+    n = nlp.meta.nvar + nlp.meta.ncon
+    nnzk = ccall((:ctd_kkt_nnz, LIB), Int64, (Ptr{Cvoid},), nlp.handle)
+    colptr = Vector{Int64}(undef, n + 1); rowval = Vector{Int64}(undef, nnzk)
+    check(ccall((:ctd_kkt_structure, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}), nlp.handle, colptr, rowval))
+    return colptr, rowval
+end
+
+"Device pointers: move `hvals`, `jvals` (and the regularisations `dx`, `dc`, or C_NULL) to KKT order in `kvals`."
+kkt_assemble!(handle::Ptr{Cvoid}, hvals, jvals, dx, dc, kvals) =
+    check(ccall((:ctd_kkt_assemble_dev, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                handle, hvals, jvals, dx, dc, kvals))
+
+"Run the handle's work on a caller-owned CUDA stream (e.g. `CUDA.stream().handle`); `C_NULL` restores its own."
+set_stream!(handle::Ptr{Cvoid}, stream::Ptr{Cvoid}) =
+    check(ccall((:ctd_set_stream, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), handle, stream))
+
 # ---- batched scenarios on several GPUs: the library's own NCCL communicator (include/ctdirect_b200.h) ----
 "128 bytes created by ONE rank; broadcast them to every rank (MPI, Distributed, a file) before `comm_init!`."
 function nccl_unique_id()

@@ -158,8 +158,28 @@ CTD_API int ctd_set_params(ctd_handle h, const double* params, int32_t n);
 CTD_API int ctd_sync(ctd_handle h);
 /* cudaStream_t of the handle (for callers that enqueue their own work around the _dev calls) */
 CTD_API void* ctd_stream(ctd_handle h);
+/* Run the handle's work on a caller-owned cudaStream_t instead (NULL: back to the handle's own stream).  Work
+ * already enqueued is finished first.  With this the evaluations take part in the caller's stream order and can
+ * be captured into the caller's CUDA graphs (the _dev entry points enqueue kernels only: no allocation, no
+ * synchronisation after the first call of each output combination).  The stream must outlive the handle or be
+ * reset with NULL before it is destroyed. */
+CTD_API int ctd_set_stream(ctd_handle h, void* stream);
 /* number of kernel launches issued through this handle so far */
 CTD_API int64_t ctd_launch_count(ctd_handle h);
+
+/* ---- KKT assembly.  Lower triangle, CSC, of
+ *        K = [ H + diag(dx)       .      ]      (nvar + ncon columns)
+ *            [ J              -diag(dc)  ]
+ * the matrix an interior-point solver factorises (in the reference MadNLP assembles it from hess_coord! /
+ * jac_coord! and hands it to cuDSS, test/test_gpu.jl:18).  Column j <= nvar: diagonal entry (always present),
+ * strictly lower Hessian entries, Jacobian entries at rows nvar + r; column nvar + r: its diagonal entry.
+ * ctd_kkt_structure: colptr (nvar+ncon+1) and rows (ctd_kkt_nnz), both 1-based.  ctd_kkt_assemble_dev moves the
+ * value arrays of an evaluation (device pointers, [batch][nnz]) to KKT order in one launch; dx / dc (device,
+ * [batch][nvar] / [batch][ncon]) may be NULL (zeros). */
+CTD_API int64_t ctd_kkt_nnz(ctd_handle h);
+CTD_API int ctd_kkt_structure(ctd_handle h, int64_t* colptr, int64_t* rows);
+CTD_API int ctd_kkt_assemble_dev(ctd_handle h, const double* hvals, const double* jvals, const double* dx,
+                                 const double* dc, double* kvals);
 
 /* ---- multi-GPU norm gather (the reference has no batching, every scenario is its own DOCP,
  * src/DOCP_data.jl:293).  One process per GPU; each rank owns a batched handle for its shard of the

@@ -8,7 +8,8 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
 nvcc $FLAGS -c ctd_model.cu -o /tmp/ctdv_$TAG/m.o &
 nvcc $FLAGS -c ctd_capi.cu -o /tmp/ctdv_$TAG/c.o &
 nvcc $FLAGS -c ctd_comm.cu -o /tmp/ctdv_$TAG/n.o &
+nvcc $FLAGS -c ctd_kkt.cu -o /tmp/ctdv_$TAG/k.o &
 nvcc $FLAGS -c generated/$ELEM.cu -o /tmp/ctdv_$TAG/e.o &
 wait
-nvcc -shared -gencode arch=compute_100a,code=sm_100a -cudart static -o ../lib/variants/libctd_$TAG.so /tmp/ctdv_$TAG/m.o /tmp/ctdv_$TAG/c.o /tmp/ctdv_$TAG/n.o /tmp/ctdv_$TAG/e.o -ldl
+nvcc -shared -gencode arch=compute_100a,code=sm_100a -cudart static -o ../lib/variants/libctd_$TAG.so /tmp/ctdv_$TAG/m.o /tmp/ctdv_$TAG/c.o /tmp/ctdv_$TAG/n.o /tmp/ctdv_$TAG/k.o /tmp/ctdv_$TAG/e.o -ldl
 echo built $TAG

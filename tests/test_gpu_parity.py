@@ -436,3 +436,75 @@ def test_native_norm_gather_two_ranks(ctd):
             g = out[rank][k]                    # (world, 2, 4)
             assert_close(g[:, 0, :].reshape(-1), obj, scale=1.0, what=f"rank {rank} evaluation {k}: objectives")
             assert_close(g[:, 1, :].reshape(-1), viol, scale=1.0, what=f"rank {rank} evaluation {k}: violations")
+
+
+@pytest.mark.gpu
+def test_caller_stream_and_graph_capture(ctd):
+    """ctd_set_stream: the evaluation runs in the caller's stream order and can be captured into a CUDA graph;
+    replays reproduce the eager results bit for bit on new inputs written into the same buffers."""
+    import torch
+    dev = torch.device("cuda", 0)
+    d = ctd.DOCP("goddard", 3000, "midpoint")
+    F = ctd.CONS | ctd.JAC | ctd.HESS
+    x0, y0 = synthetic_point(d, seed=1)
+    x1, y1 = synthetic_point(d, seed=2)
+    ref0 = d.evaluate(F, torch.from_numpy(x0).to(dev), torch.from_numpy(y0).to(dev), 1.0)
+    ref1 = d.evaluate(F, torch.from_numpy(x1).to(dev), torch.from_numpy(y1).to(dev), 1.0)
+    d.synchronize()
+    st = torch.cuda.Stream(device=dev)
+    d.set_stream(st)
+    assert d.cuda_stream == st.cuda_stream
+    x, y = torch.empty(d.nvar, dtype=torch.float64, device=dev), torch.empty(d.ncon, dtype=torch.float64, device=dev)
+    call, out = d.bind(F, x, y, 1.0)
+    with torch.cuda.stream(st):
+        x.copy_(torch.from_numpy(x0).to(dev)); y.copy_(torch.from_numpy(y0).to(dev))
+        call()                                  # ordered after the copies by the caller's stream
+    st.synchronize()
+    for k in ("cons", "jac", "hess"):
+        assert torch.equal(out[k], ref0[k]), k
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=st, capture_error_mode="thread_local"):
+        call()
+    for xs, ys, ref in ((x1, y1, ref1), (x0, y0, ref0)):
+        with torch.cuda.stream(st):
+            x.copy_(torch.from_numpy(xs).to(dev)); y.copy_(torch.from_numpy(ys).to(dev))
+            for v in out.values():
+                v.zero_()
+            g.replay()
+        st.synchronize()
+        for k in ("cons", "jac", "hess"):
+            assert torch.equal(out[k], ref[k]), k
+    d.set_stream(None)
+    d.evaluate(F, x, y, 1.0)
+    d.synchronize()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("problem,scheme,N,mode,batch", [
+    ("goddard", "midpoint", 500, "reference", 1), ("goddard", "midpoint", 500, "optimized", 3),
+    ("goddard", "gauss_legendre_3", 60, "reference", 1), ("robot", "trapeze", 50, "optimized", 2),
+    ("goddard", "midpoint", 100_000, "reference", 1),
+])
+def test_kkt_assembly(ctd, problem, scheme, N, mode, batch):
+    """ctd_kkt_assemble_dev: the values of one evaluation moved to the CSC order of
+    tril([[H + diag(dx), J'], [J, -diag(dc)]]) equal scipy's assembly of the same arrays, exactly (the only
+    arithmetic is H_jj + dx_j)."""
+    import torch
+    from test_host_structure import _kkt_reference
+    dev = torch.device("cuda", 0)
+    d = ctd.DOCP(problem, N, scheme, pattern_mode=mode, batch=batch)
+    x, y = synthetic_point(d, seed=21, batch=batch)
+    r = d.evaluate(ctd.CONS | ctd.JAC | ctd.HESS, torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev), 1.0)
+    rng = np.random.default_rng(4)
+    dx, dc = rng.uniform(0.1, 2.0, (batch, d.nvar)), rng.uniform(0.1, 2.0, (batch, d.ncon))
+    k = d.kkt_assemble(r["hess"], r["jac"], torch.from_numpy(dx).to(dev), torch.from_numpy(dc).to(dev))
+    k0 = d.kkt_assemble(r["hess"], r["jac"])     # no regularisation
+    d.synchronize()
+    k, k0 = k.cpu().numpy().reshape(batch, -1), k0.cpu().numpy().reshape(batch, -1)
+    hv, jv = r["hess"].cpu().numpy().reshape(batch, -1), r["jac"].cpu().numpy().reshape(batch, -1)
+    colptr, rows = d.kkt_structure()
+    for b in range(batch):
+        K = _kkt_reference(d, hv[b], jv[b], dx[b], dc[b])
+        assert np.array_equal(colptr - 1, K.indptr) and np.array_equal(rows - 1, K.indices)
+        assert np.array_equal(k[b], K.data), f"instance {b}"
+        assert np.array_equal(k0[b], _kkt_reference(d, hv[b], jv[b]).data), f"instance {b}, no regularisation"

@@ -124,3 +124,48 @@ def test_product_never_touches_the_oracle():
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 m = bad.search(txt)
                 assert m is None or "oracle/tracer.hpp)" in txt[m.start() - 5:m.end() + 20], (dirpath, f, m.group(0))
+
+
+class _Kkt:
+    pass
+
+
+def _kkt_reference(d, hvals=None, jvals=None, dx=None, dc=None):
+    """Lower triangle of [[H + diag(dx), J'], [J, -diag(dc)]] in CSC order, structure by scipy from the COO
+    structures, values accumulated entry by entry (explicit zeros stay in the structure)."""
+    import scipy.sparse as sp
+    n, m = d.nvar, d.ncon
+    jr, jc = d.jacobian_structure()
+    hr, hc = d.hessian_structure()
+    rows = np.concatenate([hr - 1, jr - 1 + n, np.arange(n), n + np.arange(m)])
+    cols = np.concatenate([hc - 1, jc - 1, np.arange(n), n + np.arange(m)])
+    P = sp.coo_matrix((np.ones(len(rows)), (rows, cols)), shape=(n + m, n + m)).tocsc()
+    P.sort_indices()
+    K = _Kkt()
+    K.indptr, K.indices, K.nnz = P.indptr.astype(np.int64), P.indices.astype(np.int64), P.nnz
+    if hvals is not None:
+        vals = np.concatenate([hvals, jvals, np.zeros(n) if dx is None else dx, np.zeros(m) if dc is None else -dc])
+        kcols = np.repeat(np.arange(n + m, dtype=np.int64), np.diff(K.indptr))
+        pos = np.searchsorted(kcols * (n + m) + K.indices, cols.astype(np.int64) * (n + m) + rows)
+        K.data = np.zeros(K.nnz)
+        np.add.at(K.data, pos, vals)     # diagonal: (0 + H_jj) + dx_j, the kernel's arithmetic
+    return K
+
+
+@pytest.mark.parametrize("problem,scheme,N,mode", [
+    ("goddard", "midpoint", 40, "reference"), ("goddard", "midpoint", 40, "optimized"),
+    ("goddard_all", "trapeze", 7, "reference"), ("goddard", "gauss_legendre_3", 5, "reference"),
+    ("double_integrator_minenergy", "trapeze", 100, "reference"), ("robot", "trapeze", 6, "optimized"),
+    ("goddard", "midpoint", 1, "reference"),
+])
+def test_kkt_structure_matches_scipy(ctd, problem, scheme, N, mode):
+    """ctd_kkt_structure (host only) against scipy's CSC of the same lower-triangular block matrix; the detected
+    patterns lack some Hessian diagonal entries, which the KKT structure must still provide."""
+    d = ctd.DOCP(problem, N, scheme, pattern_mode=mode)
+    colptr, rows = d.kkt_structure()
+    K = _kkt_reference(d)
+    assert colptr.dtype == np.int64 and rows.dtype == np.int64
+    assert d.nnzk == K.nnz == len(rows)
+    assert np.array_equal(colptr - 1, K.indptr)
+    assert np.array_equal(rows - 1, K.indices)
+    assert np.all(rows[colptr[:-1] - 1] == np.arange(1, d.nvar + d.ncon + 1))   # every column starts on its diagonal
