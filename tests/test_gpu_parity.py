@@ -508,3 +508,36 @@ def test_kkt_assembly(ctd, problem, scheme, N, mode, batch):
         assert np.array_equal(colptr - 1, K.indptr) and np.array_equal(rows - 1, K.indices)
         assert np.array_equal(k[b], K.data), f"instance {b}"
         assert np.array_equal(k0[b], _kkt_reference(d, hv[b], jv[b]).data), f"instance {b}, no regularisation"
+
+
+@pytest.mark.gpu
+def test_nan_and_inf_pass_through(ctd):
+    """Like the reference, a NaN / Inf iterate is not an error: it flows into the results the solver reads
+    (SURVEY.md 8b).  Only the entries that depend on the poisoned step change; the violation norm becomes NaN."""
+    import torch
+    dev = torch.device("cuda", 0)
+    N = 400
+    d = ctd.DOCP("goddard", N, "midpoint")
+    x, y = synthetic_point(d, seed=8)
+    F = ctd.CONS | ctd.JAC | ctd.HESS
+    clean = d.evaluate(F, x, y, 1.0)
+    step = 200                                      # 1-based step whose state is poisoned
+    for bad in (np.nan, np.inf):
+        xb = x.copy()
+        xb[(step - 1) * 4 + 1] = bad                # v_200
+        r = d.evaluate(F, xb, y, 1.0)
+        c = r["cons"].reshape(-1)
+        rows = slice((step - 2) * 3, step * 3)      # defects of steps 199 and 200 read x_200
+        assert not np.all(np.isfinite(c[rows]))
+        far = np.ones(d.ncon, dtype=bool)
+        far[rows] = False
+        assert np.array_equal(c[far], clean["cons"].reshape(-1)[far])
+        jr, jc = d.jacobian_structure()
+        touched = np.isin((jr - 1) // 3, (step - 2, step - 1)) & (jr <= 3 * N)
+        assert np.array_equal(r["jac"].reshape(-1)[~touched], clean["jac"].reshape(-1)[~touched])
+        assert not np.all(np.isfinite(r["jac"].reshape(-1)[touched]))
+        assert not np.all(np.isfinite(r["hess"]))
+        obj, viol = d.norms(xb)
+        assert np.isnan(viol[0]) or np.isinf(viol[0])
+    tx = torch.from_numpy(x).to(dev)
+    assert np.isfinite(d.norms(tx)[1].cpu().numpy()).all()
