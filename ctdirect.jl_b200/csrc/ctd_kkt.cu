@@ -71,7 +71,7 @@ void Model::kkt_structure(int64_t* colptr, int64_t* rows) {
 struct KktArgs {
     const double *hvals, *jvals, *dx, *dc;
     double* kvals;
-    const long long *pos_h, *pos_j, *hdiag, *colptr;
+    const int *pos_h, *pos_j, *hdiag, *diag;   // 32-bit positions inside one instance (nnzk < 2^31 is checked)
     long long nnzh, nnzj, nvar, ncon, nnzk;
 };
 
@@ -85,19 +85,19 @@ __global__ void __launch_bounds__(256) ctd_kkt_kernel(const KktArgs a) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     for (long long k = t0; k < a.nnzh; k += stride) {
-        const long long p = __ldg(a.pos_h + k);
+        const int p = __ldg(a.pos_h + k);
         if (p >= 0) kv[p] = hv[k];
     }
     for (long long k = t0; k < a.nnzj; k += stride) kv[__ldg(a.pos_j + k)] = jv[k];
     for (long long j = t0; j < a.nvar + a.ncon; j += stride) {
         double v;
         if (j < a.nvar) {
-            const long long d = __ldg(a.hdiag + j);
+            const int d = __ldg(a.hdiag + j);
             v = (d >= 0 ? hv[d] : 0.0) + (a.dx ? a.dx[inst * a.nvar + j] : 0.0);
         } else {
             v = a.dc ? -a.dc[inst * a.ncon + (j - a.nvar)] : 0.0;
         }
-        kv[__ldg(a.colptr + j)] = v;
+        kv[__ldg(a.diag + j)] = v;
     }
 }
 
@@ -107,19 +107,21 @@ void Model::kkt_assemble_dev(const double* hvals, const double* jvals, const dou
     ensure_device();
     CTD_CUDA(cudaSetDevice(device_));
     if (!d_kkt_pos_h_) {
-        auto up = [&](long long** d, const std::vector<int64_t>& h) {
-            CTD_CUDA(cudaMalloc(d, sizeof(long long) * std::max<size_t>(h.size(), 1)));
-            CTD_CUDA(cudaMemcpyAsync(*d, h.data(), sizeof(long long) * h.size(), cudaMemcpyHostToDevice, stream_));
+        if (kkt_rows_.size() >= (size_t)1 << 31) throw CtdError{-2, "ctd_kkt_assemble_dev: more than 2^31 KKT entries per instance"};
+        auto up = [&](int** d, const std::vector<int64_t>& h, size_t n) {
+            std::vector<int> h32(h.begin(), h.begin() + n);
+            CTD_CUDA(cudaMalloc(d, sizeof(int) * std::max<size_t>(n, 1)));
+            CTD_CUDA(cudaMemcpyAsync(*d, h32.data(), sizeof(int) * n, cudaMemcpyHostToDevice, stream_));
+            CTD_CUDA(cudaStreamSynchronize(stream_));   // h32 is a temporary
         };
-        up(&d_kkt_pos_h_, kkt_pos_h_);
-        up(&d_kkt_pos_j_, kkt_pos_j_);
-        up(&d_kkt_hdiag_, kkt_hdiag_);
-        up(&d_kkt_colptr_, kkt_colptr_);
-        CTD_CUDA(cudaStreamSynchronize(stream_));
+        up(&d_kkt_pos_h_, kkt_pos_h_, kkt_pos_h_.size());
+        up(&d_kkt_pos_j_, kkt_pos_j_, kkt_pos_j_.size());
+        up(&d_kkt_hdiag_, kkt_hdiag_, kkt_hdiag_.size());
+        up(&d_kkt_colptr_, kkt_colptr_, kkt_colptr_.size() - 1);   // every column starts on its diagonal entry
     }
     KktArgs a;
     a.hvals = hvals; a.jvals = jvals; a.dx = dx; a.dc = dc; a.kvals = kvals;
-    a.pos_h = d_kkt_pos_h_; a.pos_j = d_kkt_pos_j_; a.hdiag = d_kkt_hdiag_; a.colptr = d_kkt_colptr_;
+    a.pos_h = d_kkt_pos_h_; a.pos_j = d_kkt_pos_j_; a.hdiag = d_kkt_hdiag_; a.diag = d_kkt_colptr_;
     a.nnzh = hess_.nnz(); a.nnzj = jac_.nnz(); a.nvar = nvar_; a.ncon = ncon_; a.nnzk = (long long)kkt_rows_.size();
     const long long work = std::max<long long>(a.nnzh, std::max<long long>(a.nnzj, a.nvar + a.ncon));
     // a multiple of the SM count, 8 CTAs of 256 threads per SM at most, never more CTAs than work

@@ -160,7 +160,7 @@ class Model {
     void kkt_free();
     bool kkt_built_ = false;
     std::vector<int64_t> kkt_colptr_, kkt_rows_, kkt_pos_h_, kkt_pos_j_, kkt_hdiag_;
-    long long *d_kkt_pos_h_ = nullptr, *d_kkt_pos_j_ = nullptr, *d_kkt_hdiag_ = nullptr, *d_kkt_colptr_ = nullptr;
+    int *d_kkt_pos_h_ = nullptr, *d_kkt_pos_j_ = nullptr, *d_kkt_hdiag_ = nullptr, *d_kkt_colptr_ = nullptr;
     // communicator state (only after comm_init)
     void* comm_ = nullptr;
     int comm_rank_ = 0, comm_world_ = 0;
