@@ -541,3 +541,22 @@ def test_nan_and_inf_pass_through(ctd):
         assert np.isnan(viol[0]) or np.isinf(viol[0])
     tx = torch.from_numpy(x).to(dev)
     assert np.isfinite(d.norms(tx)[1].cpu().numpy()).all()
+
+
+@pytest.mark.gpu
+def test_cuda_path_against_committed_regression_vectors(ctd):
+    """The CUDA path against tests/golden/regression_vectors.npz (oracle-made regression anchors, see
+    tests/golden/make_regression_vectors.py): same tolerance as the live comparisons."""
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "regression_vectors.npz"))
+    tags = sorted({k.rsplit("|", 1)[0] for k in z.files})
+    for tag in tags:
+        p, s, n, mode = tag.split("|")
+        d = ctd.DOCP(p, int(n), s, pattern_mode=mode)
+        x, y = z[tag + "|x"], z[tag + "|y"]
+        r = d.evaluate(ctd.CONS | ctd.JAC | ctd.HESS | ctd.GRAD | ctd.OBJ, x, y, 0.75)
+        xs = max(1.0, float(np.abs(x).max()))
+        assert_close(r["cons"], z[tag + "|cons"], scale=xs, what=tag + " cons")
+        assert_close(r["jac"], z[tag + "|jac"], scale=1e-3 * float(np.abs(z[tag + "|jac"]).max()), what=tag + " jac")
+        assert_close(r["hess"], z[tag + "|hess"], scale=1e-3 * max(1e-300, float(np.abs(z[tag + "|hess"]).max())), what=tag + " hess")
+        assert_close(r["grad"], z[tag + "|grad"], scale=1e-3, what=tag + " grad")
+        assert_close(r["obj"], z[tag + "|obj"], scale=1.0, what=tag + " obj")

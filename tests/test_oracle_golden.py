@@ -198,3 +198,40 @@ def test_solution_unpacking_conventions(oracle_mod):
     x = np.arange(m.nvar, dtype=float)
     s = m.unpack(x)
     assert s["control"][0, 0] == 0.5 * x[1] + 0.5 * x[2] and s["control"][2, 0] == s["control"][1, 0]
+
+
+def _golden(name):
+    import os
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)
+
+
+def test_reference_known_answers_file(oracle_mod):
+    """tests/golden/reference_known_answers.json: the reference's own pinned numbers as data, each with its citation."""
+    import json
+    ka = json.load(open(_golden("reference_known_answers.json")))
+    for e in ka["pattern_counts"] + ka["stagewise_dims"]:
+        m = oracle_mod.OracleModel(e["problem"], e["scheme"], e["N"], pattern_mode=e.get("pattern_mode", "reference"))
+        for key in ("nvar", "ncon", "nnzj", "nnzh"):
+            if key in e:
+                assert getattr(m, key) == e[key], (e["cite"], key)
+    m = oracle_mod.OracleModel("goddard", "gauss_legendre_2_constant_control", 4)
+    x0 = m.x0()
+    assert np.any(x0 == ka["default_initial_guess"]["value"])      # stage variables keep the default
+
+
+def test_oracle_reproduces_regression_vectors(oracle_mod):
+    """tests/golden/regression_vectors.npz (made by tests/golden/make_regression_vectors.py from this oracle: regression
+    anchors, NOT reference outputs).  The oracle must still produce them bit for bit (same compiler flags, no
+    reassociation) -- a drift here means the checker itself changed."""
+    z = np.load(_golden("regression_vectors.npz"))
+    tags = sorted({k.rsplit("|", 1)[0] for k in z.files})
+    assert len(tags) >= 9
+    for tag in tags:
+        p, s, n, mode = tag.split("|")
+        o = oracle_mod.OracleModel(p, s, int(n), pattern_mode=mode)
+        x, y = z[tag + "|x"], z[tag + "|y"]
+        g, j, h = o.derivs(x, y, 0.75)
+        for key, val in (("cons", o.cons(x)), ("jac", j), ("hess", h), ("grad", g), ("obj", np.array([o.obj(x)]))):
+            ref = z[tag + "|" + key]
+            assert val.shape == ref.shape, (tag, key)
+            assert np.allclose(val, ref, rtol=1e-14, atol=0.0) or np.array_equal(val, ref), (tag, key)
