@@ -88,7 +88,11 @@ struct Cfg {
     static constexpr int NJV = NV * E::JV_STRIDE;
     // phase A stages constraints, Jacobian and gradient; phase B the Hessian (same shared memory)
     static constexpr bool PHASE_A = WC || WJ || WG || WO, PHASE_B = WH;
-    static constexpr int PER_STEP_A = (WC ? E::CB : 0) + (WJ ? E::J_BLOCK + NJV : 0) + (WG ? E::BLK : 0);
+    // GZ: no step contributes to the objective gradient (Mayer cost only, e.g. Goddard, robot arm): there is
+    // nothing to stage, the tiles store the zeros of their column blocks directly; SG: gradient staged
+    static constexpr bool GZ = WG && E::NG_OWN == 0 && E::NG_NEXT == 0 && E::NG_V == 0;
+    static constexpr bool SG = WG && !GZ;
+    static constexpr int PER_STEP_A = (WC ? E::CB : 0) + (WJ ? E::J_BLOCK + NJV : 0) + (SG ? E::BLK : 0);
     static constexpr int PER_STEP_B = WH ? E::H_BLOCK : 0;
     static constexpr int PER_STEP = PER_STEP_A > PER_STEP_B ? PER_STEP_A : PER_STEP_B;
     // WPC = the LARGEST number of warps per CTA a launch may use (the host picks blockDim per launch,
@@ -131,7 +135,7 @@ struct Cfg {
     static constexpr int S_JV = S_J + (WJ ? even((OWN + 1) * E::J_BLOCK) : 0);
     static constexpr int JV_ONE = even((OWN + 1) * E::JV_STRIDE);
     static constexpr int S_G = S_JV + (WJ ? NV * JV_ONE : 0);
-    static constexpr int A_END = S_G + (WG ? even((OWN + 1) * E::BLK) : 0);
+    static constexpr int A_END = S_G + (SG ? even((OWN + 1) * E::BLK) : 0);
     static constexpr int S_H = 0;
     static constexpr int B_END = WH ? even((OWN + 1) * E::H_BLOCK) : 0;
     static constexpr int WARP_DOUBLES = ((A_END > B_END ? A_END : B_END) + 1) & ~1;
@@ -699,8 +703,14 @@ __device__ __forceinline__ void eval_body(const EvalArgs& a) {
         if (active && Tm.hh == -1.2345) CTD_STAMP(7);   // forces the loads to have arrived
         CTD_STAMP(1);
 #endif
+        if constexpr (C::GZ) {   // gradient entries of the owned column blocks: zeros (see Cfg::GZ)
+            if (nown > 0) {
+                double* g0 = grad + (i0 - 1) * E::BLK;
+                for (int k = lane; k < nown * E::BLK; k += 32) g0[k] = 0.0;
+            }
+        }
         if constexpr (C::PHASE_A)
-            tile_phase<E, F, C::WC, C::WJ, false, C::WG, C::WO>(a, ws, z, lam, Tm, p, red, lane, nown, i0, active, c,
+            tile_phase<E, F, C::WC, C::WJ, false, C::SG, C::WO>(a, ws, z, lam, Tm, p, red, lane, nown, i0, active, c,
                                                                   jvals, hvals, grad);
         CTD_STAMP(2);
         if constexpr (C::PHASE_B) {
