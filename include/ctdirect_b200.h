@@ -8,7 +8,8 @@
  * src/collocation.jl:90-153).
  *
  * Conventions
- *  - return value: 0 = ok, < 0 = usage error, > 0 = CUDA error code; ctd_last_error() gives the message
+ *  - return value: 0 = ok, < 0 = usage error, > 0 = CUDA error code (1000 + ncclResult_t for a failure of the
+ *    norm gather); ctd_last_error() gives the message
  *    (thread-local).  Nothing is thrown across the boundary.  NaN/Inf in results are passed through.
  *  - all floating-point data are IEEE double; all indices are int64 and 1-BASED, in the order of
  *    Julia's CSC storage (column by column, rows ascending); the Hessian is the lower triangle.
