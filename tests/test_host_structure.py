@@ -109,6 +109,23 @@ def test_no_cpu_fallback(ctd):
             call()
 
 
+def test_stream_and_communicator_entry_points_without_a_device(ctd):
+    """The newer entry points follow the same convention: host-only queries work anywhere (KKT structure, NCCL id),
+    anything that needs the device returns a CUDA error instead of crashing."""
+    import torch
+    d = ctd.DOCP("goddard", 10, "midpoint")
+    assert d.nnzk == d.nnzh + d.nnzj + d.ncon + (d.nvar - int(np.sum(np.equal(*d.hessian_structure()))))
+    uid = ctd.DOCP.nccl_unique_id()
+    assert isinstance(uid, bytes) and len(uid) == 128 and any(uid)
+    with pytest.raises(ValueError):
+        d.comm_init(b"short", 0, 1)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    for call in (lambda: d.comm_init(uid, 0, 1), lambda: d.set_stream(None), lambda: d.comm_wait(0)):
+        with pytest.raises(ctd.CtdError):
+            call()
+
+
 def test_product_never_touches_the_oracle():
     """No file of the product package imports, loads, links or executes anything under oracle/."""
     import os
