@@ -771,7 +771,14 @@ struct PCfg {
     static constexpr bool FIVE = TWO && FIT5 >= 24 && FIT5 < CTD_PART_OWN;
     static constexpr int OWN_T = FIVE ? FIT5 : CTD_PART_OWN;
     static constexpr int OWN = (OWN_T < FIT) ? OWN_T : FIT;
-    static constexpr int MINB = FIVE ? 5 : 1;
+    // The single-output kernels of an element whose fused kernel runs with 5 CTAs per SM get the same register
+    // cap: the Hessian-only kernel of a 3-stage IRK otherwise takes 248 registers = 4 CTAs per SM = 592 of the
+    // 645 tiles of a 2e4-step grid resident, i.e. a second wave (the same code is spill-free in 168 registers
+    // inside the two-phase kernel).  Elements outside that class keep the full register file.
+    static constexpr int PER7 = (E::CB + E::J_BLOCK + C::NJV) > E::H_BLOCK ? (E::CB + E::J_BLOCK + C::NJV) : E::H_BLOCK;
+    static constexpr int FIT5_7 = (44 * 1024) / (PER7 * 8) - 1;
+    static constexpr bool FIVE7 = FIT5_7 >= 24 && FIT5_7 < CTD_PART_OWN;
+    static constexpr int MINB = (FIVE || (FIVE7 && PER_STEP * 8 * (OWN + 1) <= 44 * 1024)) ? 5 : 1;
     static_assert(OWN >= 1, "element too wide for one SM's shared memory");
     static constexpr int even(int n) { return (n + 3) & ~1; }
     static constexpr int S_C = 0;
