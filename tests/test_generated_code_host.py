@@ -153,6 +153,11 @@ CASES = [("goddard", "midpoint", "reference"), ("goddard", "midpoint", "optimize
          ("estimate_rotation_rate", "midpoint", "reference")]
 
 
+if os.environ.get("CTD_HOST_ALL"):   # opt-in: every compiled (problem, scheme, pattern mode) triple, ~15 min on 8 cores
+    CASES = [tuple(l.strip()[2:].split("__")) for l in open(os.path.join(GEN, "MANIFEST.txt")) if l.strip()]
+    CASES = [(c[0], c[1], c[2] if len(c) > 2 else "reference") for c in CASES]
+
+
 @pytest.mark.parametrize("problem,scheme,mode", CASES)
 def test_host_compiled_elements_match_oracle(oracle_mod, tmp_path, problem, scheme, mode):
     name = f"E_{problem}__{scheme}" + ("" if mode == "reference" else "__" + mode)
