@@ -469,7 +469,7 @@ def main():
         nms = nps = None
         if world > 1:
             from ctdirect_b200.batch import NativeNormsPipeline, broadcast_unique_id
-            npipe = NativeNormsPipeline(bd, rank, world, broadcast_unique_id(), depth=2)
+            npipe = NativeNormsPipeline(bd, rank, world, broadcast_unique_id(), depth=2, n_instances=bl * world)
             nout = {k_: v_ for k_, v_ in bout.items() if k_ != "obj"}
             nms = timed_batched(lambda: npipe.submit(ALL, tx, ty, nout, serial=True), npipe.drain)
             nps = timed_batched(lambda: npipe.submit(ALL, tx, ty, nout), npipe.drain)

@@ -158,10 +158,14 @@ class NativeNormsPipeline:
         norms = pipe.result(slot)                  # (world, 2, batch) tensor, valid on the handle's stream
     """
 
-    def __init__(self, docp, rank: int, world: int, unique_id: bytes, depth: int = 2):
+    def __init__(self, docp, rank: int, world: int, unique_id: bytes, depth: int = 2, n_instances: Optional[int] = None):
         import torch
         if not (1 <= depth <= 4):
             raise ValueError("depth must be 1..4 (CTD_COMM_SLOTS)")
+        # ncclAllGather moves the same count from every rank: unequal shards would corrupt the result or hang
+        if n_instances is not None and docp.batch * world != n_instances:
+            raise ValueError(f"shards must have the same size on every rank: {n_instances} instances over {world} ranks "
+                             f"with {docp.batch} here (pad the batch to a multiple of the number of ranks)")
         self.docp, self.world, self.depth, self.k = docp, world, depth, 0
         docp.comm_init(unique_id, rank, world)
         dev = torch.device("cuda", docp.device)

@@ -118,3 +118,15 @@ def test_numa_binding_helper_never_raises():
     info = bind_to_gpu_numa_node(0)
     assert info["device"] == 0 and "numa_node" in info
     assert os.sched_getaffinity(0) <= before and len(os.sched_getaffinity(0)) > 0
+
+
+def test_native_pipeline_rejects_unequal_shards():
+    from ctdirect_b200.batch import NativeNormsPipeline
+
+    class FakeDocp:
+        batch, device = 3, 0
+
+    with pytest.raises(ValueError, match="same size on every rank"):
+        NativeNormsPipeline(FakeDocp(), 0, 2, b"x" * 128, n_instances=7)
+    with pytest.raises(ValueError, match="depth"):
+        NativeNormsPipeline(FakeDocp(), 0, 2, b"x" * 128, depth=9)
