@@ -62,6 +62,7 @@ struct ElemInfo {
     int ctrl_blk = 0, blk = 0, eqs = 0, cb = 0, nown = 0, nnext = 0, nz = 0;
     int j_block = 0, h_block = 0, j_first = 0, h_first = 0, jv_stride = 0, fp_nloc = 0, bc_nloc = 0;
     int n_dropped = 0;
+    int nh_vv_emit = 0;   // (v,v) Hessian terms emitted by a step (0: no grid-wide sum for them)
     SlotTable j_own, j_next, j_v, h_own, h_next, h_vv, fp_j, fp_h, bc_j, bc_h, g_own, g_next, g_v, bc_g;
     SlotTable s_step_j, s_step_h, s_fp_j, s_fp_h, s_bc_j, s_bc_h;   // detected structure (pattern mode 2)
     ProblemMeta meta;
@@ -90,6 +91,7 @@ inline ElemInfo make_elem_info() {
     f.nown = E::NOWN; f.nnext = E::NNEXT; f.nz = E::NZ;
     f.j_block = E::J_BLOCK; f.h_block = E::H_BLOCK; f.j_first = E::J_FIRST; f.h_first = E::H_FIRST;
     f.jv_stride = E::JV_STRIDE; f.fp_nloc = E::FP_NLOC; f.bc_nloc = E::BC_NLOC; f.n_dropped = E::N_DROPPED;
+    f.nh_vv_emit = E::NH_VV_EMIT;
     CTD_FILL_TABLE(f, E, J_OWN, j_own);
     CTD_FILL_TABLE(f, E, J_NEXT, j_next);
     CTD_FILL_TABLE(f, E, J_V, j_v);

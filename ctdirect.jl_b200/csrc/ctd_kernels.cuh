@@ -20,8 +20,15 @@
 //   * the irregular ends (column blocks 1, N, N+1, boundary / final-path rows) are handled by CTA 0
 //     through host-built position tables;
 //   * (v,v) Hessian entries, d/dv of the cost and the Lagrange sum are reduced with warp shuffles into
-//     per-CTA partials and summed in a fixed order by the last CTA to finish (deterministic, no
-//     floating-point atomics on global memory).
+//     per-CTA partials that are summed in a fixed order (deterministic, no floating-point atomics on
+//     global memory): for a single instance by a collector warp of CTA 0 that picks the partials up as
+//     they are published (self-validating 16-byte records, no fences or tickets on the critical path),
+//     for batches by the last CTA of the instance to finish.  Slots to which no STEP contributes
+//     (e.g. the (tf,tf) entry of an autonomous free-final-time problem) are not reduced at all: the
+//     edge CTA writes them;
+//   * everything that does not depend on earlier work of the stream (tile geometry, normalized times,
+//     parameters, edge tables, L2 prefetch of the tile's inputs) runs BEFORE griddepcontrol.wait, i.e.
+//     while the previous kernel of the stream drains (programmatic dependent launch).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -61,8 +68,10 @@ struct EvalArgs {
     long long jv_base[MAX_NV];    // position of the first value of column v_k in jvals
     long long hvv_pos[MAX_NVV];   // positions of the (v_a, v_b) entries in hvals (packed lower triangle)
     double* viol;                 // [batch] max(lcon - c, c - ucon, 0) per instance, or nullptr
-    double* partials;             // [batch][ctas][NRED + 1]
+    double* partials;             // [batch][ctas][NREDX] doubles (ticket mode) or 16-byte records (collector mode)
     unsigned int* counters;       // [batch]
+    unsigned long long key;       // collector mode: validation key of THIS launch (never 0; changes with every launch)
+    int poll;                     // 1: collector mode (see publish_reduction), 0: ticket mode
     // edge tables (identical for every instance)
     const int* edge_map;
     const long long* edge_pos;    // destination position of every edge-buffer entry
@@ -81,8 +90,13 @@ struct Cfg {
     static_assert(!WV || WC, "the violation norm is a by-product of the constraint rows");
     static constexpr int NV = E::NV;
     static constexpr int NVV = NV * (NV + 1) / 2;
-    static constexpr int R_H = 0, R_G = R_H + (WH ? NVV : 0), R_O = R_G + (WG ? NV : 0);
-    static constexpr int NRED = R_O + (WO ? 1 : 0);
+    // grid-wide sums exist only for the quantities a STEP contributes to: (v,v) Hessian entries (none for
+    // autonomous dynamics with the free times entering through h only), d cost / d v and the cost itself
+    // (none for a Mayer cost).  What only the boundary / final-path elements touch is written by the edge
+    // CTA through its value buffer (Model::build_edge_tables makes the same distinction).
+    static constexpr bool RH = WH && E::NH_VV_EMIT > 0, RG = WG && E::NG_V > 0, RO = WO && E::LAGRANGE;
+    static constexpr int R_H = 0, R_G = R_H + (RH ? NVV : 0), R_O = R_G + (RG ? NV : 0);
+    static constexpr int NRED = R_O + (RO ? 1 : 0);
     // one more slot, combined with max instead of +: the constraint violation of the instance
     static constexpr int R_V = NRED, NREDX = NRED + (WV ? 1 : 0);
     static constexpr int NJV = NV * E::JV_STRIDE;
@@ -157,14 +171,13 @@ __device__ __forceinline__ double grid_point(const EvalArgs& a, long long j /*0-
     return __ldg(a.sgrid + j);
 }
 
+// t_i = t0 + s_i * (tf - t0) for the two nodes of a step (normalized times si, sp), the step length and their
+// forward-mode seeds w.r.t. the free times in v  (get_time_grid: DOCP_data.jl:437-458)
 template <class E>
-__device__ __forceinline__ void time_args(const EvalArgs& a, const double* v, const double* p, long long i,
-                                          TimeArgs<E::NV>& T) {
-    // get_time_grid: DOCP_data.jl:437-458, t_i = t0 + s_i * (tf - t0)
+__device__ __forceinline__ void time_args_s(const double si, const double sp, const double* v, const double* p,
+                                            TimeArgs<E::NV>& T) {
     const double t0 = E::T0_KIND == 0 ? E::T0_CONST : (E::T0_KIND == 1 ? v[E::T0_IDX > 0 ? E::T0_IDX : 0] : p[E::T0_IDX > 0 ? E::T0_IDX : 0]);
     const double tf = E::TF_KIND == 0 ? E::TF_CONST : (E::TF_KIND == 1 ? v[E::TF_IDX > 0 ? E::TF_IDX : 0] : p[E::TF_IDX > 0 ? E::TF_IDX : 0]);
-    const double si = grid_point(a, i - 1);
-    const double sp = (i <= a.N) ? grid_point(a, i) : si;
     T.ti = CTD_ADD(t0, CTD_MUL(si, CTD_SUB(tf, t0)));
     T.tp = CTD_ADD(t0, CTD_MUL(sp, CTD_SUB(tf, t0)));
     T.hh = CTD_SUB(T.tp, T.ti);
@@ -179,6 +192,14 @@ __device__ __forceinline__ void time_args(const EvalArgs& a, const double* v, co
     }
 }
 
+template <class E>
+__device__ __forceinline__ void time_args(const EvalArgs& a, const double* v, const double* p, long long i,
+                                          TimeArgs<E::NV>& T) {
+    const double si = grid_point(a, i - 1);
+    const double sp = (i <= a.N) ? grid_point(a, i) : si;
+    time_args_s<E>(si, sp, v, p, T);
+}
+
 // ---- TMA bulk store (cp.async.bulk, shared::cta -> global): one elected lane hands a staged range to
 // the copy engine, the warp's issue slots stay free for the next phase.
 __device__ __forceinline__ void fence_proxy_async_smem() {
@@ -186,24 +207,32 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-// contiguous shared -> global copy of n doubles; s and g have the same 16-byte phase.  Called by the
-// whole warp after fence_proxy_async_smem() + __syncwarp(); lane 0 issues the bulk copy of the
-// 16-byte-aligned body, the (at most one) leading and trailing doubles are stored directly.
-__device__ __forceinline__ void bulk_store_range(double* __restrict__ g, const double* __restrict__ s, int n, int lane) {
-    const int ph = (int)((reinterpret_cast<unsigned long long>(g) >> 3) & 1ull);
-    const int head = ph < n ? ph : n;
-    const int n2 = (n - head) >> 1;
-    if (lane == 0) {
-        if (n2 > 0) {
-            const unsigned int saddr = (unsigned int)__cvta_generic_to_shared(s + head);
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                         :: "l"(g + head), "r"(saddr), "r"(n2 * 16) : "memory");
-        }
-    } else if (lane == 1) {
-        if (head) g[0] = s[0];
-        const int done = head + 2 * n2;
-        if (done < n) g[done] = s[done];
-    }
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+// One lane of a converged warp, chosen by the hardware: ptxas then knows that the block it guards runs in a
+// single thread and moves its operands to uniform registers without a per-value loop (a `lane == 0` test
+// costs ~25 instructions per bulk copy).
+__device__ __forceinline__ bool elect_one() {
+    unsigned int pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ int phase_of(const double* g) {
+    return (int)(((unsigned int)reinterpret_cast<unsigned long long>(g) >> 3) & 1u);
+}
+// A staged range of n >= 1 doubles, destination g (8-byte aligned), staged copy s with the SAME 16-byte phase
+// as g (s_u32 = its shared-memory address).  The 16-byte-aligned body goes through the copy engine (issued by
+// the elected lane), the at most one leading and one trailing double are stored directly (by lane 1).
+__device__ __forceinline__ void bulk_body(double* __restrict__ g, unsigned int s_u32, int n) {
+    const int ph = phase_of(g);
+    const int body = (n - ph) >> 1;
+    if (body > 0)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     :: "l"(g + ph), "r"(s_u32 + 8u * (unsigned int)ph), "r"(body << 4) : "memory");
+}
+__device__ __forceinline__ void ragged_ends(double* __restrict__ g, const double* __restrict__ s, int n) {
+    const int ph = phase_of(g);
+    if (ph) g[0] = s[0];
+    if ((n - ph) & 1) g[n - 1] = s[n - 1];
 }
 
 #ifdef CTD_TRACE
@@ -220,10 +249,6 @@ __device__ __forceinline__ long long gtime() {
 // NaN-propagating max (a NaN constraint value must surface as a NaN violation)
 __device__ __forceinline__ double nanmax(double a, double b) { return (b > a || b != b) ? b : a; }
 __device__ __forceinline__ double row_violation(double lb, double ub, double v) { return nanmax(lb - v, v - ub); }
-
-__device__ __forceinline__ int phase_of(const double* g) {
-    return (int)((reinterpret_cast<unsigned long long>(g) >> 3) & 1ull);
-}
 
 // ---------------------------------------------------------------------------------------------
 // Sink of a tile thread for one phase (PC/PJ/PH/PG select what this phase keeps): derivative values go
@@ -255,10 +280,10 @@ struct TileSink {
     }
     template <int N> __device__ __forceinline__ void ho(double v) { if (PH) ho_[E::H_OWN(N, 2)] = v; }
     template <int N> __device__ __forceinline__ void hn(double v) { if (PH) hn_[N] = v; }
-    template <int K> __device__ __forceinline__ void hv(double v) { if (PH) red[C::R_H + K] += owner ? v : 0.0; }
+    template <int K> __device__ __forceinline__ void hv(double v) { if constexpr (PH && C::RH) red[C::R_H + K] += owner ? v : 0.0; }
     template <int N> __device__ __forceinline__ void go(double v) { if (PG) go_[E::G_OWN(N, 2)] = v; }
     template <int N> __device__ __forceinline__ void gn(double v) { if (PG) gn_[N] = v; }
-    template <int N> __device__ __forceinline__ void gv(double v) { if (PG) red[C::R_G + E::G_V(N, 2)] += owner ? v : 0.0; }
+    template <int N> __device__ __forceinline__ void gv(double v) { if constexpr (PG && C::RG) red[C::R_G + E::G_V(N, 2)] += owner ? v : 0.0; }
 };
 
 // Sink of an edge step job: like a tile, every value is staged at its compile-time slot of the task's
@@ -283,10 +308,10 @@ struct EdgeSink {
     template <int N> __device__ __forceinline__ void jv(double v) { st[C::M_JV + N] = v; }
     template <int N> __device__ __forceinline__ void ho(double v) { st[C::M_HO + N] = v; }
     template <int N> __device__ __forceinline__ void hn(double v) { st[C::M_HN + N] = v; }
-    template <int K> __device__ __forceinline__ void hv(double v) { if (sums) red[C::R_H + K] += v; }
+    template <int K> __device__ __forceinline__ void hv(double v) { if constexpr (C::RH) { if (sums) red[C::R_H + K] += v; } }
     template <int N> __device__ __forceinline__ void go(double v) { st[C::M_GO + N] = v; }
     template <int N> __device__ __forceinline__ void gn(double v) { st[C::M_GN + N] = v; }
-    template <int N> __device__ __forceinline__ void gv(double v) { if (sums) red[C::R_G + E::G_V(N, 2)] += v; }
+    template <int N> __device__ __forceinline__ void gv(double v) { if constexpr (C::RG) { if (sums) red[C::R_G + E::G_V(N, 2)] += v; } }
 };
 
 // final path / boundary elements (edge CTA only): c<R>, j<N>, h<N>, g<N>
@@ -314,12 +339,12 @@ struct EdgeElemSink {
     template <int N> __device__ __forceinline__ void h(double v) {
         const int m = map[MH + N];
         if (m >= 0) buf[m] = v;
-        else if (m <= -2) red[C::R_H + (-m - 2)] += v;
+        else if constexpr (C::RH) { if (m <= -2) red[C::R_H + (-m - 2)] += v; }
     }
     template <int N> __device__ __forceinline__ void g(double v) {
         const int m = map[MG + N];
         if (m >= 0) buf[m] = v;
-        else if (m <= -2) red[C::R_G + (-m - 2)] += v;
+        else if constexpr (C::RG) { if (m <= -2) red[C::R_G + (-m - 2)] += v; }
     }
 };
 
@@ -334,6 +359,23 @@ __device__ __forceinline__ void load_step(const double* __restrict__ x, long lon
     for (int k = 0; k < E::NV; ++k) z[E::NOWN + E::NNEXT + k] = __ldg(x + nvar - E::NV + k);
 }
 
+// Programmatic dependent launch: a launch made with the programmatic-stream-serialization attribute may
+// be scheduled while the previous kernel of the stream is still draining; `griddepcontrol.wait` blocks
+// until that kernel has completed and its memory is visible.  Everything a thread does BEFORE it must not
+// depend on (or disturb) earlier work of the stream: tile geometry, the normalized time grid, parameters
+// and edge tables (handle-owned, only ever written by stream-ordered copies), shared-memory setup, and L2
+// prefetches of the inputs (a prefetch returns no data; the L2 is the coherence point).
+#ifndef CTD_PDL
+#define CTD_PDL 1
+#endif
+__device__ __forceinline__ void pdl_entry() {
+#if CTD_PDL
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
 // Edge CTA: the elements that touch column blocks 1, N, N+1 and the boundary / final-path rows.  The
 // work is cut into jobs -- (step elements, phase A), (step elements, phase B), final-path element,
 // boundary+Mayer element -- one warp each; the step elements of one phase run in the lanes of one warp.  Jobs whose values can land on the same entry
@@ -346,7 +388,7 @@ __device__ __forceinline__ void edge_step_job(const EvalArgs& a, const EdgeTask&
                                               const double* __restrict__ y, const double* __restrict__ p, double* c,
                                               double* stage, const int* smap, double* red) {
     using C = Cfg<E, F>;
-    constexpr bool JC = PA && C::WC, JJ = PA && C::WJ, JH = PB && C::WH, JG = PA && C::WG, JO = PA && C::WO;
+    constexpr bool JC = PA && C::WC, JJ = PA && C::WJ, JH = PB && C::WH, JG = PA && C::WG, JO = PA && C::RO;
     double z[E::NZ], lam[E::CB];
     load_step<E>(x, a.nvar, tk.step, z);
 #pragma unroll
@@ -363,21 +405,27 @@ __device__ __forceinline__ void edge_step_job(const EvalArgs& a, const EdgeTask&
     if constexpr (JO) { if (tk.own) red[C::R_O] += E::cost_step(z, Tm, p); }
 }
 
+// shared-memory layout of the edge CTA (dynamic shared memory, sized by Model::eval_dev):
+//   EDGE_LAYERS x ne doubles (value layers) | nmap ints (position maps) | ntask x M_STEP doubles (staging
+//   blocks of the step tasks) | ne int64 (destination positions)
 template <class E, int F>
 __device__ void edge_cta(const EvalArgs& a, const double* __restrict__ x, const double* __restrict__ y,
                          const double* __restrict__ p, double* c, double* jvals, double* hvals, double* grad,
-                         double* buf, double* red, const int NW) {
+                         double* obj, double* buf, double* red, const int NW) {
     using C = Cfg<E, F>;
     const int tid = threadIdx.x;
     const int T = NW * 32;
     const int ne = a.ne_j + a.ne_h + a.ne_g;
-    // the position maps are staged in shared memory first (one coalesced pass): the sinks look up one
-    // map entry per value, and those lookups must not be dependent global loads
     int* smap = reinterpret_cast<int*>(buf + EDGE_LAYERS * ne);
-    // staging blocks of the step tasks (behind the maps): see EdgeSink
     double* stage = buf + EDGE_LAYERS * ne + (a.nmap + 1) / 2;
+    long long* spos = reinterpret_cast<long long*>(stage + a.ntask * C::M_STEP);
+    // ---- before the grid dependency: the (immutable) position tables are staged in shared memory -- the
+    //      sinks look up one map entry per value and those lookups must not be dependent global loads --
+    //      and the value layers are cleared
     for (int k = tid; k < a.nmap; k += T) smap[k] = __ldg(a.edge_map + k);
+    for (int k = tid; k < ne; k += T) spos[k] = __ldg(a.edge_pos + k);
     for (int k = tid; k < EDGE_LAYERS * ne; k += T) buf[k] = 0.0;
+    pdl_entry();
     __syncthreads();
     {
         // warp roles: the step elements of all edge tasks run side by side in the lanes of one warp
@@ -442,7 +490,11 @@ __device__ void edge_cta(const EvalArgs& a, const double* __restrict__ x, const 
                 s.red = red;
                 if constexpr (C::WC || C::WJ || C::WH) E::template bc<C::WC, C::WJ, C::WH>(z, p, lam, a.sigma, s);
                 if constexpr (C::WG) E::grad_bc(z, p, s);
-                if constexpr (C::WO) red[C::R_O] += E::mayer(z, p);
+                if constexpr (C::WO) {
+                    // a Mayer-only objective is this one number: no grid-wide sum
+                    if constexpr (C::RO) red[C::R_O] += E::mayer(z, p);
+                    else if (obj) *obj = E::mayer(z, p);
+                }
             }
         }
     }
@@ -467,11 +519,11 @@ __device__ void edge_cta(const EvalArgs& a, const double* __restrict__ x, const 
     // ---- scatter the edge buffer (layers summed in a fixed order)
     auto total = [&](int k) { return ((buf[k] + buf[ne + k]) + buf[2 * ne + k]) + buf[3 * ne + k]; };
     if constexpr (C::WJ)
-        for (int k = tid; k < a.ne_j; k += T) jvals[__ldg(a.edge_pos + k)] = total(k);
+        for (int k = tid; k < a.ne_j; k += T) jvals[spos[k]] = total(k);
     if constexpr (C::WH)
-        for (int k = a.ne_j + tid; k < a.ne_j + a.ne_h; k += T) hvals[__ldg(a.edge_pos + k)] = total(k);
+        for (int k = a.ne_j + tid; k < a.ne_j + a.ne_h; k += T) hvals[spos[k]] = total(k);
     if constexpr (C::WG)
-        for (int k = a.ne_j + a.ne_h + tid; k < ne; k += T) grad[__ldg(a.edge_pos + k)] = total(k);
+        for (int k = a.ne_j + a.ne_h + tid; k < ne; k += T) grad[spos[k]] = total(k);
     __syncthreads();   // the caller reuses the shared memory of `buf` for its reduction scratch
 }
 
@@ -479,14 +531,14 @@ __device__ void edge_cta(const EvalArgs& a, const double* __restrict__ x, const 
 template <class E, int F, bool PC, bool PJ, bool PH, bool PG, bool PO>
 __device__ __forceinline__ void tile_phase(const EvalArgs& a, double* __restrict__ ws, const double* __restrict__ z,
                                            const double* __restrict__ lam, const TimeArgs<E::NV>& Tm,
-                                           const double* __restrict__ p, double* red, int lane, int nown, long long i0,
+                                           const double* __restrict__ p, double* red, int lane, int nown, int i0,
                                            bool active, double* c, double* jvals, double* hvals, double* grad) {
     using C = Cfg<E, F>;
     // global destinations of this tile and the matching shared-memory phases
-    double* gC = PC ? c + (i0 - 1) * E::CB : nullptr;
-    double* gJ = PJ ? jvals + E::J_FIRST + (i0 - 2) * E::J_BLOCK : nullptr;
-    double* gH = PH ? hvals + E::H_FIRST + (i0 - 2) * E::H_BLOCK : nullptr;
-    double* gG = PG ? grad + (i0 - 1) * E::BLK : nullptr;
+    double* gC = PC ? c + (long long)(i0 - 1) * E::CB : nullptr;
+    double* gJ = PJ ? jvals + (E::J_FIRST + (long long)(i0 - 2) * E::J_BLOCK) : nullptr;
+    double* gH = PH ? hvals + (E::H_FIRST + (long long)(i0 - 2) * E::H_BLOCK) : nullptr;
+    double* gG = PG ? grad + (long long)(i0 - 1) * E::BLK : nullptr;
     double* sC = ws + C::S_C + (PC ? phase_of(gC) : 0);
     double* sJ = ws + C::S_J + (PJ ? phase_of(gJ) : 0);
     double* sH = ws + C::S_H + (PH ? phase_of(gH) : 0);
@@ -496,7 +548,7 @@ __device__ __forceinline__ void tile_phase(const EvalArgs& a, double* __restrict
     if constexpr (PJ && C::NV > 0) {
 #pragma unroll
         for (int k = 0; k < C::NV; ++k) {
-            gJV[k] = jvals + a.jv_base[k] + (i0 - 1) * E::JV_STRIDE;
+            gJV[k] = jvals + (a.jv_base[k] + (long long)(i0 - 1) * E::JV_STRIDE);
             sJV[k] = ws + C::S_JV + k * C::JV_ONE + phase_of(gJV[k]);
         }
     }
@@ -522,7 +574,7 @@ __device__ __forceinline__ void tile_phase(const EvalArgs& a, double* __restrict
         }
         if constexpr (PC || PJ || PH) E::template step<PC, PJ, PH>(z, Tm, p, lam, a.sigma, s);
         if constexpr (PG) E::grad_step(z, Tm, p, s);
-        if constexpr (PO) { if (s.owner) red[C::R_O] += E::cost_step(z, Tm, p); }
+        if constexpr (PO && C::RO) { if (s.owner) red[C::R_O] += E::cost_step(z, Tm, p); }
     }
     __syncwarp();
     if constexpr ((PH && E::NH_NEXT > 0) || (PG && E::NG_NEXT > 0)) {
@@ -541,23 +593,62 @@ __device__ __forceinline__ void tile_phase(const EvalArgs& a, double* __restrict
     fence_proxy_async_smem();
     __syncwarp();
     if (nown > 0) {
-        if constexpr (PC) bulk_store_range(gC, sC, nown * E::CB, lane);
-        if constexpr (PJ) {
-            bulk_store_range(gJ, sJ, nown * E::J_BLOCK, lane);
-            if constexpr (C::NV > 0) {
+        // the elected lane hands the 16-byte-aligned bodies of all ranges to the copy engine, lane 1 stores
+        // the ragged ends (ranges start on 8-byte, not 16-byte, boundaries for odd block sizes)
+        if (elect_one()) {
+            if constexpr (PC) bulk_body(gC, smem_u32(sC), nown * E::CB);
+            if constexpr (PJ) {
+                bulk_body(gJ, smem_u32(sJ), nown * E::J_BLOCK);
+                if constexpr (C::NV > 0) {
 #pragma unroll
-                for (int k = 0; k < C::NV; ++k) bulk_store_range(gJV[k], sJV[k], nown * E::JV_STRIDE, lane);
+                    for (int k = 0; k < C::NV; ++k) bulk_body(gJV[k], smem_u32(sJV[k]), nown * E::JV_STRIDE);
+                }
             }
+            if constexpr (PH) bulk_body(gH, smem_u32(sH), nown * E::H_BLOCK);
+            if constexpr (PG) bulk_body(gG, smem_u32(sG), nown * E::BLK);
+            bulk_commit();
         }
-        if constexpr (PH) bulk_store_range(gH, sH, nown * E::H_BLOCK, lane);
-        if constexpr (PG) bulk_store_range(gG, sG, nown * E::BLK, lane);
-        if (lane == 0) bulk_commit();
+        if (lane == 1) {
+            if constexpr (PC) ragged_ends(gC, sC, nown * E::CB);
+            if constexpr (PJ) {
+                ragged_ends(gJ, sJ, nown * E::J_BLOCK);
+                if constexpr (C::NV > 0) {
+#pragma unroll
+                    for (int k = 0; k < C::NV; ++k) ragged_ends(gJV[k], sJV[k], nown * E::JV_STRIDE);
+                }
+            }
+            if constexpr (PH) ragged_ends(gH, sH, nown * E::H_BLOCK);
+            if constexpr (PG) ragged_ends(gG, sG, nown * E::BLK);
+        }
     }
 }
 
-// Deterministic reduction of the global sums ((v,v) Hessian entries, d cost / d v, cost) over the grid.
-// No CTA barrier: the last warp of a CTA to arrive combines the CTA's NW warps in a fixed order and
-// publishes one partial; the last CTA to publish sums all partials in a fixed order.
+// ---------------------------------------------------------------------------------------------
+// Deterministic reduction of the global sums ((v,v) Hessian entries, d cost / d v, cost, violation) over
+// the grid.  Inside a CTA: warp shuffles, then the last warp to arrive (shared-memory ticket, no CTA
+// barrier) combines the CTA's NW warps in a fixed order into ONE partial per slot.  Across CTAs:
+//   * ticket mode (batches): the partial is stored, fenced, a global ticket is taken and the last CTA of
+//     the instance sums all partials in a fixed order;
+//   * collector mode (a.poll, single instances, where this tail is on the critical path of the launch):
+//     the partial is published as a self-validating 16-byte record {bits(v), bits(v) ^ key} with one plain
+//     vector store -- no fence, no atomic -- and the last warp of CTA 0 collects the records of all CTAs
+//     while the grid is still running (re-reading those that have not landed), then sums them in the same
+//     fixed order.  `key` changes with every launch of the handle, so a record left by an earlier launch
+//     (or a torn read) never validates; producers never wait on anything, so the collector cannot deadlock
+//     whatever the CTA dispatch order.
+struct alignas(16) RedRecord { unsigned long long v, chk; };
+
+__device__ __forceinline__ void store_record(RedRecord* dst, double v, unsigned long long key) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" :: "l"(dst), "l"(b), "l"(b ^ key) : "memory");
+}
+__device__ __forceinline__ bool load_record(const RedRecord* src, unsigned long long key, double& v) {
+    unsigned long long b, chk;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(b), "=l"(chk) : "l"(src) : "memory");
+    v = __longlong_as_double((long long)b);
+    return (b ^ chk) == key;
+}
+
 template <class E, int F>
 __device__ __forceinline__ void publish_reduction(const EvalArgs& a, const double* red, double* sred,
                                                   unsigned int* cta_ticket_p, long long inst, int cta, int lane,
@@ -567,6 +658,21 @@ __device__ __forceinline__ void publish_reduction(const EvalArgs& a, const doubl
         constexpr int NR = C::NREDX;
         // slot R_V (the constraint violation) is combined with max, every other slot with +
         auto comb = [](int k, double x, double y) { return (C::WV && k == C::R_V) ? nanmax(x, y) : x + y; };
+        // final values of the instance -> their destinations (lane 0 of the finishing warp)
+        auto finish = [&](const double* acc) {
+#pragma unroll
+            for (int k = 0; k < NR; ++k) {
+                double v = acc[k];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v = comb(k, v, __shfl_xor_sync(0xffffffffu, v, o));
+                if (lane == 0) {
+                    if (C::WV && k == C::R_V) { if (a.viol) a.viol[inst] = v; }
+                    else if (C::RH && k < C::R_G) { if (a.hvv_pos[k - C::R_H] >= 0) hvals[a.hvv_pos[k - C::R_H]] = v; }
+                    else if (C::RG && k < C::R_O) grad[a.nvar - E::NV + (k - C::R_G)] = v;
+                    else if (C::RO && a.obj) a.obj[inst] = v;
+                }
+            }
+        };
         unsigned int& cta_ticket = *cta_ticket_p;
         const int nblk = a.ctas;
         double wv[NR];
@@ -585,75 +691,93 @@ __device__ __forceinline__ void publish_reduction(const EvalArgs& a, const doubl
             flag = (atomicAdd(&cta_ticket, 1u) == (unsigned int)(NW - 1));
         }
         flag = __shfl_sync(0xffffffffu, flag, 0);
-        if (flag) {
-            __threadfence_block();
-            double* part = a.partials + (inst * nblk) * NR;
-            if (lane < NR) {
-                double v = sred[lane];
-                for (int w = 1; w < NW; ++w) v = comb(lane, v, sred[w * NR + lane]);
-                part[(long long)cta * NR + lane] = v;
-                __threadfence();
-            }
-            __syncwarp();
-            unsigned int last = 0;
-            if (lane == 0) last = (atomicAdd(&a.counters[inst], 1u) == (unsigned int)(nblk - 1));
-            last = __shfl_sync(0xffffffffu, last, 0);
-            if (last) {
-                __threadfence();
-                double acc[NR];
+        if (!flag) return;
+        __threadfence_block();
+        double cv = 0.0;   // lane k < NR: slot k of this CTA
+        if (lane < NR) {
+            cv = sred[lane];
+            for (int w = 1; w < NW; ++w) cv = comb(lane, cv, sred[w * NR + lane]);
+        }
+        if (a.poll) {
+            RedRecord* rec = reinterpret_cast<RedRecord*>(a.partials) + (inst * nblk) * NR;
+            if (lane < NR) store_record(rec + (long long)cta * NR + lane, cv, a.key);
+            if (cta != 0) return;
+            // ---- collector: lane l takes the CTAs l, l + 32, ... in ascending order, U at a time (one memory
+            //      round trip per pass over the pending ones)
+            constexpr int U = NR <= 2 ? 8 : (NR <= 4 ? 4 : 2);
+            double acc[NR];
 #pragma unroll
-                for (int k = 0; k < NR; ++k) acc[k] = 0.0;
-                // 16 independent loads per lane in flight (one memory round trip per 512 partials)
-                for (int base = 0; base < nblk; base += 32 * 16) {
+            for (int k = 0; k < NR; ++k) acc[k] = 0.0;
+            for (int base = 0; base < nblk; base += 32 * U) {
+                double t[U][NR];
+                unsigned int pend = 0;
 #pragma unroll
-                    for (int k = 0; k < NR; ++k) {
-                        double t[16];
+                for (int u = 0; u < U; ++u) {
+                    if (base + u * 32 + lane < nblk) pend |= 1u << u;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int bb = base + j * 32 + lane;
-                            t[j] = bb < nblk ? __ldcg(&part[(long long)bb * NR + k]) : 0.0;
+                    for (int k = 0; k < NR; ++k) t[u][k] = 0.0;
+                }
+                while (pend) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (pend & (1u << u)) {
+                            const RedRecord* r = rec + (long long)(base + u * 32 + lane) * NR;
+                            bool ok = true;
+#pragma unroll
+                            for (int k = 0; k < NR; ++k) ok = load_record(r + k, a.key, t[u][k]) && ok;
+                            if (ok) pend &= ~(1u << u);
                         }
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) acc[k] = comb(k, acc[k], t[j]);
                     }
+                    if (pend) __nanosleep(40);
                 }
 #pragma unroll
                 for (int k = 0; k < NR; ++k) {
-                    double v = acc[k];
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) v = comb(k, v, __shfl_xor_sync(0xffffffffu, v, o));
-                    if (lane == 0) {
-                        if (C::WV && k == C::R_V) { if (a.viol) a.viol[inst] = v; }
-                        else if (C::WH && k < C::R_G) { if (a.hvv_pos[k - C::R_H] >= 0) hvals[a.hvv_pos[k - C::R_H]] = v; }
-                        else if (C::WG && k < C::R_O) grad[a.nvar - E::NV + (k - C::R_G)] = v;
-                        else if (C::WO && a.obj) a.obj[inst] = v;
-                    }
+                    for (int u = 0; u < U; ++u) acc[k] = comb(k, acc[k], t[u][k]);
                 }
-                if (lane == 0) a.counters[inst] = 0u;
             }
+            __syncwarp();
+            finish(acc);
+            return;
+        }
+        // ---- ticket mode
+        double* part = a.partials + (inst * nblk) * NR;
+        if (lane < NR) {
+            part[(long long)cta * NR + lane] = cv;
+            __threadfence();
+        }
+        __syncwarp();
+        unsigned int last = 0;
+        if (lane == 0) last = (atomicAdd(&a.counters[inst], 1u) == (unsigned int)(nblk - 1));
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            __threadfence();
+            double acc[NR];
+#pragma unroll
+            for (int k = 0; k < NR; ++k) acc[k] = 0.0;
+            // 16 independent loads per lane in flight (one memory round trip per 512 partials)
+            for (int base = 0; base < nblk; base += 32 * 16) {
+#pragma unroll
+                for (int k = 0; k < NR; ++k) {
+                    double t[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int bb = base + j * 32 + lane;
+                        t[j] = bb < nblk ? __ldcg(&part[(long long)bb * NR + k]) : 0.0;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[k] = comb(k, acc[k], t[j]);
+                }
+            }
+            finish(acc);
+            if (lane == 0) a.counters[inst] = 0u;
         }
     }
-}
-
-// Programmatic dependent launch: a launch made with the programmatic-stream-serialization attribute may
-// be scheduled while the previous kernel of the stream is still draining; `griddepcontrol.wait` blocks
-// until that kernel has completed and its memory is visible, so only launch latency and CTA scheduling
-// overlap -- results and the handle's scratch buffers are never touched early.
-#ifndef CTD_PDL
-#define CTD_PDL 1
-#endif
-__device__ __forceinline__ void pdl_entry() {
-#if CTD_PDL
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-#endif
 }
 
 template <class E, int F>
 __device__ __forceinline__ void eval_body(const EvalArgs& a) {
     using C = Cfg<E, F>;
-    constexpr int T = C::T;
-    pdl_entry();
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -663,7 +787,6 @@ __device__ __forceinline__ void eval_body(const EvalArgs& a) {
 
     const double* __restrict__ x = a.x + inst * a.x_stride;
     const double* __restrict__ y = a.y ? a.y + inst * a.y_stride : nullptr;
-    const double* __restrict__ p = a.params + inst * (E::NPAR > 0 ? E::NPAR : 1);
     double* c = C::WC ? a.c + inst * a.c_stride : nullptr;
     double* jvals = C::WJ ? a.jvals + inst * a.j_stride : nullptr;
     double* hvals = C::WH ? a.hvals + inst * a.h_stride : nullptr;
@@ -677,27 +800,59 @@ __device__ __forceinline__ void eval_body(const EvalArgs& a) {
         if (tid == 0) cta_ticket = 0u;
         __syncthreads();
     }
+    // the parameters of the instance live in registers: both phases (and the compiler's common
+    // subexpressions across them, e.g. Goddard's exp) see the same values instead of reloading them
+    double pr[E::NPAR > 0 ? E::NPAR : 1];
+    {
+        const double* __restrict__ pg = a.params + inst * (E::NPAR > 0 ? E::NPAR : 1);
+#pragma unroll
+        for (int k = 0; k < E::NPAR; ++k) pr[k] = __ldg(pg + k);
+    }
 
     CTD_STAMP(0);
     if (cta == 0) {
-        edge_cta<E, F>(a, x, y, p, c, jvals, hvals, grad, smem, red, nw);
+        edge_cta<E, F>(a, x, y, pr, c, jvals, hvals, grad, (C::WO && a.obj) ? a.obj + inst : nullptr, smem, red, nw);
         CTD_STAMP(4);
     } else {
-        const long long tile = (long long)(cta - 1) * nw + warp;
-        const long long i0 = 2 + tile * C::OWN;                       // first owned step / column block
-        const long long last = (long long)a.N - 1;                    // last regular column block
-        const long long left = last - i0 + 1;
-        const int nown = (int)(left < C::OWN ? (left < 0 ? 0 : left) : C::OWN);
-        const long long i = i0 - 1 + lane;                            // this thread's step
+        const int tile = (cta - 1) * nw + warp;
+        const int i0 = 2 + tile * C::OWN;                             // first owned step / column block
+        const int left = a.N - i0;                                    // owned blocks end with block N - 1
+        const int nown = left < C::OWN ? (left < 0 ? 0 : left) : C::OWN;
+        const int i = i0 - 1 + lane;                                  // this thread's step (lane 0: halo)
         const bool active = nown > 0 && lane <= nown;
         double* ws = smem + warp * C::WARP_DOUBLES;
+        const double* __restrict__ xs = x + (long long)(i - 1) * E::BLK;
+        const double* __restrict__ ys = (C::WH && y) ? y + (long long)(i - 1) * E::CB : nullptr;
+        // ---- before the grid dependency: normalized times of the step, L2 prefetch of the tile's inputs
+        double si = 0.0, sp = 0.0;
+        if (active) {
+            si = grid_point(a, i - 1);
+            sp = grid_point(a, i);
+            // one 128-byte line per lane and pass: lanes 0..15 walk the x range of the tile, 16..31 its y range
+            // (every address lies inside the range: a prefetch must not touch what may be unmapped)
+            const int half = lane & 15;
+            if (lane < 16) {
+                const int bytes = ((nown + 1) * E::BLK + E::NNEXT) * 8;
+                const char* b0 = reinterpret_cast<const char*>(x + (long long)(i0 - 2) * E::BLK);
+                for (int o = half * 128; o < bytes + 128; o += 16 * 128) prefetch_l2(b0 + (o < bytes - 8 ? o : bytes - 8));
+            } else if (C::WH && y) {
+                const int bytes = (nown + 1) * E::CB * 8;
+                const char* b0 = reinterpret_cast<const char*>(y + (long long)(i0 - 2) * E::CB);
+                for (int o = half * 128; o < bytes + 128; o += 16 * 128) prefetch_l2(b0 + (o < bytes - 8 ? o : bytes - 8));
+            }
+            if (lane == 0 && E::NV > 0) prefetch_l2(x + a.nvar - E::NV);
+        }
+        pdl_entry();
         double z[E::NZ], lam[E::CB];
         TimeArgs<E::NV> Tm;
         if (active) {
-            load_step<E>(x, a.nvar, i, z);
 #pragma unroll
-            for (int r = 0; r < E::CB; ++r) lam[r] = (C::WH && y) ? y[(i - 1) * E::CB + r] : 0.0;
-            time_args<E>(a, z + E::NOWN + E::NNEXT, p, i, Tm);
+            for (int k = 0; k < E::NOWN + E::NNEXT; ++k) z[k] = __ldg(xs + k);
+#pragma unroll
+            for (int k = 0; k < E::NV; ++k) z[E::NOWN + E::NNEXT + k] = __ldg(x + a.nvar - E::NV + k);
+#pragma unroll
+            for (int r = 0; r < E::CB; ++r) lam[r] = ys ? __ldg(ys + r) : 0.0;
+            time_args_s<E>(si, sp, z + E::NOWN + E::NNEXT, pr, Tm);
         }
 #ifdef CTD_TRACE
         if (active && Tm.hh == -1.2345) CTD_STAMP(7);   // forces the loads to have arrived
@@ -705,21 +860,21 @@ __device__ __forceinline__ void eval_body(const EvalArgs& a) {
 #endif
         if constexpr (C::GZ) {   // gradient entries of the owned column blocks: zeros (see Cfg::GZ)
             if (nown > 0) {
-                double* g0 = grad + (i0 - 1) * E::BLK;
+                double* g0 = grad + (long long)(i0 - 1) * E::BLK;
                 for (int k = lane; k < nown * E::BLK; k += 32) g0[k] = 0.0;
             }
         }
         if constexpr (C::PHASE_A)
-            tile_phase<E, F, C::WC, C::WJ, false, C::SG, C::WO>(a, ws, z, lam, Tm, p, red, lane, nown, i0, active, c,
+            tile_phase<E, F, C::WC, C::WJ, false, C::SG, C::WO>(a, ws, z, lam, Tm, pr, red, lane, nown, i0, active, c,
                                                                   jvals, hvals, grad);
         CTD_STAMP(2);
         if constexpr (C::PHASE_B) {
             if constexpr (C::PHASE_A) {   // phase B reuses the region: the copy engine must have read it
-                if (lane == 0) bulk_wait_read();
+                bulk_wait_read();         // (returns at once in the lanes that issued no copy)
                 __syncwarp();
             }
             CTD_STAMP(3);
-            tile_phase<E, F, false, false, true, false, false>(a, ws, z, lam, Tm, p, red, lane, nown, i0, active, c,
+            tile_phase<E, F, false, false, true, false, false>(a, ws, z, lam, Tm, pr, red, lane, nown, i0, active, c,
                                                                 jvals, hvals, grad);
         }
         CTD_STAMP(4);
@@ -728,7 +883,7 @@ __device__ __forceinline__ void eval_body(const EvalArgs& a) {
     // the partial sums are published while the copy engine is still draining the last phase
     publish_reduction<E, F>(a, red, smem + nw * C::WARP_DOUBLES, &cta_ticket, inst, cta, lane, warp, hvals, grad, nw);
     CTD_STAMP(5);
-    if (cta != 0 && lane == 0) bulk_wait_read();   // shared memory must outlive the copies that read it
+    if (cta != 0) bulk_wait_read();   // shared memory must outlive the copies that read it (no-op for lanes without copies)
     CTD_STAMP(6);
 }
 
@@ -847,12 +1002,12 @@ struct PartSink {
     template <int N> __device__ __forceinline__ void ho(double v) { if constexpr (WH && mine(PC::O_HO + N)) ho_[E::H_OWN(N, 2)] = v; }
     template <int N> __device__ __forceinline__ void hn(double v) { if constexpr (WH && mine(PC::O_HN + N)) hn_[N] = v; }
     template <int K> __device__ __forceinline__ void hv(double v) {
-        if constexpr (WH && mine(PC::O_HV + K)) red[C::R_H + K] += owner ? v : 0.0;
+        if constexpr (WH && C::RH && mine(PC::O_HV + K)) red[C::R_H + K] += owner ? v : 0.0;
     }
     template <int N> __device__ __forceinline__ void go(double v) { if constexpr (WG && mine(PC::O_GO + N)) go_[E::G_OWN(N, 2)] = v; }
     template <int N> __device__ __forceinline__ void gn(double v) { if constexpr (WG && mine(PC::O_GN + N)) gn_[N] = v; }
     template <int N> __device__ __forceinline__ void gv(double v) {
-        if constexpr (WG && mine(PC::O_GV + N)) red[C::R_G + E::G_V(N, 2)] += owner ? v : 0.0;
+        if constexpr (WG && C::RG && mine(PC::O_GV + N)) red[C::R_G + E::G_V(N, 2)] += owner ? v : 0.0;
     }
 };
 
@@ -882,7 +1037,7 @@ __device__ __forceinline__ void run_part(const EvalArgs& a, const double* z, con
         }
         if constexpr (S::WC || S::WJ || S::WH) E::template step<S::WC, S::WJ, S::WH>(z, Tm, p, lam, a.sigma, s);
         if constexpr (S::WG) E::grad_step(z, Tm, p, s);
-        if constexpr (PA && C::WO && PART == 0) { if (owner) red[C::R_O] += E::cost_step(z, Tm, p); }
+        if constexpr (PA && C::RO && PART == 0) { if (owner) red[C::R_O] += E::cost_step(z, Tm, p); }
     }
     __syncthreads();   // all owners have stored: the neighbours' contributions can be added
     if (active) {
@@ -912,7 +1067,6 @@ template <class E, int F>
 __global__ void __launch_bounds__(PCfg<E, F>::T, PCfg<E, F>::MINB) ctd_eval_kernel_parts(const EvalArgs a) {
     using C = Cfg<E, F>;
     using PC = PCfg<E, F>;
-    pdl_entry();
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -935,9 +1089,10 @@ __global__ void __launch_bounds__(PCfg<E, F>::T, PCfg<E, F>::MINB) ctd_eval_kern
     }
     CTD_STAMP(0);
     if (cta == 0) {
-        edge_cta<E, F>(a, x, y, p, c, jvals, hvals, grad, smem, red, PC::P);
+        edge_cta<E, F>(a, x, y, p, c, jvals, hvals, grad, (C::WO && a.obj) ? a.obj + inst : nullptr, smem, red, PC::P);
         CTD_STAMP(4);
     } else {
+        pdl_entry();
         const long long i0 = 2 + (long long)(cta - 1) * PC::OWN;
         const long long left = (long long)a.N - 1 - i0 + 1;
         const int nown = (int)(left < PC::OWN ? (left < 0 ? 0 : left) : PC::OWN);
@@ -976,24 +1131,30 @@ __global__ void __launch_bounds__(PCfg<E, F>::T, PCfg<E, F>::MINB) ctd_eval_kern
         if (active && Tm.hh == -1.2345) CTD_STAMP(7);   // forces the loads to have arrived
         CTD_STAMP(1);
 #endif
-        // hands the staged ranges of phase A and / or B to the copy engine (warp 0)
+        // hands the staged ranges of phase A and / or B to the copy engine (warp 0: the elected lane issues the
+        // bulk copies, lane 1 stores the ragged ends)
         auto store = [&](bool pa, bool pb) {
             if (warp == 0 && nown > 0) {
+                const bool leader = elect_one();
+                auto range = [&](double* g, double* s, int n) {
+                    if (leader) bulk_body(g, smem_u32(s), n);
+                    if (lane == 1) ragged_ends(g, s, n);
+                };
                 if (pa) {
-                    if constexpr (C::WC) bulk_store_range(gC, sC, nown * E::CB, lane);
+                    if constexpr (C::WC) range(gC, sC, nown * E::CB);
                     if constexpr (C::WJ) {
-                        bulk_store_range(gJ, sJ, nown * E::J_BLOCK, lane);
+                        range(gJ, sJ, nown * E::J_BLOCK);
                         if constexpr (C::NV > 0) {
 #pragma unroll
-                            for (int k = 0; k < C::NV; ++k) bulk_store_range(gJV[k], sJV[k], nown * E::JV_STRIDE, lane);
+                            for (int k = 0; k < C::NV; ++k) range(gJV[k], sJV[k], nown * E::JV_STRIDE);
                         }
                     }
-                    if constexpr (C::WG) bulk_store_range(gG, sG, nown * E::BLK, lane);
+                    if constexpr (C::WG) range(gG, sG, nown * E::BLK);
                 }
                 if (pb) {
-                    if constexpr (C::WH) bulk_store_range(gH, sH, nown * E::H_BLOCK, lane);
+                    if constexpr (C::WH) range(gH, sH, nown * E::H_BLOCK);
                 }
-                if (lane == 0) bulk_commit();
+                if (leader) bulk_commit();
             }
         };
         if constexpr (!PC::TWO) {
@@ -1010,7 +1171,7 @@ __global__ void __launch_bounds__(PCfg<E, F>::T, PCfg<E, F>::MINB) ctd_eval_kern
             store(true, false);
             CTD_STAMP(2);
             // phase B reuses the region: the copy engine must have read it
-            if (warp == 0 && lane == 0 && nown > 0) bulk_wait_read();
+            if (warp == 0 && nown > 0) bulk_wait_read();
             __syncthreads();
             CTD_STAMP(3);
             PartDispatch<E, F, 0, false, true>::run(warp, a, z, lam, Tm, p, red, active, owner, ob, nb, sC, sJ, sJV, sH, sG);
@@ -1018,7 +1179,7 @@ __global__ void __launch_bounds__(PCfg<E, F>::T, PCfg<E, F>::MINB) ctd_eval_kern
             __syncthreads();
             store(false, true);
         }
-        if (warp == 0 && lane == 0 && nown > 0) bulk_wait_read();   // shared memory must outlive the copies that read it
+        if (warp == 0 && nown > 0) bulk_wait_read();   // shared memory must outlive the copies that read it
         CTD_STAMP(4);
     }
     publish_reduction<E, F>(a, red, smem + PC::S_RED, &cta_ticket, inst, cta, lane, warp, hvals, grad, PC::P);

@@ -15,6 +15,9 @@
 
 #include "ctd_model.hpp"
 
+#include <mutex>
+#include <tuple>
+
 namespace ctd {
 
 #define CTD_CUDA(call)                                                                         \
@@ -94,6 +97,7 @@ Model::Model(const Registration& reg, int grid_size, const double* time_grid, in
     if (batch < 1) throw CtdError{-2, "batch must be >= 1"};
     if (batch > 65535) throw CtdError{-2, "batch must be <= 65535 (instances are the y dimension of the grid)"};
     if (f.nv > MAX_NV) throw CtdError{-2, "too many optimisation variables v for this build"};
+    if (const char* e = getenv("CTD_POLL_MAX_BATCH")) poll_max_batch_ = atoi(e);   // 0: ticketed reduction everywhere
     // DOCPtime: DOCP_data.jl:176-214
     if (!time_grid) {
         if (grid_size < 1) throw CtdError{-2, "grid_size must be >= 1"};
@@ -415,6 +419,13 @@ void Model::build_edge_tables() {
     add_range(hpos, hess_.colptr[std::min<int64_t>(first_tail_col, nvar_ - nv)], hess_.colptr[nvar_ - nv]);
     add_range(gpos, 0, std::min<int64_t>(B, nvar_ - nv));
     add_range(gpos, std::min<int64_t>(first_tail_col, nvar_ - nv), nvar_ - nv);
+    // Quantities no STEP contributes to are not summed over the grid (Cfg::RH / RG in ctd_kernels.cuh): the
+    // (v,v) Hessian entries and the v entries of the gradient then belong to the edge blocks (the boundary and
+    // final-path elements are the only writers; an entry nobody writes is a structural zero of the pattern)
+    const bool vv_edge = f.nh_vv_emit == 0, gv_edge = f.g_v.n == 0;
+    if (vv_edge)
+        for (int k = 0; k < nv * (nv + 1) / 2; ++k) if (hvv_pos_[k] >= 0) hpos.push_back(hvv_pos_[k]);
+    if (gv_edge) add_range(gpos, nvar_ - nv, nvar_);
     // v columns of the Jacobian: rows of the edge-owned steps, final path rows, boundary rows
     for (int k = 0; k < nv; ++k) {
         const int64_t col = nvar_ - nv + k;  // 0-based
@@ -493,7 +504,8 @@ void Model::build_edge_tables() {
             const int a = f.fp_h(n, 0), b = f.fp_h(n, 1), nl = f.fp_nloc - f.nv;
             if (a >= nl && b >= nl) {
                 const int ka = std::max(a, b) - nl, kb = std::min(a, b) - nl;
-                m[f.fp_j.n + n] = -2 - (ka * (ka + 1) / 2 + kb);
+                const int kk = ka * (ka + 1) / 2 + kb;
+                m[f.fp_j.n + n] = vv_edge ? slot_of(hpos, hvv_pos_[kk], ne_j_) : -2 - kk;
             } else {
                 const int64_t ga = fcol(a), gb = fcol(b);
                 m[f.fp_j.n + n] = slot_of(hpos, hess_.find(std::max(ga, gb), std::min(ga, gb)), ne_j_);
@@ -514,7 +526,8 @@ void Model::build_edge_tables() {
             const int a = f.bc_h(n, 0), b = f.bc_h(n, 1);
             if (a >= 2 * f.nx && b >= 2 * f.nx) {
                 const int ka = std::max(a, b) - 2 * f.nx, kb = std::min(a, b) - 2 * f.nx;
-                m[f.bc_j.n + n] = -2 - (ka * (ka + 1) / 2 + kb);
+                const int kk = ka * (ka + 1) / 2 + kb;
+                m[f.bc_j.n + n] = vv_edge ? slot_of(hpos, hvv_pos_[kk], ne_j_) : -2 - kk;
             } else {
                 const int64_t ga = bcol(a), gb = bcol(b);
                 m[f.bc_j.n + n] = slot_of(hpos, hess_.find(std::max(ga, gb), std::min(ga, gb)), ne_j_);
@@ -522,7 +535,7 @@ void Model::build_edge_tables() {
         }
         for (int n = 0; n < f.bc_g.n; ++n) {
             const int a = f.bc_g(n, 0);
-            if (a >= 2 * f.nx) m[f.bc_j.n + f.bc_h.n + n] = -2 - (a - 2 * f.nx);
+            if (a >= 2 * f.nx) m[f.bc_j.n + f.bc_h.n + n] = gv_edge ? slot_of(gpos, nvar_ - nv + (a - 2 * f.nx), ne_j_ + ne_h_) : -2 - (a - 2 * f.nx);
             else m[f.bc_j.n + f.bc_h.n + n] = slot_of(gpos, bcol(a) - 1, ne_j_ + ne_h_);
         }
     }
@@ -557,7 +570,9 @@ void Model::ensure_device() {
         max_ctas = std::max<int64_t>(max_ctas, tiles + 1);   // (one warp per CTA is the smallest launch configuration)
         if (q.p_threads > 0) max_ctas = std::max<int64_t>(max_ctas, ((N_ >= 3) ? ((int64_t)N_ - 2 + q.p_own - 1) / q.p_own : 0) + 1);
     }
-    CTD_CUDA(cudaMalloc(&d_partials_, sizeof(double) * (size_t)batch_ * max_ctas * max_nred));
+    // (x2: in collector mode a partial is a 16-byte self-validating record, see publish_reduction)
+    CTD_CUDA(cudaMalloc(&d_partials_, sizeof(double) * 2 * (size_t)batch_ * max_ctas * max_nred));
+    CTD_CUDA(cudaMemsetAsync(d_partials_, 0, sizeof(double) * 2 * (size_t)batch_ * max_ctas * max_nred, stream_));
     CTD_CUDA(cudaMalloc(&d_counters_, sizeof(unsigned int) * batch_));
     CTD_CUDA(cudaMemsetAsync(d_counters_, 0, sizeof(unsigned int) * batch_, stream_));
     CTD_CUDA(cudaMemcpyAsync(d_edge_map_, edge_map_.data(), sizeof(int) * edge_map_.size(), cudaMemcpyHostToDevice, stream_));
@@ -692,16 +707,40 @@ void Model::eval_dev(int flags, const double* x, const double* y, double sigma, 
     }
     // the edge CTA uses the same dynamic shared memory as its value buffer (its reduction scratch at
     // S_RED is only touched after the buffer has been scattered)
-    // (layers, position maps, then one staging block per step task)
-    const size_t edge_smem = sizeof(double) * (EDGE_LAYERS * ((size_t)ne_j_ + ne_h_ + ne_g_) + 2) + sizeof(int) * (edge_map_.size() + 2) +
-                             sizeof(double) * (size_t)ntask_ * (size_t)lc.map_step;
+    // (layers, position maps, one staging block per step task, destination positions)
+    const size_t ne_all = (size_t)ne_j_ + ne_h_ + ne_g_;
+    const size_t edge_smem = sizeof(double) * (EDGE_LAYERS * ne_all + 2) + sizeof(int) * (edge_map_.size() + 2) +
+                             sizeof(double) * (size_t)ntask_ * (size_t)lc.map_step + sizeof(long long) * (ne_all + 1);
     const size_t smem = std::max(tile_smem, edge_smem);
-    const int pkey = flags + 256 * parts;
-    auto it = prepared_.find(pkey);
-    if (it == prepared_.end() || it->second < smem) {
-        const int e = reg_.launcher.prepare(flags, smem, parts);
-        if (e != 0) throw CtdError{e, std::string("cudaFuncSetAttribute failed: ") + cudaGetErrorString((cudaError_t)e)};
-        prepared_[pkey] = smem;
+    // The dynamic shared-memory opt-in is an attribute of the KERNEL (per device, for the whole process), not
+    // of this handle: another handle on the same element may have raised it already, and lowering it would
+    // break that handle's launches.  It only ever grows, under a process-wide lock.
+    {
+        static std::mutex mu;
+        static std::map<std::tuple<int, const void*, int>, size_t> optin;   // (device, element, flag set) -> bytes
+        std::lock_guard<std::mutex> lock(mu);
+        size_t& cur = optin[std::make_tuple(device_, (const void*)reg_.launcher.launch, flags + 256 * parts)];
+        if (cur < smem) {
+            const int e = reg_.launcher.prepare(flags, smem, parts);
+            if (e != 0) throw CtdError{e, std::string("cudaFuncSetAttribute failed: ") + cudaGetErrorString((cudaError_t)e)};
+            cur = smem;
+        }
+    }
+    // collector mode for single instances (the reduction tail is on the critical path of the launch); a launch
+    // that is being captured into a CUDA graph would replay the same key, so it takes the ticketed reduction
+    a.poll = 0;
+    if (batch_ <= poll_max_batch_ && lc.nred > 0) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(stream_, &cs) != cudaSuccess) { cs = cudaStreamCaptureStatusActive; (void)cudaGetLastError(); }
+        if (cs == cudaStreamCaptureStatusNone) {
+            a.poll = 1;
+            uint64_t e = ++epoch_;   // splitmix64 finaliser: consecutive launches get unrelated keys; never 0
+            e += 0x9E3779B97F4A7C15ull;
+            e = (e ^ (e >> 30)) * 0xBF58476D1CE4E5B9ull;
+            e = (e ^ (e >> 27)) * 0x94D049BB133111EBull;
+            e ^= e >> 31;
+            a.key = e | 1ull;
+        }
     }
 #ifdef CTD_TRACE
     // debug builds only: per-warp timestamps of the launch, dumped as raw int64 to $CTD_TRACE_FILE

@@ -231,6 +231,9 @@ def emit_pair(ocp: OCP, scheme: str, pattern_mode: str = "reference") -> str:
     o.append(f"  static constexpr int NOWN = {L.n_own}, NNEXT = {L.n_next}, NZ = {L.nz};\n")
     o.append(f"  static constexpr int J_BLOCK = {E.j_block}, H_BLOCK = {E.h_block}, J_FIRST = {E.j_first}, H_FIRST = {E.h_first}, JV_STRIDE = {E.jv_stride};\n")
     o.append(f"  static constexpr int NH_VV_SLOTS = {d.nv * (d.nv + 1) // 2};\n")
+    # (v,v) Hessian terms / d cost / d v terms that a STEP emits: when there are none (autonomous dynamics with the
+    # free time entering only through h, Mayer cost) the kernels drop the grid-wide reduction of those slots
+    o.append(f"  static constexpr int NH_VV_EMIT = {len(E.h_vv)};\n")
     o.append(f"  static constexpr int FP_NLOC = {FP.nloc}, BC_NLOC = {BC.nloc};\n")
     o.append(f"  static constexpr int N_DROPPED = {len(E.dropped)};  // mathematically nonzero entries absent from the pattern\n")
     # tables: {local row / a, local col / b, slot}

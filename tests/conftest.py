@@ -43,10 +43,35 @@ def synthetic_point(model, seed=20261018, batch=1):
     return np.ascontiguousarray(x), np.ascontiguousarray(y)
 
 
+def column_scale(structure, ref, n, symmetric=False):
+    """Per-entry tolerance floor of SURVEY.md §7 for a sparse value array in COO form: the largest magnitude
+    in the entry's COLUMN (for the lower-triangular Hessian: in the row or column of the full symmetric
+    matrix that bears the entry's column index).  `structure` = (rows, cols), 1-based."""
+    rows, cols = structure
+    ref = np.abs(np.asarray(ref, dtype=np.float64))
+    cmax = np.zeros(n + 1)
+    np.maximum.at(cmax, cols, ref)
+    if symmetric:
+        np.maximum.at(cmax, rows, ref)
+        return np.maximum(cmax[cols], cmax[rows])
+    return cmax[cols]
+
+
+WORST = {}   # kind ("jac", "hess", ...) -> (largest pure relative error seen, where)
+
+
+def pytest_terminal_summary(terminalreporter):
+    if WORST:
+        terminalreporter.write_line("worst pure relative error |a-b|/max(|a|,|b|) over entries above 1e-300, by quantity:")
+        for kind in sorted(WORST):
+            terminalreporter.write_line(f"  {kind:10s} {WORST[kind][0]:.3e}   ({WORST[kind][1]})")
+
+
 def assert_close(a, b, scale=None, rtol=1e-12, what=""):
     """|a-b| <= rtol * max(|a|, |b|, scale): relative 1e-12 with a floor at the natural scale of the
     quantities that were combined (entries of the :manual pattern can be structurally present but
-    numerically zero or the result of cancellation)."""
+    numerically zero or the result of cancellation).  For Jacobian / Hessian values `scale` is the
+    per-entry column scale (column_scale above)."""
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     if a.size == b.size == 1:
@@ -55,9 +80,15 @@ def assert_close(a, b, scale=None, rtol=1e-12, what=""):
     if a.size == 0:
         return
     s = np.maximum(np.abs(a), np.abs(b))
+    err = np.abs(a - b)
+    big = s > 1e-300
+    if big.any() and what:
+        rel = float(np.max(err[big] / s[big]))
+        kind = what.split()[-1]
+        if rel > WORST.get(kind, (-1.0, ""))[0]:
+            WORST[kind] = (rel, what)
     if scale is not None:
         s = np.maximum(s, scale)
-    err = np.abs(a - b)
     bad = ~(err <= rtol * s)
     if bad.any():
         k = int(np.argmax(np.where(bad, err / np.maximum(s, 1e-300), 0)))

@@ -1,14 +1,16 @@
 """Parity of the CUDA path (through the C ABI) with the CPU oracle.  Run on a B200: pytest -m gpu.
 
 Tolerance (BASELINE.json north_star): indices bit-exact, values within 1e-12 relative.  `assert_close`
-uses |a-b| <= 1e-12 * max(|a|, |b|, scale) where `scale` is the magnitude of the quantities that were
-combined to form the entry (stated at each call)."""
+uses |a-b| <= 1e-12 * max(|a|, |b|, scale) where `scale` is, for Jacobian and Hessian values, the largest
+magnitude in the entry's COLUMN (entries of the :manual pattern can be structural zeros or
+the result of cancellation between terms of that size), for constraints the magnitude of x.  The largest
+PURE relative error met by every comparison is printed at the end of the run."""
 import os
 
 import numpy as np
 import pytest
 
-from conftest import assert_close, synthetic_point
+from conftest import assert_close, column_scale, synthetic_point
 
 pytestmark = pytest.mark.gpu
 
@@ -43,20 +45,20 @@ def test_all_models_small_grids(ctd, oracle_mod, N):
         g_ref, j_ref, h_ref = o.derivs(x, y, sigma)
         c_ref, f_ref = o.cons(x), o.obj(x)
         sx = max(1.0, float(np.abs(x).max()))
-        sj = max(1.0, float(np.abs(j_ref).max()))
-        sh = max(1e-300, float(np.abs(h_ref).max()))
+        sj = column_scale(nlp.jac_structure(), j_ref, d.nvar)
+        sh = column_scale(nlp.hess_structure(), h_ref, d.nvar, symmetric=True)
         sg = max(1.0, float(np.abs(g_ref).max()))
         # separate callbacks
         assert_close(nlp.cons(x), c_ref, scale=sx, rtol=RTOL, what=tag + " cons")
-        assert_close(nlp.jac_coord(x), j_ref, scale=sj * 1e-3, rtol=RTOL, what=tag + " jac")
-        assert_close(nlp.hess_coord(x, y, obj_weight=sigma), h_ref, scale=sh * 1e-3, rtol=RTOL, what=tag + " hess")
+        assert_close(nlp.jac_coord(x), j_ref, scale=sj, rtol=RTOL, what=tag + " jac")
+        assert_close(nlp.hess_coord(x, y, obj_weight=sigma), h_ref, scale=sh, rtol=RTOL, what=tag + " hess")
         assert_close(nlp.obj(x), f_ref, scale=1.0, rtol=RTOL, what=tag + " obj")
         assert_close(nlp.grad(x), g_ref, scale=sg * 1e-3, rtol=RTOL, what=tag + " grad")
         # fused launch gives the same numbers as the separate ones
         r = nlp.eval_all(x, y, obj_weight=sigma)
         assert_close(r["cons"], c_ref, scale=sx, rtol=RTOL, what=tag + " fused cons")
-        assert_close(r["jac"], j_ref, scale=sj * 1e-3, rtol=RTOL, what=tag + " fused jac")
-        assert_close(r["hess"], h_ref, scale=sh * 1e-3, rtol=RTOL, what=tag + " fused hess")
+        assert_close(r["jac"], j_ref, scale=sj, rtol=RTOL, what=tag + " fused jac")
+        assert_close(r["hess"], h_ref, scale=sh, rtol=RTOL, what=tag + " fused hess")
         assert_close(r["grad"], g_ref, scale=sg * 1e-3, rtol=RTOL, what=tag + " fused grad")
         assert_close(r["obj"], f_ref, scale=1.0, rtol=RTOL, what=tag + " fused obj")
 
@@ -68,8 +70,9 @@ def _compare_all(ctd, o, d, x, y, sigma, tag, rtol=RTOL):
     sx = max(1.0, float(np.abs(x).max()))
     r = nlp.eval_all(x, y, obj_weight=sigma)
     assert_close(r["cons"], c_ref, scale=sx, rtol=rtol, what=tag + " cons")
-    assert_close(r["jac"], j_ref, scale=1e-3 * max(1.0, float(np.abs(j_ref).max())), rtol=rtol, what=tag + " jac")
-    assert_close(r["hess"], h_ref, scale=1e-3 * max(1e-300, float(np.abs(h_ref).max())), rtol=rtol, what=tag + " hess")
+    assert_close(r["jac"], j_ref, scale=column_scale(nlp.jac_structure(), j_ref, d.nvar), rtol=rtol, what=tag + " jac")
+    assert_close(r["hess"], h_ref, scale=column_scale(nlp.hess_structure(), h_ref, d.nvar, symmetric=True), rtol=rtol,
+                 what=tag + " hess")
     assert_close(r["grad"], g_ref, scale=1e-3 * max(1.0, float(np.abs(g_ref).max())), rtol=rtol, what=tag + " grad")
     assert_close(r["obj"], f_ref, scale=1.0, rtol=rtol, what=tag + " obj")
     return r
@@ -92,7 +95,8 @@ def test_baseline_configs_full_size(ctd, oracle_mod, problem, scheme, N):
         nlp = d.nlp_model()
         h1 = nlp.hess_coord(x, y, obj_weight=0.25)
         h2 = nlp.hess_coord(x, 2.0 * y, obj_weight=0.5)
-        assert_close(h2, 2.0 * h1, scale=1e-3 * max(1e-300, float(np.abs(h1).max())), rtol=1e-13, what="hessian linearity")
+        assert_close(h2, 2.0 * h1, scale=column_scale(nlp.hess_structure(), h1, d.nvar, symmetric=True), rtol=1e-13,
+                     what="hessian linearity")
         r2 = nlp.eval_all(x, y, obj_weight=1.0)
         for k in ("cons", "jac", "hess", "grad", "obj"):
             assert np.array_equal(r[k], r2[k]), f"{k} not reproducible bit for bit"
@@ -154,8 +158,8 @@ def test_batched_instances_match_single_instance_oracles(ctd, oracle_mod):
             c = o.cons(x[b])
             tag = f"instance {b}/{B}"
             assert_close(r["cons"][b], c, scale=max(1.0, np.abs(x[b]).max()), what=tag + " cons")
-            assert_close(r["jac"][b], j, scale=1e-3 * np.abs(j).max(), what=tag + " jac")
-            assert_close(r["hess"][b], h, scale=1e-3 * np.abs(h).max(), what=tag + " hess")
+            assert_close(r["jac"][b], j, scale=column_scale(d.jacobian_structure(), j, d.nvar), what=tag + " jac")
+            assert_close(r["hess"][b], h, scale=column_scale(d.hessian_structure(), h, d.nvar, symmetric=True), what=tag + " hess")
             assert_close(r["grad"][b], g, scale=1e-3, what=tag + " grad")
             assert_close(r["obj"][b], o.obj(x[b]), scale=1.0, what=tag + " obj")
             assert_close(obj[b], o.obj(x[b]), scale=1.0, what=tag + " norms obj")
@@ -335,8 +339,8 @@ def test_wide_elements_on_large_grids_and_batches(ctd, oracle_mod):
         g, j, h = o.derivs(x[b], y[b], 1.0)
         c = o.cons(x[b])
         assert_close(r["cons"][b], c, scale=max(1.0, np.abs(x[b]).max()), what=f"b={b} cons")
-        assert_close(r["jac"][b], j, scale=1e-3 * np.abs(j).max(), what=f"b={b} jac")
-        assert_close(r["hess"][b], h, scale=1e-3 * np.abs(h).max(), what=f"b={b} hess")
+        assert_close(r["jac"][b], j, scale=column_scale(d.jacobian_structure(), j, d.nvar), what=f"b={b} jac")
+        assert_close(r["hess"][b], h, scale=column_scale(d.hessian_structure(), h, d.nvar, symmetric=True), what=f"b={b} hess")
         assert_close(viol[b], max(0.0, float(np.max(np.maximum(lcon - c, c - ucon)))), scale=max(1.0, np.abs(x[b]).max()),
                      what=f"b={b} violation (stand-alone norm kernel for wide elements)")
 
@@ -556,7 +560,8 @@ def test_cuda_path_against_committed_regression_vectors(ctd):
         r = d.evaluate(ctd.CONS | ctd.JAC | ctd.HESS | ctd.GRAD | ctd.OBJ, x, y, 0.75)
         xs = max(1.0, float(np.abs(x).max()))
         assert_close(r["cons"], z[tag + "|cons"], scale=xs, what=tag + " cons")
-        assert_close(r["jac"], z[tag + "|jac"], scale=1e-3 * float(np.abs(z[tag + "|jac"]).max()), what=tag + " jac")
-        assert_close(r["hess"], z[tag + "|hess"], scale=1e-3 * max(1e-300, float(np.abs(z[tag + "|hess"]).max())), what=tag + " hess")
+        assert_close(r["jac"], z[tag + "|jac"], scale=column_scale(d.jacobian_structure(), z[tag + "|jac"], d.nvar), what=tag + " jac")
+        assert_close(r["hess"], z[tag + "|hess"], scale=column_scale(d.hessian_structure(), z[tag + "|hess"], d.nvar, symmetric=True),
+                     what=tag + " hess")
         assert_close(r["grad"], z[tag + "|grad"], scale=1e-3, what=tag + " grad")
         assert_close(r["obj"], z[tag + "|obj"], scale=1.0, what=tag + " obj")
