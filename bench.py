@@ -3,18 +3,25 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-One "step" = one fused cons + Jacobian + Hessian evaluation (ctd_eval_dev, flags CONS|JAC|HESS) of the
-Goddard / midpoint / grid_size=1e5 DOCP on synthetic inputs resident in HBM.  With N > 1 ranks (torchrun)
-every rank evaluates its own instance (independent scenarios, no data-path collective): weak scaling,
-`value` = evaluations of all ranks / max-over-ranks device time.  The same JSON line carries
-  e2e           the same evaluation through the host-pointer C ABI call (ctd_eval) with pinned host buffers,
-                H2D of x,y and D2H of c, J values, H values inside the timed region;
+N = 1   metric "cons+Jacobian+Hessian evals/s @ grid 1e5": one step = one fused cons + Jacobian + Hessian
+        evaluation (ctd_eval_dev, flags CONS|JAC|HESS) of the Goddard / midpoint / grid_size=1e5 DOCP on synthetic
+        inputs resident in HBM.  `value` is what a solver's serially dependent callbacks see: ONE stream, launches
+        back to back.  The throughput with several independent evaluations in flight is reported as `overlapped`.
+N > 1   metric "batched evals/s": the 4096-instance Goddard MPC-scenario batch (grid_size=1000) sharded over the
+        ranks (strong scaling), objective + gradient + constraints + Jacobian + Hessian + violation norm in one
+        launch per rank and one all-gather of (objective, violation) per evaluation.  `value` is the best
+        schedule; the serialised and pipelined schedules are all listed under `batched`.
+The same JSON line carries
+  e2e           the same step through the host-pointer C ABI with pinned host buffers, host<->device copies inside
+                the timed region;
   roofline      algorithmic bytes / measured launch time against the measured HBM copy bandwidth;
-  cpu_baseline  the CPU oracle port (oracle/, test infrastructure) timed on the host cores;
-  batched       the 4096-instance Goddard MPC-scenario batch (grid_size=1000) sharded over the ranks with
-                one NCCL all-gather of (objective, violation) per evaluation.
-`--impl reference` times the CPU port of the reference's algorithm instead (the reference itself is Julia
-and cannot run in this image).
+  configs       (N = 1) one-stream time and HBM fraction of the other BASELINE configurations (3-stage IRK, both
+                variants, at grid 2e4; robot arm / trapeze at grid 1e5);
+  separate_callbacks_us  (N = 1) cons, jac_coord, hess_coord as separate launches against the fused one;
+  cpu_baseline  (N = 1) the CPU oracle port (oracle/, test infrastructure) timed on the host cores;
+  batched       the 4096-instance configuration (at N = 1 on one GPU).
+`--impl reference` times the CPU port of the reference's algorithm instead (the reference itself is Julia and
+cannot run in this image).
 """
 from __future__ import annotations
 
@@ -34,6 +41,12 @@ PROBLEM, SCHEME, GRID = "goddard", "midpoint", 100_000
 B_TOTAL, B_GRID = 4096, 1000
 SEED = 20261018
 METRIC = "cons+Jacobian+Hessian evals/s @ grid 1e5"
+METRIC_BATCHED = "batched evals/s (4096-instance Goddard MPC batch, grid 1000, sharded over the GPUs)"
+OTHER_CONFIGS = (   # BASELINE.json configs 3 (both variants) and 4
+    ("cfg3_gl3_constant_control", "goddard", "gauss_legendre_3_constant_control", 20_000),
+    ("cfg3_gl3_stagewise", "goddard", "gauss_legendre_3", 20_000),
+    ("cfg4_robot_trapeze", "robot", "trapeze", 100_000),
+)
 
 
 def synthetic_point(x0, ncon, seed, batch=1):
@@ -52,6 +65,15 @@ def measured_peak():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def measured_traffic(key):
+    """DRAM bytes per launch from the committed ncu capture (profiles/traffic.json: how it was taken is in the file)."""
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(tp)).get(key)
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -108,9 +130,9 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------
-def cpu_fused_eval_time(orc_mod, n_threads, budget_s, min_reps=2):
-    """Time one fused cons + Jacobian + Hessian evaluation of the CPU oracle at the bench workload."""
-    o = orc_mod.OracleModel(PROBLEM, SCHEME, GRID)
+def cpu_fused_eval_time(orc_mod, n_threads, budget_s, problem=PROBLEM, scheme=SCHEME, grid=GRID, min_reps=2):
+    """Time one fused cons + Jacobian + Hessian evaluation of the CPU oracle."""
+    o = orc_mod.OracleModel(problem, scheme, grid)
     x, y = synthetic_point(o.x0(), o.ncon, SEED)
     x, y = x[0], y[0]
     used = orc_mod.set_threads(n_threads)
@@ -130,41 +152,82 @@ def cpu_fused_eval_time(orc_mod, n_threads, budget_s, min_reps=2):
 
 
 def workload_text(nvar, ncon, nnzj, nnzh):
-    """`config.workload`, identical in both arms."""
+    """`config.workload` at N = 1, identical in both arms."""
     return (f"{PROBLEM}/{SCHEME}/grid_size={GRID}: fused cons+jac+hess, :manual pattern, "
-            f"nvar={nvar} ncon={ncon} nnzj={nnzj} nnzh={nnzh}; one instance per GPU")
+            f"nvar={nvar} ncon={ncon} nnzj={nnzj} nnzh={nnzh}; single-GPU NLP callback evaluation")
 
 
-def run_reference(args, rank):
+def batched_workload_text(world):
+    """`config.workload` at N > 1, identical in both arms."""
+    return (f"{B_TOTAL} {PROBLEM}/{SCHEME} MPC-scenario instances (Tmax in [1, 3.5]), grid_size={B_GRID}, "
+            f"{B_TOTAL // world} per GPU on {world} GPUs: obj+grad+cons+jac+hess + violation norm per instance, "
+            f"all-gather of (objective, violation)")
+
+
+def run_reference(args, rank, world):
     """--impl reference: the CPU port of the reference's algorithm on the host cores (rank 0 only)."""
     if rank != 0:
         return
     from oracle import oracle as orc
     orc.build()
     ncores = os.cpu_count() or 1
-    o = orc.OracleModel(PROBLEM, SCHEME, GRID)
-    x, y = synthetic_point(o.x0(), o.ncon, SEED)
-    x, y = x[0], y[0]
     used = orc.set_threads(ncores)
-    for _ in range(max(args.warmup, 1)):
-        o.cons(x)
-        o.derivs(x, y, 1.0, want=("jac", "hess"))
-    steps = max(1, min(args.steps, 50))
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        o.cons(x)
-        o.derivs(x, y, 1.0, want=("jac", "hess"))
-    el = time.perf_counter() - t0
-    val = steps / el
+    note = ("CPU port of the reference algorithm (oracle/): the reference is Julia + ADNLPModels and cannot run in "
+            "this image; derivatives by element-wise second-order forward AD, OpenMP")
+    if world == 1:
+        o = orc.OracleModel(PROBLEM, SCHEME, GRID)
+        x, y = synthetic_point(o.x0(), o.ncon, SEED)
+        x, y = x[0], y[0]
+        for _ in range(max(args.warmup, 1)):
+            o.cons(x)
+            o.derivs(x, y, 1.0, want=("jac", "hess"))
+        steps = max(1, min(args.steps, 50))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            o.cons(x)
+            o.derivs(x, y, 1.0, want=("jac", "hess"))
+        el = time.perf_counter() - t0
+        val, ms = steps / el, 1e3 * el / steps
+        metric, scaling = METRIC, "weak"
+        workload = workload_text(o.nvar, o.ncon, o.nnzj, o.nnzh)
+        sample = f"{steps} fused evaluations of the full workload"
+    else:
+        # one step = a bounded SAMPLE of the batch (SAMPLE instances, all outputs); a batched evaluation is
+        # B_TOTAL / SAMPLE such samples
+        SAMPLE = 64
+        rng = np.random.default_rng(SEED + 17)
+        tmax = rng.uniform(1.0, 3.5, size=B_TOTAL)
+        models = []
+        for b in range(SAMPLE):
+            o = orc.OracleModel(PROBLEM, SCHEME, B_GRID, params=[310.0, 500.0, 2.0, float(tmax[b])])
+            xb, yb = synthetic_point(o.x0(), o.ncon, SEED + 99 + b)
+            models.append((o, xb[0], yb[0]))
+
+        def sample_once():
+            for o, xb, yb in models:
+                o.obj(xb)
+                o.cons(xb)
+                o.derivs(xb, yb, 1.0, want=("grad", "jac", "hess"))
+
+        for _ in range(max(args.warmup, 1)):
+            sample_once()
+        steps = max(1, min(args.steps, 20))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            sample_once()
+        el = time.perf_counter() - t0
+        per_batched_eval = (el / steps) * (B_TOTAL / SAMPLE)
+        val, ms = 1.0 / per_batched_eval, 1e3 * per_batched_eval
+        metric, scaling = METRIC_BATCHED, "strong"
+        workload = batched_workload_text(world)
+        sample = (f"{steps} passes over {SAMPLE} of the {B_TOTAL} instances (all outputs), scaled by {B_TOTAL // SAMPLE} "
+                  "to one batched evaluation; the host has one socket, so the figure does not change with --gpus")
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": "evals/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * el / steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_text(o.nvar, o.ncon, o.nnzj, o.nnzh),
-                   "note": "CPU port of the reference algorithm (oracle/): the reference is Julia + ADNLPModels and "
-                           "cannot run in this image; derivatives by element-wise second-order forward AD, OpenMP"},
-        "cpu_baseline": {"value": val, "unit": "evals/s", "cores": used, "kind": "port",
-                         "sample": f"{steps} fused evaluations of the full workload"},
+        "impl": "reference", "metric": metric, "value": val, "unit": "evals/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload, "note": note},
+        "cpu_baseline": {"value": val, "unit": "evals/s", "cores": used, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -195,163 +258,160 @@ def _emit(line: dict):
         sys.stdout.flush()
 
 
-def main():
-    _quiet_stdout()
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--impl", default="b200")
-    ap.add_argument("--streams", type=int, default=3, help="independent evaluation streams in flight")
-    ap.add_argument("--no-batched", action="store_true")
-    ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
-    args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference":
-        run_reference(args, rank)
-        return 0
-    if args.warmup < 3:
-        args.warmup = 3
+class Ctx:
+    """torch / torch.distributed plumbing shared by the legs."""
 
-    import torch
-    import torch.distributed as dist
-    import ctdirect_b200 as ctd
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.numa = None
+        if self.world > 1 and not os.environ.get("CTD_BENCH_NO_NUMA"):
+            # one process per GPU: sit on the GPU's NUMA node before any pinned buffer is allocated
+            from ctdirect_b200.batch import bind_to_gpu_numa_node
+            self.numa = bind_to_gpu_numa_node(self.local_rank)
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+                os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line
+            os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")   # the gather's CTAs go ahead of queued evaluation CTAs
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.peak, self.peak_src = measured_peak()
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU port")
-    numa = None
-    if world > 1 and not os.environ.get("CTD_BENCH_NO_NUMA"):   # one process per GPU: sit on the GPU's NUMA node before any pinned buffer is allocated
-        from ctdirect_b200.batch import bind_to_gpu_numa_node
-        numa = bind_to_gpu_numa_node(local_rank)
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line
-        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")   # the gather's CTAs go ahead of queued evaluation CTAs
-        dist.init_process_group("nccl", device_id=dev)
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    def max_over_ranks(self, v):
+        if self.world > 1:
+            t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
             return float(t.item())
-        return ms
+        return v
 
-    FLAGS = ctd.CONS | ctd.JAC | ctd.HESS
-    # Evaluations are independent of each other (MPC scenarios, trial points): they are issued round-robin
-    # on NSTREAMS handles, each with its own CUDA stream, so that the launch latency and the tail of one
-    # evaluation overlap the body of the next.  The single-stream figure is reported beside it.
-    NSTREAMS = max(1, args.streams)
-    docps = [ctd.DOCP(PROBLEM, GRID, SCHEME, device=local_rank) for _ in range(NSTREAMS)]
-    docp = docps[0]
-    nlp = docp.nlp_model()
-    nvar, ncon, nnzj, nnzh = docp.nvar, docp.ncon, docp.nnzj, docp.nnzh
-    alg_bytes = 8 * (nvar + 2 * ncon + nnzj + nnzh)
-    streams = [torch.cuda.ExternalStream(d.cuda_stream, device=dev) for d in docps]
-    stream = streams[0]
-    # rotating buffer sets so that consecutive evaluations do not find their lines in the 126 MB L2
-    nsets = max(3, int(np.ceil(1.5 * 126e6 / alg_bytes)))
-    nsets = ((nsets + NSTREAMS - 1) // NSTREAMS) * NSTREAMS
-    xh, yh = synthetic_point(nlp.meta.x0, ncon, SEED + rank)
-    sets = []
-    for s in range(nsets):
-        xs, ys = synthetic_point(nlp.meta.x0, ncon, SEED + 1000 * s + rank)
-        sets.append({
-            "x": torch.from_numpy(xs[0]).to(dev), "y": torch.from_numpy(ys[0]).to(dev),
-            "out": {"cons": torch.empty(ncon, dtype=torch.float64, device=dev),
-                    "jac": torch.empty(nnzj, dtype=torch.float64, device=dev),
-                    "hess": torch.empty(nnzh, dtype=torch.float64, device=dev)},
-        })
-    torch.cuda.synchronize()
-    # buffer set k is always evaluated by handle k % NSTREAMS
-    calls = [docps[k % NSTREAMS].bind(FLAGS, s["x"], s["y"], 1.0, out=s["out"])[0] for k, s in enumerate(sets)]
-    calls1 = [docp.bind(FLAGS, s["x"], s["y"], 1.0, out=s["out"])[0] for s in sets]
-
-    REPEATS = 5
-
-    def timed(call_list, used_streams, steps, warmup):
-        """REPEATS timed regions of exactly `steps` evaluations each (barrier + synchronize on both sides of
-        every region); returns the per-region times (ms, this rank) and the launches of one region.  A region
-        of 100 evaluations lasts under a millisecond, so a single region is at the mercy of one host hiccup
-        on any rank: the reported figure is the median region of the max over ranks."""
-        for i in range(warmup):
-            call_list[i % nsets]()
-        regions, launches = [], 0
-        for _ in range(REPEATS):
-            barrier()
-            l0 = sum(d.launch_count for d in docps)
-            ev0 = [torch.cuda.Event(enable_timing=True) for _ in used_streams]
-            ev1 = [torch.cuda.Event(enable_timing=True) for _ in used_streams]
-            for e, st in zip(ev0, used_streams):
-                e.record(st)
-            for i in range(steps):
-                call_list[i % nsets]()
-            for e, st in zip(ev1, used_streams):
-                e.record(st)
-            barrier()
-            # every stream starts at the barrier; the region ends when the last stream finishes
-            regions.append(max(a.elapsed_time(b) for a, b in zip(ev0, ev1)))
-            launches = sum(d.launch_count for d in docps) - l0
-        return regions, launches
-
-    def regions_over_ranks(regions):
+    def regions_over_ranks(self, regions):
         """max over ranks of every region -> (median region, all regions)"""
-        t = torch.tensor(regions, dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor(regions, dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         r = sorted(t.tolist())
         return r[len(r) // 2], r
 
-    sampler = ClockSampler(local_rank)
-    # (1) single stream: the kernel timed back to back on its own -> roofline of the kernel
-    reg1_local, _ = timed(calls1, [stream], args.steps, args.warmup)
-    # (2) NSTREAMS handles in flight -> whole-job throughput (`value`)
-    sampler.start()
-    reg_local, launches = timed(calls, streams, args.steps, args.warmup)
-    ms, regions = regions_over_ranks(reg_local)
-    ms1, regions1 = regions_over_ranks(reg1_local)
-    ms_local = sorted(reg_local)[len(reg_local) // 2]
-    ms1_local = sorted(reg1_local)[len(reg1_local) // 2]
-    value = world * args.steps / (ms * 1e-3)
-    peak, peak_src = measured_peak()
-    launch_s = ms1_local * 1e-3 / args.steps
-    achieved = alg_bytes / launch_s / 1e9
-    achieved_ov = alg_bytes / (ms_local * 1e-3 / args.steps) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "ctd_eval_kernel_light<E_goddard__midpoint, CONS|JAC|HESS>",
-                "algorithmic_bytes_per_launch": alg_bytes, "launch_us": launch_s * 1e6, "peak_source": peak_src,
-                "how": "one stream, launches back to back, CUDA events over the timed region / steps",
-                "overlapped": {"streams": NSTREAMS, "achieved": achieved_ov, "frac": achieved_ov / peak,
-                               "us_per_eval": ms_local * 1e3 / args.steps,
-                               "how": "same kernel, evaluations issued round-robin on independent streams"}}
-    single_stream = {"value": world * args.steps / (ms1 * 1e-3), "unit": "evals/s", "ms_per_step": ms1 / args.steps}
 
-    # ---- e2e: host buffers through the host-pointer C ABI (H2D + kernel + D2H every step).
-    # The evaluations are independent, so NSTREAMS of them are kept in flight (ctd_eval_async on one handle
-    # each, ctd_sync before a handle's buffers are reused): the H2D, kernel and D2H stages of consecutive
-    # evaluations overlap on the full-duplex link.  The strictly synchronous figure is reported beside it.
-    e2e = None
+def timed_regions(cx, call_list, used_streams, steps, warmup, repeats, launch_counters=()):
+    """`repeats` timed regions of exactly `steps` calls each (barrier + synchronize on both sides of every region,
+    CUDA events on the streams the kernels are launched on); returns the per-region times (ms, this rank) and the
+    launches of one region.  A region of a few hundred evaluations lasts milliseconds, so a single region is at the
+    mercy of one host hiccup on any rank: the reported figure is the median region of the max over ranks."""
+    torch = cx.torch
+    n = len(call_list)
+    for i in range(warmup):
+        call_list[i % n]()
+    regions, launches = [], 0
+    for _ in range(repeats):
+        cx.barrier()
+        l0 = sum(d.launch_count for d in launch_counters)
+        ev0 = [torch.cuda.Event(enable_timing=True) for _ in used_streams]
+        ev1 = [torch.cuda.Event(enable_timing=True) for _ in used_streams]
+        for e, st in zip(ev0, used_streams):
+            e.record(st)
+        for i in range(steps):
+            call_list[i % n]()
+        for e, st in zip(ev1, used_streams):
+            e.record(st)
+        cx.barrier()
+        # every stream starts at the barrier; the region ends when the last stream finishes
+        regions.append(max(a.elapsed_time(b) for a, b in zip(ev0, ev1)))
+        launches = sum(d.launch_count for d in launch_counters) - l0
+    return regions, launches
+
+
+def rotating_sets(cx, ctd, docp, flags, seed0, min_bytes=1.5 * 126e6, multiple=1):
+    """Input / output buffer sets such that consecutive evaluations do not find their lines in the 126 MB L2."""
+    torch = cx.torch
+    alg_bytes = 8 * (docp.nvar + 2 * docp.ncon + docp.nnzj + docp.nnzh)
+    nsets = max(3, int(np.ceil(min_bytes / alg_bytes)))
+    nsets = ((nsets + multiple - 1) // multiple) * multiple
+    x0 = docp.initial_guess()
+    sets = []
+    for s in range(nsets):
+        xs, ys = synthetic_point(x0, docp.ncon, seed0 + 1000 * s + cx.rank)
+        sets.append({"x": torch.from_numpy(xs[0]).to(cx.dev), "y": torch.from_numpy(ys[0]).to(cx.dev),
+                     "out": {"cons": torch.empty(docp.ncon, dtype=torch.float64, device=cx.dev),
+                             "jac": torch.empty(docp.nnzj, dtype=torch.float64, device=cx.dev),
+                             "hess": torch.empty(docp.nnzh, dtype=torch.float64, device=cx.dev)}})
+    torch.cuda.synchronize()
+    return sets, alg_bytes
+
+
+# ---------------------------------------------------------------------------------------------------
+def leg_single(cx, ctd, sampler):
+    """N = 1 headline: the fused evaluation at grid 1e5 on one stream, and with NSTREAMS evaluations in flight."""
+    torch, args = cx.torch, cx.args
+    FLAGS = ctd.CONS | ctd.JAC | ctd.HESS
+    NS = max(1, args.streams)
+    docps = [ctd.DOCP(PROBLEM, GRID, SCHEME, device=cx.local_rank, stream="own") for _ in range(NS)]
+    docp = docps[0]
+    nvar, ncon, nnzj, nnzh = docp.nvar, docp.ncon, docp.nnzj, docp.nnzh
+    streams = [torch.cuda.ExternalStream(d.cuda_stream, device=cx.dev) for d in docps]
+    sets, alg_bytes = rotating_sets(cx, ctd, docp, FLAGS, SEED, multiple=NS)
+    nsets = len(sets)
+    calls_ov = [docps[k % NS].bind(FLAGS, s["x"], s["y"], 1.0, out=s["out"])[0] for k, s in enumerate(sets)]
+    calls_1 = [docp.bind(FLAGS, s["x"], s["y"], 1.0, out=s["out"])[0] for s in sets]
+    REPEATS = 5
+    sampler.start()
+    reg1, launches = timed_regions(cx, calls_1, [streams[0]], args.steps, args.warmup, REPEATS, [docp])
+    sampler.stop()
+    reg_ov, _ = timed_regions(cx, calls_ov, streams, args.steps, args.warmup, REPEATS, docps)
+    ms1, regions1 = cx.regions_over_ranks(reg1)
+    ms_ov, regions_ov = cx.regions_over_ranks(reg_ov)
+    launch_s = ms1 * 1e-3 / args.steps
+    achieved = alg_bytes / launch_s / 1e9
+    ach_ov = alg_bytes / (ms_ov * 1e-3 / args.steps) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": cx.peak, "unit": "GB/s", "frac": achieved / cx.peak,
+                "traffic": measured_traffic("dram_bytes_per_launch"),
+                "traffic_how": measured_traffic("how"),
+                "kernel": "ctd_eval_kernel_light<E_goddard__midpoint, CONS|JAC|HESS>",
+                "algorithmic_bytes_per_launch": alg_bytes, "launch_us": launch_s * 1e6, "peak_source": cx.peak_src,
+                "how": "one stream, launches back to back (programmatic dependent launch), CUDA events over the timed region / steps",
+                "overlapped": {"streams": NS, "achieved": ach_ov, "frac": ach_ov / cx.peak,
+                               "us_per_eval": ms_ov * 1e3 / args.steps,
+                               "how": "same kernel, evaluations issued round-robin on independent streams"}}
+    res = {
+        "value": args.steps / (ms1 * 1e-3), "ms_per_step": ms1 / args.steps, "region_ms": regions1, "launches": int(launches),
+        "overlapped": {"value": args.steps / (ms_ov * 1e-3), "unit": "evals/s", "ms_per_step": ms_ov / args.steps,
+                       "streams": NS, "region_ms": regions_ov,
+                       "what": f"{NS} independent evaluations in flight (one handle + CUDA stream each): MPC scenarios / trial points"},
+        "roofline": roofline, "dims": (nvar, ncon, nnzj, nnzh), "nsets": nsets, "alg_bytes": alg_bytes, "repeats": REPEATS,
+    }
+
+    # ---- separate callbacks (cons, jac_coord, hess_coord as three launches, what an Ipopt iteration issues) against
+    #      the fused launch
+    sep = {}
+    K = max(50, min(args.steps, 500))
+    for name, fl in (("cons", ctd.CONS), ("jac_coord", ctd.JAC), ("hess_coord", ctd.HESS)):
+        calls = [docp.bind(fl, s["x"], s["y"], 1.0, out={k: v for k, v in s["out"].items()})[0] for s in sets]
+        r, _ = timed_regions(cx, calls, [streams[0]], K, 10, 3)
+        sep[name] = sorted(r)[1] * 1e3 / K
+    sep["sum_of_three"] = sep["cons"] + sep["jac_coord"] + sep["hess_coord"]
+    sep["fused"] = launch_s * 1e6
+    sep["note"] = ("an NLPModels solver passes its own output buffer to every callback, so results of a fused launch "
+                   "kept by the handle would have to be copied into it: a device copy of the 19 MB of Jacobian values "
+                   "costs as much as recomputing them (DESIGN.md, 'separate callbacks')")
+    res["separate_callbacks_us"] = sep
+
+    # ---- e2e: host buffers through the host-pointer C ABI (H2D + kernel + D2H every step)
     if not args.no_e2e:
         pin = lambda n: torch.empty(n, dtype=torch.float64).pin_memory()
+        xh, yh = synthetic_point(docp.initial_guess(), ncon, SEED + cx.rank)
         hsets = []
-        for k in range(NSTREAMS):
+        for k in range(NS):
             hx, hy = pin(nvar), pin(ncon)
             hx.numpy()[:] = xh[0]
             hy.numpy()[:] = yh[0]
@@ -359,178 +419,329 @@ def main():
             hsets.append((hx, hy, hout))
         sync_call = docp.bind(FLAGS, hsets[0][0].numpy(), hsets[0][1].numpy(), 1.0, out=hsets[0][2])[0]
         async_calls = [docps[k].bind(FLAGS, hsets[k][0].numpy(), hsets[k][1].numpy(), 1.0, out=hsets[k][2], wait=False)[0]
-                       for k in range(NSTREAMS)]
+                       for k in range(NS)]
         e2e_steps = max(3, min(args.steps, 300))
         for _ in range(3):
             sync_call()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            sync_call()   # synchronous: returns with results on the host
-        el_sync = time.perf_counter() - t0
+
+        def sync_region():
+            cx.barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                sync_call()   # synchronous: returns with results on the host
+            return cx.max_over_ranks((time.perf_counter() - t0) * 1e3) * 1e-3
+
         def pipelined_region():
-            barrier()
+            cx.barrier()
             t0 = time.perf_counter()
             for i in range(e2e_steps):
-                k = i % NSTREAMS
-                if i >= NSTREAMS:
-                    docps[k].synchronize()          # results of evaluation i - NSTREAMS are on the host
+                k = i % NS
+                if i >= NS:
+                    docps[k].synchronize()          # results of evaluation i - NS are on the host
                 async_calls[k]()
             for d_ in docps:
                 d_.synchronize()
-            return max_over_ranks((time.perf_counter() - t0) * 1e3) * 1e-3
+            return cx.max_over_ranks((time.perf_counter() - t0) * 1e3) * 1e-3
 
-        el_pipe = sorted(pipelined_region() for _ in range(3))[1]   # median of 3 regions (wall clock is noisy)
-        el_sync = max_over_ranks(el_sync * 1e3) * 1e-3
-        legs = {"pipelined": {"value": world * e2e_steps / el_pipe, "ms_per_step": 1e3 * el_pipe / e2e_steps,
-                              "api": f"ctd_eval_async (host pointers, pinned buffers), {NSTREAMS} evaluations in flight"},
-                "synchronous": {"value": world * e2e_steps / el_sync, "ms_per_step": 1e3 * el_sync / e2e_steps,
-                                "api": "ctd_eval: one blocking call per evaluation"}}
-        best = max(legs, key=lambda k_: legs[k_]["value"])
-        # both legs move the same bytes over PCIe (the D2H of 42 MB bounds them); the headline is the faster one
-        e2e = {"value": legs[best]["value"], "unit": "evals/s", "h2d_bytes_per_step": 8 * (nvar + ncon),
-               "d2h_bytes_per_step": 8 * (ncon + nnzj + nnzh), "steps": e2e_steps,
-               "ms_per_step": legs[best]["ms_per_step"], "api": legs[best]["api"] + ", wall clock", "mode": best,
-               "pipelined": legs["pipelined"], "synchronous": legs["synchronous"]}
-    sampler.stop()
+        el_sync = sorted(sync_region() for _ in range(3))[1]      # median of 3 regions (wall clock is noisy)
+        el_pipe = sorted(pipelined_region() for _ in range(3))[1]
+        legs = {"synchronous": {"value": e2e_steps / el_sync, "ms_per_step": 1e3 * el_sync / e2e_steps,
+                                "api": "ctd_eval: one blocking call per evaluation (what a solver's serial callbacks see)"},
+                "pipelined": {"value": e2e_steps / el_pipe, "ms_per_step": 1e3 * el_pipe / e2e_steps,
+                              "api": f"ctd_eval_async (host pointers, pinned buffers), {NS} evaluations in flight"}}
+        # like `value`, the headline is the serially dependent (synchronous) call; the pipelined leg is beside it
+        res["e2e"] = {"value": legs["synchronous"]["value"], "unit": "evals/s", "h2d_bytes_per_step": 8 * (nvar + ncon),
+                      "d2h_bytes_per_step": 8 * (ncon + nnzj + nnzh), "steps": e2e_steps,
+                      "ms_per_step": legs["synchronous"]["ms_per_step"], "mode": "synchronous",
+                      "api": legs["synchronous"]["api"] + ", wall clock", "synchronous": legs["synchronous"],
+                      "pipelined": legs["pipelined"]}
+    return res
 
-    # ---- batched MPC scenarios: 4096 instances of grid 1000 sharded over the ranks
-    batched = None
-    if not args.no_batched:
-        bl = B_TOTAL // world
-        rng = np.random.default_rng(SEED + 17)
-        tmax = rng.uniform(1.0, 3.5, size=B_TOTAL)          # continuation range test_initial_guess.jl:242
-        par = np.tile(np.array([310.0, 500.0, 2.0, 3.5]), (B_TOTAL, 1))
-        par[:, 3] = tmax
-        par = par[rank * bl:(rank + 1) * bl]
-        bd = ctd.DOCP(PROBLEM, B_GRID, SCHEME, params=par, batch=bl, device=local_rank)
-        bx, by = synthetic_point(bd.initial_guess(), bd.ncon, SEED + 99 + rank, batch=bl)
-        tx, ty = torch.from_numpy(bx).to(dev), torch.from_numpy(by).to(dev)
-        bout = {"cons": torch.empty((bl, bd.ncon), dtype=torch.float64, device=dev),
-                "jac": torch.empty((bl, bd.nnzj), dtype=torch.float64, device=dev),
-                "hess": torch.empty((bl, bd.nnzh), dtype=torch.float64, device=dev),
-                "grad": torch.empty((bl, bd.nvar), dtype=torch.float64, device=dev),
-                "obj": torch.empty(bl, dtype=torch.float64, device=dev)}
-        norms = torch.empty((2, bl), dtype=torch.float64, device=dev)
-        gathered = torch.empty((world * 2, bl), dtype=torch.float64, device=dev)
-        ALL = ctd.CONS | ctd.JAC | ctd.HESS | ctd.GRAD | ctd.OBJ
-        bstream = torch.cuda.ExternalStream(bd.cuda_stream, device=dev)
-        bsteps = max(3, min(args.steps, 50))
 
-        bout["obj"] = norms[0]     # objective and violation land directly in the buffer that is gathered
+def leg_other_configs(cx, ctd):
+    """One-stream time and HBM fraction of BASELINE configs 3 and 4 (fused cons+jac+hess, :manual pattern)."""
+    torch, args = cx.torch, cx.args
+    out = {}
+    FLAGS = ctd.CONS | ctd.JAC | ctd.HESS
+    K = max(50, min(args.steps, 300))
+    for key, prob, sch, n in OTHER_CONFIGS:
+        d = ctd.DOCP(prob, n, sch, device=cx.local_rank, stream="own")
+        st = torch.cuda.ExternalStream(d.cuda_stream, device=cx.dev)
+        sets, alg = rotating_sets(cx, ctd, d, FLAGS, SEED + 7)
+        calls = [d.bind(FLAGS, s["x"], s["y"], 1.0, out=s["out"])[0] for s in sets]
+        r, _ = timed_regions(cx, calls, [st], K, 10, 3)
+        us = sorted(r)[1] * 1e3 / K
+        out[key] = {"workload": f"{prob}/{sch}/grid_size={n}", "us_per_eval": us, "algorithmic_bytes": alg,
+                    "achieved_gbs": alg / us / 1e3, "frac": alg / us / 1e3 / cx.peak, "steps": K,
+                    "how": "one stream, launches back to back, median of 3 regions"}
+        del calls, sets, d
+        torch.cuda.empty_cache()
+    return out
 
-        beval = bd.bind_with_norms(ALL, tx, ty, 1.0, out=bout, viol=norms[1])[0]
 
-        def bstep():
-            beval()
-            if world > 1:
-                dist.all_gather_into_tensor(gathered, norms)
+def leg_batched(cx, ctd):
+    """The 4096-instance batch sharded over the ranks: all schedules, kernel-only time, gather latency, e2e."""
+    torch, dist, args = cx.torch, cx.dist, cx.args
+    world, rank = cx.world, cx.rank
+    bl = B_TOTAL // world
+    rng = np.random.default_rng(SEED + 17)
+    tmax = rng.uniform(1.0, 3.5, size=B_TOTAL)          # continuation range test_initial_guess.jl:242
+    par_all = np.tile(np.array([310.0, 500.0, 2.0, 3.5]), (B_TOTAL, 1))
+    par_all[:, 3] = tmax
+    ALL = ctd.CONS | ctd.JAC | ctd.HESS | ctd.GRAD | ctd.OBJ
+    bsteps = max(3, min(args.steps, 50))
 
-        def timed_batched(step, drain=None):
-            regs = []
-            with torch.cuda.stream(bstream):
-                for _ in range(3):
+    def make(lo, hi):
+        n = hi - lo
+        bd = ctd.DOCP(PROBLEM, B_GRID, SCHEME, params=par_all[lo:hi], batch=n, device=cx.local_rank, stream="own")
+        bx, by = synthetic_point(bd.initial_guess(), bd.ncon, SEED + 99 + lo, batch=n)
+        tx, ty = torch.from_numpy(bx).to(cx.dev), torch.from_numpy(by).to(cx.dev)
+        bout = {"cons": torch.empty((n, bd.ncon), dtype=torch.float64, device=cx.dev),
+                "jac": torch.empty((n, bd.nnzj), dtype=torch.float64, device=cx.dev),
+                "hess": torch.empty((n, bd.nnzh), dtype=torch.float64, device=cx.dev),
+                "grad": torch.empty((n, bd.nvar), dtype=torch.float64, device=cx.dev)}
+        return bd, tx, ty, bout, (bx, by)
+
+    bd, tx, ty, bout, (bx, by) = make(rank * bl, (rank + 1) * bl)
+    bstream = torch.cuda.ExternalStream(bd.cuda_stream, device=cx.dev)
+    norms = torch.empty((2, bl), dtype=torch.float64, device=cx.dev)
+    gathered = torch.empty((world * 2, bl), dtype=torch.float64, device=cx.dev)
+    o1 = dict(bout)
+    o1["obj"] = norms[0]     # objective and violation land directly in the buffer that is gathered
+    beval = bd.bind_with_norms(ALL, tx, ty, 1.0, out=o1, viol=norms[1])[0]
+    bbytes = 8 * bl * (2 * bd.nvar + 2 * bd.ncon + bd.nnzj + bd.nnzh)
+
+    def timed_b(step, drain=None, steps=bsteps, stream=None, barrier=cx.barrier, reduce=True):
+        stream = stream or bstream
+        regs = []
+        with torch.cuda.stream(stream):
+            for _ in range(3):
+                step()
+            for _ in range(3):          # 3 timed regions; the median is reported
+                if drain:
+                    drain()
+                barrier()
+                b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                b0.record(stream)
+                for _ in range(steps):
                     step()
-                for _ in range(3):          # 3 timed regions of bsteps evaluations; the median is reported
-                    if drain:
-                        drain()
-                    barrier()
-                    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    b0.record(bstream)
-                    for _ in range(bsteps):
-                        step()
-                    if drain:
-                        drain()             # the timed region ends when the last gather has landed
-                    b1.record(bstream)
-                    barrier()
-                    regs.append(b0.elapsed_time(b1))
-            return regions_over_ranks(regs)[0]
+                if drain:
+                    drain()             # the timed region ends when the last gather has landed
+                b1.record(stream)
+                barrier()
+                regs.append(b0.elapsed_time(b1))
+        return cx.regions_over_ranks(regs)[0] if reduce else sorted(regs)[1]
 
-        bms = timed_batched(bstep)
-        # the same with the all-gather of evaluation k overlapping the kernel of evaluation k+1
-        # (ctdirect_b200.batch.NormsPipeline: collective on its own stream, two result slots)
-        pms = None
+    kms = timed_b(beval)                                   # the evaluation kernel of the shard alone
+
+    def bstep():
+        beval()
         if world > 1:
-            from ctdirect_b200.batch import NormsPipeline
-            pipe = NormsPipeline(bl, dev, depth=2, eval_stream=bstream)
+            dist.all_gather_into_tensor(gathered, norms)
 
-            pevals = []
-            for slot in range(2):
-                po = dict(bout)
-                po["obj"] = pipe.local[slot][0]
-                pevals.append(bd.bind_with_norms(ALL, tx, ty, 1.0, out=po, viol=pipe.local[slot][1])[0])
+    legs = {}
+    how_serial_torch = "kernel then all-gather on one stream (torch.distributed)"
+    legs[how_serial_torch] = timed_b(bstep)
+    gather_us = None
+    if world > 1:
+        from ctdirect_b200.batch import NativeNormsPipeline, NormsPipeline, broadcast_unique_id
+        # the all-gather of 2 x B doubles on its own (latency of the collective, nothing else on the stream)
+        gms = timed_b(lambda: dist.all_gather_into_tensor(gathered, norms), steps=max(bsteps, 50))
+        gather_us = gms * 1e3 / max(bsteps, 50)
+        pipe = NormsPipeline(bl, cx.dev, depth=2, eval_stream=bstream)
+        pevals = []
+        for slot in range(2):
+            po = dict(bout)
+            po["obj"] = pipe.local[slot][0]
+            pevals.append(bd.bind_with_norms(ALL, tx, ty, 1.0, out=po, viol=pipe.local[slot][1])[0])
+        legs["all-gather of evaluation k overlaps the kernel of evaluation k+1 (torch.distributed, separate stream, 2 slots)"] = \
+            timed_b(lambda: pipe.submit(lambda slot, o, v: pevals[slot]()), pipe.drain)
+        npipe = NativeNormsPipeline(bd, rank, world, broadcast_unique_id(), depth=2, n_instances=bl * world)
+        legs["kernel then all-gather, both issued by the library (ctd_gather_norms_dev)"] = \
+            timed_b(lambda: npipe.submit(ALL, tx, ty, bout, serial=True), npipe.drain)
+        legs["all-gather of evaluation k overlaps the kernel of evaluation k+1, both issued by the library "
+             "(ctd_gather_norms_dev on the handle's communication stream, 2 slots)"] = \
+            timed_b(lambda: npipe.submit(ALL, tx, ty, bout), npipe.drain)
+    best_how = min(legs, key=lambda k_: legs[k_])
+    best = legs[best_how]
+    serial_best = min(v for k_, v in legs.items() if k_.startswith("kernel then"))
+    ach = bbytes / (kms * 1e-3 / bsteps) / 1e9
+    res = {"workload": batched_workload_text(world), "steps": bsteps, "scaling": "strong",
+           "batched_evals_per_s": bsteps / (best * 1e-3), "instance_evals_per_s": B_TOTAL * bsteps / (best * 1e-3),
+           "ms_per_batched_eval": best / bsteps, "how": best_how,
+           "serialised_batched_evals_per_s": bsteps / (serial_best * 1e-3),
+           "schedules": {k_: {"batched_evals_per_s": bsteps / (v * 1e-3), "ms_per_batched_eval": v / bsteps} for k_, v in legs.items()},
+           "kernel_only": {"us": kms * 1e3 / bsteps, "achieved_gbs_per_gpu": ach, "hbm_frac_per_gpu": ach / cx.peak,
+                           "algorithmic_bytes_per_gpu": bbytes,
+                           "what": "the evaluation launch of one rank's shard alone, max over ranks"},
+           "hbm_gbs_per_gpu": bbytes / (best * 1e-3 / bsteps) / 1e9,
+           "hbm_frac_per_gpu": bbytes / (best * 1e-3 / bsteps) / 1e9 / cx.peak,
+           "all_gather_alone_us": gather_us, "instances_per_gpu": bl}
 
-            def pstep():
-                return pipe.submit(lambda slot, o, v: pevals[slot]())
+    # ---- e2e of the batched step: the scenario points come from the host every step (pinned x, y -> device), the
+    #      product of the step -- the gathered (objective, violation) of all instances -- goes back to the host
+    if not args.no_e2e:
+        hx = torch.from_numpy(bx).pin_memory()
+        hy = torch.from_numpy(by).pin_memory()
+        hres = torch.empty((world * 2, bl), dtype=torch.float64).pin_memory()
+        esteps = max(3, min(args.steps, 10))
 
-            pms = timed_batched(pstep, pipe.drain)
-        # the same two schedules through the library's own communicator (ctd_comm_init / ctd_gather_norms_dev:
-        # two C calls per step instead of a torch.distributed call)
-        nms = nps = None
-        if world > 1:
-            from ctdirect_b200.batch import NativeNormsPipeline, broadcast_unique_id
-            npipe = NativeNormsPipeline(bd, rank, world, broadcast_unique_id(), depth=2, n_instances=bl * world)
-            nout = {k_: v_ for k_, v_ in bout.items() if k_ != "obj"}
-            nms = timed_batched(lambda: npipe.submit(ALL, tx, ty, nout, serial=True), npipe.drain)
-            nps = timed_batched(lambda: npipe.submit(ALL, tx, ty, nout), npipe.drain)
-        bbytes = 8 * bl * (2 * bd.nvar + 2 * bd.ncon + bd.nnzj + bd.nnzh)
-        legs_b = {"kernel then all-gather on one stream (torch.distributed)": bms,
-                  "all-gather of evaluation k overlaps the kernel of evaluation k+1 (torch.distributed, separate stream, 2 slots)": pms,
-                  "kernel then all-gather, both issued by the library (ctd_gather_norms_dev)": nms,
-                  "all-gather of evaluation k overlaps the kernel of evaluation k+1, both issued by the library "
-                  "(ctd_gather_norms_dev on the handle's communication stream, 2 slots)": nps}
-        best_how = min((k_ for k_ in legs_b if legs_b[k_] is not None), key=lambda k_: legs_b[k_])
-        best = legs_b[best_how]
-        bach = bbytes / (best * 1e-3 / bsteps) / 1e9
-        batched = {"workload": f"{B_TOTAL} Goddard/midpoint instances, grid_size={B_GRID}, Tmax in [1,3.5], "
-                               f"{bl} per GPU; obj+grad+cons+jac+hess + violation norm in ONE launch + NCCL all-gather",
-                   "batched_evals_per_s": bsteps / (best * 1e-3), "instance_evals_per_s": B_TOTAL * bsteps / (best * 1e-3),
-                   "ms_per_batched_eval": best / bsteps, "steps": bsteps, "scaling": "strong",
-                   "hbm_gbs_per_gpu": bach, "hbm_frac_per_gpu": bach / peak,
-                   "how": best_how,
-                   "serialised": {"batched_evals_per_s": bsteps / (bms * 1e-3), "ms_per_batched_eval": bms / bsteps,
-                                  "how": "kernel then all-gather on one stream (torch.distributed)"},
-                   "native_serialised": (None if nms is None else
-                                         {"batched_evals_per_s": bsteps / (nms * 1e-3), "ms_per_batched_eval": nms / bsteps}),
-                   "native_pipelined": (None if nps is None else
-                                        {"batched_evals_per_s": bsteps / (nps * 1e-3), "ms_per_batched_eval": nps / bsteps}),
-                   "pipelined": (None if pms is None else
-                                 {"batched_evals_per_s": bsteps / (pms * 1e-3), "ms_per_batched_eval": pms / bsteps})}
+        def e2e_step():
+            with torch.cuda.stream(bstream):
+                tx.copy_(hx, non_blocking=True)
+                ty.copy_(hy, non_blocking=True)
+                beval()
+                if world > 1:
+                    dist.all_gather_into_tensor(gathered, norms)
+                    hres.copy_(gathered, non_blocking=True)
+                else:
+                    hres.copy_(norms, non_blocking=True)
+            bstream.synchronize()
 
-    # ---- CPU baseline on the host cores (rank 0, bounded sample)
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        try:
-            from oracle import oracle as orc
-            orc.build()
-            ncores = os.cpu_count() or 1
-            t1, r1, _ = cpu_fused_eval_time(orc, 1, 4.0)
-            tn, rn, used = cpu_fused_eval_time(orc, ncores, 8.0)
-            cpu = {"value": 1.0 / tn, "unit": "evals/s", "cores": used, "kind": "port",
-                   "sample": f"{rn} fused cons+jac+hess evaluations of the full workload on {used} threads "
-                             f"(OpenMP over steps); single thread: {1.0 / t1:.3f} evals/s over {r1} evaluations",
-                   "single_thread_value": 1.0 / t1}
-        except Exception as ex:  # the oracle is only a reported baseline
-            cpu = {"value": None, "unit": "evals/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+        for _ in range(2):
+            e2e_step()
+        els = []
+        for _ in range(3):
+            cx.barrier()
+            t0 = time.perf_counter()
+            for _ in range(esteps):
+                e2e_step()
+            els.append(cx.max_over_ranks((time.perf_counter() - t0) * 1e3) * 1e-3)
+        el = sorted(els)[1]
+        res["e2e"] = {"value": esteps / el, "unit": "evals/s", "ms_per_step": 1e3 * el / esteps, "steps": esteps,
+                      "h2d_bytes_per_step": 8 * bl * (bd.nvar + bd.ncon), "d2h_bytes_per_step": 8 * world * 2 * bl,
+                      "api": "pinned x, y -> device, ctd_eval_norms_dev, all-gather, gathered norms -> pinned host; "
+                             "blocking per step, wall clock, max over ranks; bytes are per GPU"}
 
-    if rank == 0:
+    # ---- same-run one-GPU reference for the strong-scaling efficiency (rank 0 alone evaluates all 4096 instances)
+    if world > 1:
+        one = None
+        del beval, tx, ty, bout, norms, gathered
+        if rank == 0:
+            bd1, tx1, ty1, bout1, _ = make(0, B_TOTAL)
+            st1 = torch.cuda.ExternalStream(bd1.cuda_stream, device=cx.dev)
+            n1 = torch.empty((2, B_TOTAL), dtype=torch.float64, device=cx.dev)
+            o = dict(bout1)
+            o["obj"] = n1[0]
+            ev1 = bd1.bind_with_norms(ALL, tx1, ty1, 1.0, out=o, viol=n1[1])[0]
+            ms1 = timed_b(ev1, stream=st1, barrier=torch.cuda.synchronize, reduce=False)
+            one = bsteps / (ms1 * 1e-3)
+        cx.barrier()
+        res["one_gpu_same_run"] = {"batched_evals_per_s": one,
+                                   "what": "rank 0 alone evaluates all 4096 instances (no collective) while the other ranks idle"}
+        if one:
+            res["strong_scaling_efficiency_vs_one_gpu_same_run"] = res["batched_evals_per_s"] / (world * one)
+    return res, bd
+
+
+def main():
+    _quiet_stdout()
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--streams", type=int, default=3, help="independent evaluation streams in flight (`overlapped`)")
+    ap.add_argument("--no-batched", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return 0
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import ctdirect_b200 as ctd
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU port")
+    cx = Ctx(args)
+    sampler = ClockSampler(cx.local_rank)
+    timing = ("CUDA events on the handles' streams, max over streams and ranks; median of repeated timed regions of "
+              "exactly --steps evaluations each (all regions in region_ms)")
+
+    if world == 1:
+        single = leg_single(cx, ctd, sampler)
+        nvar, ncon, nnzj, nnzh = single["dims"]
+        configs = None if args.no_configs else leg_other_configs(cx, ctd)
+        batched = None
+        if not args.no_batched:
+            batched, _ = leg_batched(cx, ctd)
+        cpu = None
+        if not args.no_cpu:
+            try:
+                from oracle import oracle as orc
+                orc.build()
+                ncores = os.cpu_count() or 1
+                t1, r1, _ = cpu_fused_eval_time(orc, 1, 4.0)
+                tn, rn, used = cpu_fused_eval_time(orc, ncores, 8.0)
+                cpu = {"value": 1.0 / tn, "unit": "evals/s", "cores": used, "kind": "port",
+                       "sample": f"{rn} fused cons+jac+hess evaluations of the full workload on {used} threads "
+                                 f"(OpenMP over steps); single thread (the reference's own design): {1.0 / t1:.3f} evals/s "
+                                 f"over {r1} evaluations",
+                       "single_thread_value": 1.0 / t1}
+            except Exception as ex:  # the oracle is only a reported baseline
+                cpu = {"value": None, "unit": "evals/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
         line = {
-            "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": single["value"], "unit": "evals/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": single["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_text(nvar, ncon, nnzj, nnzh),
-                       "launches": "one kernel launch per evaluation",
-                       "l2": f"rotating {nsets} input/output buffer sets ({nsets * alg_bytes / 1e6:.0f} MB > 126 MB L2)",
-                       "streams": f"{NSTREAMS} independent evaluations in flight per GPU (one handle + CUDA stream each); "
-                                  "single_stream / roofline give the one-stream figures",
-                       "timing": f"CUDA events on the handles' streams, max over streams and ranks; median of {REPEATS} timed regions of exactly --steps evaluations each (all regions in region_ms)"},
-            "single_stream": single_stream, "region_ms": regions, "numa": numa,
-            "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu, "batched": batched,
+                       "launches": "one kernel launch per evaluation, one stream, back to back (serially dependent callbacks)",
+                       "l2": f"rotating {single['nsets']} input/output buffer sets "
+                             f"({single['nsets'] * single['alg_bytes'] / 1e6:.0f} MB > 126 MB L2)",
+                       "timing": timing},
+            "region_ms": single["region_ms"], "overlapped": single["overlapped"], "clocks": sampler.summary(),
+            "e2e": single.get("e2e"), "gpu_launches": single["launches"], "roofline": single["roofline"],
+            "configs": configs, "separate_callbacks_us": single["separate_callbacks_us"],
+            "cpu_baseline": cpu, "batched": batched,
         }
         _emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+        return 0
+
+    # ---- N > 1: the batched metric
+    sampler.start()
+    batched, bd = leg_batched(cx, ctd)
+    sampler.stop()
+    replicas = None
+    if not args.no_configs:
+        # for reference: every rank evaluates its own grid-1e5 instance on one stream (replicas, no collective)
+        FLAGS = ctd.CONS | ctd.JAC | ctd.HESS
+        d = ctd.DOCP(PROBLEM, GRID, SCHEME, device=cx.local_rank, stream="own")
+        st = torch.cuda.ExternalStream(d.cuda_stream, device=cx.dev)
+        sets, alg = rotating_sets(cx, ctd, d, FLAGS, SEED)
+        calls = [d.bind(FLAGS, s["x"], s["y"], 1.0, out=s["out"])[0] for s in sets]
+        K = max(50, min(args.steps, 500))
+        r, _ = timed_regions(cx, calls, [st], K, 10, 3)
+        ms, _ = cx.regions_over_ranks(r)
+        replicas = {"metric": METRIC, "value": world * K / (ms * 1e-3), "unit": "evals/s", "scaling": "weak",
+                    "what": "one independent grid-1e5 instance per GPU, one stream each, no collective (replicas)"}
+    if rank == 0:
+        ko = batched["kernel_only"]
+        line = {
+            "metric": METRIC_BATCHED, "value": batched["batched_evals_per_s"], "unit": "evals/s", "n_gpus": world,
+            "steps": batched["steps"], "warmup": 3, "ms_per_step": batched["ms_per_batched_eval"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": batched_workload_text(world), "schedule": batched["how"],
+                       "l2": f"the shard of one GPU moves {ko['algorithmic_bytes_per_gpu'] / 1e6:.0f} MB per evaluation (> 126 MB L2)",
+                       "timing": "CUDA events on the evaluation stream, barrier + synchronize on both sides, median of 3 "
+                                 "regions, max over ranks"},
+            "numa": cx.numa, "clocks": sampler.summary(), "e2e": batched.get("e2e"),
+            "gpu_launches": int(batched["steps"]),
+            "roofline": {"bound": "hbm", "achieved": ko["achieved_gbs_per_gpu"], "peak": cx.peak, "unit": "GB/s",
+                         "frac": ko["hbm_frac_per_gpu"], "traffic": measured_traffic("batched_dram_bytes_per_launch"),
+                         "kernel": "ctd_eval_kernel_light<E_goddard__midpoint, ALL|VIOL> on one rank's shard",
+                         "algorithmic_bytes_per_launch": ko["algorithmic_bytes_per_gpu"], "launch_us": ko["us"],
+                         "peak_source": cx.peak_src, "how": ko["what"]},
+            "batched": batched, "single_instance_replicas": replicas,
+        }
+        _emit(line)
+    cx.dist.destroy_process_group()
     return 0
 
 

@@ -20,12 +20,10 @@
 //   * the irregular ends (column blocks 1, N, N+1, boundary / final-path rows) are handled by CTA 0
 //     through host-built position tables;
 //   * (v,v) Hessian entries, d/dv of the cost and the Lagrange sum are reduced with warp shuffles into
-//     per-CTA partials that are summed in a fixed order (deterministic, no floating-point atomics on
-//     global memory): for a single instance by a collector warp of CTA 0 that picks the partials up as
-//     they are published (self-validating 16-byte records, no fences or tickets on the critical path),
-//     for batches by the last CTA of the instance to finish.  Slots to which no STEP contributes
-//     (e.g. the (tf,tf) entry of an autonomous free-final-time problem) are not reduced at all: the
-//     edge CTA writes them;
+//     per-CTA partials and summed in a fixed order by the last CTA to finish (deterministic, no
+//     floating-point atomics on global memory).  Slots to which no STEP contributes (e.g. the (tf,tf)
+//     entry of an autonomous free-final-time problem, a Mayer cost) are not reduced at all: the edge
+//     CTA writes them;
 //   * everything that does not depend on earlier work of the stream (tile geometry, normalized times,
 //     parameters, edge tables, L2 prefetch of the tile's inputs) runs BEFORE griddepcontrol.wait, i.e.
 //     while the previous kernel of the stream drains (programmatic dependent launch).
@@ -68,10 +66,8 @@ struct EvalArgs {
     long long jv_base[MAX_NV];    // position of the first value of column v_k in jvals
     long long hvv_pos[MAX_NVV];   // positions of the (v_a, v_b) entries in hvals (packed lower triangle)
     double* viol;                 // [batch] max(lcon - c, c - ucon, 0) per instance, or nullptr
-    double* partials;             // [batch][ctas][NREDX] doubles (ticket mode) or 16-byte records (collector mode)
+    double* partials;             // [batch][ctas][NREDX]
     unsigned int* counters;       // [batch]
-    unsigned long long key;       // collector mode: validation key of THIS launch (never 0; changes with every launch)
-    int poll;                     // 1: collector mode (see publish_reduction), 0: ticket mode
     // edge tables (identical for every instance)
     const int* edge_map;
     const long long* edge_pos;    // destination position of every edge-buffer entry
@@ -625,30 +621,12 @@ __device__ __forceinline__ void tile_phase(const EvalArgs& a, double* __restrict
 
 // ---------------------------------------------------------------------------------------------
 // Deterministic reduction of the global sums ((v,v) Hessian entries, d cost / d v, cost, violation) over
-// the grid.  Inside a CTA: warp shuffles, then the last warp to arrive (shared-memory ticket, no CTA
-// barrier) combines the CTA's NW warps in a fixed order into ONE partial per slot.  Across CTAs:
-//   * ticket mode (batches): the partial is stored, fenced, a global ticket is taken and the last CTA of
-//     the instance sums all partials in a fixed order;
-//   * collector mode (a.poll, single instances, where this tail is on the critical path of the launch):
-//     the partial is published as a self-validating 16-byte record {bits(v), bits(v) ^ key} with one plain
-//     vector store -- no fence, no atomic -- and the last warp of CTA 0 collects the records of all CTAs
-//     while the grid is still running (re-reading those that have not landed), then sums them in the same
-//     fixed order.  `key` changes with every launch of the handle, so a record left by an earlier launch
-//     (or a torn read) never validates; producers never wait on anything, so the collector cannot deadlock
-//     whatever the CTA dispatch order.
-struct alignas(16) RedRecord { unsigned long long v, chk; };
-
-__device__ __forceinline__ void store_record(RedRecord* dst, double v, unsigned long long key) {
-    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
-    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" :: "l"(dst), "l"(b), "l"(b ^ key) : "memory");
-}
-__device__ __forceinline__ bool load_record(const RedRecord* src, unsigned long long key, double& v) {
-    unsigned long long b, chk;
-    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(b), "=l"(chk) : "l"(src) : "memory");
-    v = __longlong_as_double((long long)b);
-    return (b ^ chk) == key;
-}
-
+// the grid -- only compiled for the slots a STEP contributes to (Cfg::RH / RG / RO / WV).  Inside a CTA:
+// warp shuffles, then the last warp to arrive (shared-memory ticket, no CTA barrier) combines the CTA's NW
+// warps in a fixed order into ONE partial per slot; across CTAs the partial is stored, fenced, a global
+// ticket is taken and the last CTA of the instance sums all partials in a fixed order.
+// (Measured and dropped: a collector warp in CTA 0 that polls self-validating 16-byte records instead of
+// the fence + ticket -- 8.4 vs 7.3 us on bolza/midpoint at grid 1e5, 10.8 vs 8.3 us on the double integrator.)
 template <class E, int F>
 __device__ __forceinline__ void publish_reduction(const EvalArgs& a, const double* red, double* sred,
                                                   unsigned int* cta_ticket_p, long long inst, int cta, int lane,
@@ -658,21 +636,6 @@ __device__ __forceinline__ void publish_reduction(const EvalArgs& a, const doubl
         constexpr int NR = C::NREDX;
         // slot R_V (the constraint violation) is combined with max, every other slot with +
         auto comb = [](int k, double x, double y) { return (C::WV && k == C::R_V) ? nanmax(x, y) : x + y; };
-        // final values of the instance -> their destinations (lane 0 of the finishing warp)
-        auto finish = [&](const double* acc) {
-#pragma unroll
-            for (int k = 0; k < NR; ++k) {
-                double v = acc[k];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v = comb(k, v, __shfl_xor_sync(0xffffffffu, v, o));
-                if (lane == 0) {
-                    if (C::WV && k == C::R_V) { if (a.viol) a.viol[inst] = v; }
-                    else if (C::RH && k < C::R_G) { if (a.hvv_pos[k - C::R_H] >= 0) hvals[a.hvv_pos[k - C::R_H]] = v; }
-                    else if (C::RG && k < C::R_O) grad[a.nvar - E::NV + (k - C::R_G)] = v;
-                    else if (C::RO && a.obj) a.obj[inst] = v;
-                }
-            }
-        };
         unsigned int& cta_ticket = *cta_ticket_p;
         const int nblk = a.ctas;
         double wv[NR];
@@ -693,85 +656,49 @@ __device__ __forceinline__ void publish_reduction(const EvalArgs& a, const doubl
         flag = __shfl_sync(0xffffffffu, flag, 0);
         if (!flag) return;
         __threadfence_block();
-        double cv = 0.0;   // lane k < NR: slot k of this CTA
-        if (lane < NR) {
-            cv = sred[lane];
-            for (int w = 1; w < NW; ++w) cv = comb(lane, cv, sred[w * NR + lane]);
-        }
-        if (a.poll) {
-            RedRecord* rec = reinterpret_cast<RedRecord*>(a.partials) + (inst * nblk) * NR;
-            if (lane < NR) store_record(rec + (long long)cta * NR + lane, cv, a.key);
-            if (cta != 0) return;
-            // ---- collector: lane l takes the CTAs l, l + 32, ... in ascending order, U at a time (one memory
-            //      round trip per pass over the pending ones)
-            constexpr int U = NR <= 2 ? 8 : (NR <= 4 ? 4 : 2);
-            double acc[NR];
-#pragma unroll
-            for (int k = 0; k < NR; ++k) acc[k] = 0.0;
-            for (int base = 0; base < nblk; base += 32 * U) {
-                double t[U][NR];
-                unsigned int pend = 0;
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    if (base + u * 32 + lane < nblk) pend |= 1u << u;
-#pragma unroll
-                    for (int k = 0; k < NR; ++k) t[u][k] = 0.0;
-                }
-                while (pend) {
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        if (pend & (1u << u)) {
-                            const RedRecord* r = rec + (long long)(base + u * 32 + lane) * NR;
-                            bool ok = true;
-#pragma unroll
-                            for (int k = 0; k < NR; ++k) ok = load_record(r + k, a.key, t[u][k]) && ok;
-                            if (ok) pend &= ~(1u << u);
-                        }
-                    }
-                    if (pend) __nanosleep(40);
-                }
-#pragma unroll
-                for (int k = 0; k < NR; ++k) {
-#pragma unroll
-                    for (int u = 0; u < U; ++u) acc[k] = comb(k, acc[k], t[u][k]);
-                }
-            }
-            __syncwarp();
-            finish(acc);
-            return;
-        }
-        // ---- ticket mode
         double* part = a.partials + (inst * nblk) * NR;
         if (lane < NR) {
-            part[(long long)cta * NR + lane] = cv;
+            double v = sred[lane];
+            for (int w = 1; w < NW; ++w) v = comb(lane, v, sred[w * NR + lane]);
+            part[(long long)cta * NR + lane] = v;
             __threadfence();
         }
         __syncwarp();
         unsigned int last = 0;
         if (lane == 0) last = (atomicAdd(&a.counters[inst], 1u) == (unsigned int)(nblk - 1));
         last = __shfl_sync(0xffffffffu, last, 0);
-        if (last) {
-            __threadfence();
-            double acc[NR];
+        if (!last) return;
+        __threadfence();
+        double acc[NR];
 #pragma unroll
-            for (int k = 0; k < NR; ++k) acc[k] = 0.0;
-            // 16 independent loads per lane in flight (one memory round trip per 512 partials)
-            for (int base = 0; base < nblk; base += 32 * 16) {
+        for (int k = 0; k < NR; ++k) acc[k] = 0.0;
+        // 16 independent loads per lane in flight (one memory round trip per 512 partials)
+        for (int base = 0; base < nblk; base += 32 * 16) {
 #pragma unroll
-                for (int k = 0; k < NR; ++k) {
-                    double t[16];
+            for (int k = 0; k < NR; ++k) {
+                double t[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int bb = base + j * 32 + lane;
-                        t[j] = bb < nblk ? __ldcg(&part[(long long)bb * NR + k]) : 0.0;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[k] = comb(k, acc[k], t[j]);
+                for (int j = 0; j < 16; ++j) {
+                    const int bb = base + j * 32 + lane;
+                    t[j] = bb < nblk ? __ldcg(&part[(long long)bb * NR + k]) : 0.0;
                 }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[k] = comb(k, acc[k], t[j]);
             }
-            finish(acc);
-            if (lane == 0) a.counters[inst] = 0u;
         }
+#pragma unroll
+        for (int k = 0; k < NR; ++k) {
+            double v = acc[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v = comb(k, v, __shfl_xor_sync(0xffffffffu, v, o));
+            if (lane == 0) {
+                if (C::WV && k == C::R_V) { if (a.viol) a.viol[inst] = v; }
+                else if (C::RH && k < C::R_G) { if (a.hvv_pos[k - C::R_H] >= 0) hvals[a.hvv_pos[k - C::R_H]] = v; }
+                else if (C::RG && k < C::R_O) grad[a.nvar - E::NV + (k - C::R_G)] = v;
+                else if (C::RO && a.obj) a.obj[inst] = v;
+            }
+        }
+        if (lane == 0) a.counters[inst] = 0u;
     }
 }
 
@@ -843,6 +770,7 @@ __device__ __forceinline__ void eval_body(const EvalArgs& a) {
             if (lane == 0 && E::NV > 0) prefetch_l2(x + a.nvar - E::NV);
         }
         pdl_entry();
+        CTD_STAMP(7);
         double z[E::NZ], lam[E::CB];
         TimeArgs<E::NV> Tm;
         if (active) {
@@ -855,7 +783,7 @@ __device__ __forceinline__ void eval_body(const EvalArgs& a) {
             time_args_s<E>(si, sp, z + E::NOWN + E::NNEXT, pr, Tm);
         }
 #ifdef CTD_TRACE
-        if (active && Tm.hh == -1.2345) CTD_STAMP(7);   // forces the loads to have arrived
+        if (active && Tm.hh == -1.2345) CTD_STAMP(5);   // forces the loads to have arrived
         CTD_STAMP(1);
 #endif
         if constexpr (C::GZ) {   // gradient entries of the owned column blocks: zeros (see Cfg::GZ)

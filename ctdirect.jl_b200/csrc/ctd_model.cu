@@ -97,7 +97,6 @@ Model::Model(const Registration& reg, int grid_size, const double* time_grid, in
     if (batch < 1) throw CtdError{-2, "batch must be >= 1"};
     if (batch > 65535) throw CtdError{-2, "batch must be <= 65535 (instances are the y dimension of the grid)"};
     if (f.nv > MAX_NV) throw CtdError{-2, "too many optimisation variables v for this build"};
-    if (const char* e = getenv("CTD_POLL_MAX_BATCH")) poll_max_batch_ = atoi(e);   // 0: ticketed reduction everywhere
     // DOCPtime: DOCP_data.jl:176-214
     if (!time_grid) {
         if (grid_size < 1) throw CtdError{-2, "grid_size must be >= 1"};
@@ -570,9 +569,7 @@ void Model::ensure_device() {
         max_ctas = std::max<int64_t>(max_ctas, tiles + 1);   // (one warp per CTA is the smallest launch configuration)
         if (q.p_threads > 0) max_ctas = std::max<int64_t>(max_ctas, ((N_ >= 3) ? ((int64_t)N_ - 2 + q.p_own - 1) / q.p_own : 0) + 1);
     }
-    // (x2: in collector mode a partial is a 16-byte self-validating record, see publish_reduction)
-    CTD_CUDA(cudaMalloc(&d_partials_, sizeof(double) * 2 * (size_t)batch_ * max_ctas * max_nred));
-    CTD_CUDA(cudaMemsetAsync(d_partials_, 0, sizeof(double) * 2 * (size_t)batch_ * max_ctas * max_nred, stream_));
+    CTD_CUDA(cudaMalloc(&d_partials_, sizeof(double) * (size_t)batch_ * max_ctas * max_nred));
     CTD_CUDA(cudaMalloc(&d_counters_, sizeof(unsigned int) * batch_));
     CTD_CUDA(cudaMemsetAsync(d_counters_, 0, sizeof(unsigned int) * batch_, stream_));
     CTD_CUDA(cudaMemcpyAsync(d_edge_map_, edge_map_.data(), sizeof(int) * edge_map_.size(), cudaMemcpyHostToDevice, stream_));
@@ -618,6 +615,7 @@ cudaStream_t Model::stream() {
 
 void Model::set_stream(cudaStream_t s) {
     ensure_device();
+    if ((s ? s : own_stream_) == stream_) return;   // already there: nothing to order
     // work already enqueued on the previous stream is not ordered with the new one: finish it first
     CTD_CUDA(cudaSetDevice(device_));
     CTD_CUDA(cudaStreamSynchronize(stream_));
@@ -681,9 +679,16 @@ void Model::eval_dev(int flags, const double* x, const double* y, double sigma, 
     // an instance rarely fill a large CTA)
     // (measured: N = 1000 x 4096 instances 78 % -> 94 % of the HBM peak with 3 warps per CTA, whereas a
     // single 1e6-step grid is faster with 8)
-    const int wpc = batch_ > 1 ? std::min(lc.wpc, 3) : lc.wpc;
-    int threads = 32 * wpc;
+    static const int wpc_env = getenv("CTD_WPC") ? atoi(getenv("CTD_WPC")) : 0;   // tuning runs only
     a.tiles = (N_ >= 3) ? (int)(((int64_t)N_ - 2 + lc.own - 1) / lc.own) : 0;
+    // A single instance whose tiles are all resident at once (one wave: <= 24 warps on each of the 148 SMs) is
+    // launched as 2-warp CTAs: 3226 tiles of a 1e5-step grid then spread as 22 warps on EVERY SM instead of a mix of
+    // 24 and 16 (8-warp CTAs), and with programmatic dependent launch the CTAs are scheduled while the previous
+    // kernel drains, so their number costs nothing (10.30 -> 9.95 us per evaluation, one stream).
+    int wpc = batch_ > 1 ? std::min(lc.wpc, 3) : lc.wpc;
+    if (batch_ == 1 && lc.wpc >= 8 && a.tiles <= 148 * 24) wpc = 2;
+    if (wpc_env > 0) wpc = std::min(lc.wpc, wpc_env);
+    int threads = 32 * wpc;
     a.ctas = (a.tiles + wpc - 1) / wpc + 1;
     // wide elements on small grids: one tile per CTA, the tile's outputs split over the CTA's warps
     // (enough warps to occupy the GPU although the grid has few steps)
@@ -726,28 +731,26 @@ void Model::eval_dev(int flags, const double* x, const double* y, double sigma, 
             cur = smem;
         }
     }
-    // collector mode for single instances (the reduction tail is on the critical path of the launch); a launch
-    // that is being captured into a CUDA graph would replay the same key, so it takes the ticketed reduction
-    a.poll = 0;
-    if (batch_ <= poll_max_batch_ && lc.nred > 0) {
-        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-        if (cudaStreamIsCapturing(stream_, &cs) != cudaSuccess) { cs = cudaStreamCaptureStatusActive; (void)cudaGetLastError(); }
-        if (cs == cudaStreamCaptureStatusNone) {
-            a.poll = 1;
-            uint64_t e = ++epoch_;   // splitmix64 finaliser: consecutive launches get unrelated keys; never 0
-            e += 0x9E3779B97F4A7C15ull;
-            e = (e ^ (e >> 30)) * 0xBF58476D1CE4E5B9ull;
-            e = (e ^ (e >> 27)) * 0x94D049BB133111EBull;
-            e ^= e >> 31;
-            a.key = e | 1ull;
-        }
-    }
 #ifdef CTD_TRACE
-    // debug builds only: per-warp timestamps of the launch, dumped as raw int64 to $CTD_TRACE_FILE
+    // debug builds only: per-warp timestamps, dumped as raw int64 to $CTD_TRACE_FILE.  Without CTD_TRACE_AT every
+    // launch is traced on its own (memset before, copy + synchronize after).  With CTD_TRACE_AT=K the launches K-1
+    // and K of this handle are traced into one preallocated buffer with nothing but the two kernels on the stream
+    // between them: the timeline of a launch in the steady state of back-to-back (PDL) launches.
     long long* d_trace = nullptr;
     const size_t ntrace = (size_t)a.ctas * std::max(lc.wpc, std::max(threads, lc.p_threads) / 32) * 8;
     const char* trace_file = getenv("CTD_TRACE_FILE");
-    if (trace_file) {
+    const char* trace_at = getenv("CTD_TRACE_AT");
+    static long long* d_pair = nullptr;
+    const int64_t at = trace_at ? atoll(trace_at) : -1;
+    if (trace_file && at >= 0) {
+        if (!d_pair) {
+            CTD_CUDA(cudaMalloc(&d_pair, 2 * ntrace * sizeof(long long)));
+            CTD_CUDA(cudaMemsetAsync(d_pair, 0, 2 * ntrace * sizeof(long long), stream_));
+            CTD_CUDA(cudaStreamSynchronize(stream_));
+        }
+        if (launches_ == at - 1) a.trace = d_pair;
+        if (launches_ == at) a.trace = d_pair + ntrace;
+    } else if (trace_file) {
         CTD_CUDA(cudaMalloc(&d_trace, ntrace * sizeof(long long)));
         CTD_CUDA(cudaMemsetAsync(d_trace, 0, ntrace * sizeof(long long), stream_));
         a.trace = d_trace;
@@ -763,6 +766,12 @@ void Model::eval_dev(int flags, const double* x, const double* y, double sigma, 
         CTD_CUDA(cudaStreamSynchronize(stream_));
         if (FILE* f = fopen(trace_file, "wb")) { fwrite(h.data(), sizeof(long long), ntrace, f); fclose(f); }
         cudaFree(d_trace);
+    }
+    if (d_pair && launches_ == at + 8) {   // a few launches later: the traced pair had successors like any other
+        std::vector<long long> h(2 * ntrace);
+        CTD_CUDA(cudaMemcpyAsync(h.data(), d_pair, 2 * ntrace * sizeof(long long), cudaMemcpyDeviceToHost, stream_));
+        CTD_CUDA(cudaStreamSynchronize(stream_));
+        if (FILE* f = fopen(trace_file, "wb")) { fwrite(h.data(), sizeof(long long), 2 * ntrace, f); fclose(f); }
     }
 #endif
 }

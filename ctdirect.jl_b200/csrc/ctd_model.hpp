@@ -153,8 +153,6 @@ class Model {
     unsigned int* d_counters_ = nullptr;
     double *d_x_ = nullptr, *d_y_ = nullptr, *d_c_ = nullptr, *d_j_ = nullptr, *d_h_ = nullptr, *d_g_ = nullptr,
            *d_obj_ = nullptr, *d_lcon_ = nullptr, *d_ucon_ = nullptr, *d_viol_ = nullptr;
-    uint64_t epoch_ = 0;        // launches in collector mode (key of the reduction records)
-    int poll_max_batch_ = 4;    // collector-mode reduction up to this many instances (CTD_POLL_MAX_BATCH)
     int64_t launches_ = 0;
     // KKT structure and position maps (built on first use)
     void build_kkt();

@@ -9,7 +9,10 @@ and, for the model, the NLPModels API [3P] that Ipopt / MadNLP drive:
   obj, grad, cons, jac_structure, jac_coord, hess_structure, hess_coord(x, y; obj_weight), meta.
 
 Arrays may be numpy arrays (host; copied through the handle, synchronous) or torch CUDA tensors
-(device; no copies, enqueued on the handle's stream).  All compute happens in libctdirect_b200.so.
+(device; no copies).  Device work is enqueued on torch's CURRENT stream by default (`stream="torch"`), so
+it is ordered with the torch kernels that produce the inputs and consume the results; `stream="own"`
+keeps the handle's private non-blocking stream (the caller then synchronises explicitly: `synchronize()`,
+events, or `torch.cuda.ExternalStream(docp.cuda_stream)`).  All compute happens in libctdirect_b200.so.
 """
 from __future__ import annotations
 
@@ -74,7 +77,11 @@ class DOCP:
     """Discretised optimal control problem bound to one GPU (DOCP struct, src/DOCP_data.jl:265-366)."""
 
     def __init__(self, ocp, grid_size: int = 250, scheme: str = "midpoint", time_grid=None, params=None,
-                 pattern_mode: str = "reference", batch: int = 1, device: int = 0, disc_method: Optional[str] = None):
+                 pattern_mode: str = "reference", batch: int = 1, device: int = 0, disc_method: Optional[str] = None,
+                 stream: str = "torch"):
+        if stream not in ("torch", "own"):
+            raise ValueError("stream must be 'torch' (follow torch's current stream) or 'own'")
+        self._stream_mode, self._stream_set = stream, None
         lib = _lib.load()
         name = ocp if isinstance(ocp, str) else ocp.name
         scheme = str(disc_method if disc_method is not None else scheme).lstrip(":")
@@ -164,7 +171,8 @@ class DOCP:
         dc = self._check_in(dc, self.ncon, "dc")
         if not _is_torch(hvals):
             raise TypeError("kkt_assemble needs CUDA tensors")
-        out = self._check_in(out, self.nnzk, "out") if out is not None else self._empty_like(hvals, self.nnzk)
+        out = self._check_in(out, self.nnzk, "out", output=True) if out is not None else self._empty_like(hvals, self.nnzk)
+        self._follow_stream(hvals)
         _lib.check(self._lib.ctd_kkt_assemble_dev(self._h, _ptr(hvals), _ptr(jvals), _ptr(dx), _ptr(dc), _ptr(out)))
         return out
 
@@ -180,7 +188,10 @@ class DOCP:
             return torch.empty(self._shape(n), dtype=torch.float64, device=x.device)
         return np.empty(self._shape(n))
 
-    def _check_in(self, a, n, what):
+    def _check_in(self, a, n, what, output=False):
+        """Inputs: CUDA tensors must be contiguous float64 on the handle's device, host arrays are converted.
+        Outputs (`output=True`) are filled IN PLACE (NLPModels semantics), so a host buffer that would have to
+        be copied to become C-contiguous float64 is an error, not a silent temporary."""
         if a is None:
             return None
         if _is_torch(a):
@@ -189,14 +200,27 @@ class DOCP:
                 raise TypeError(f"{what}: expected a contiguous float64 CUDA tensor")
             if a.device.index != self.device:
                 raise ValueError(f"{what}: tensor is on cuda:{a.device.index}, handle on cuda:{self.device}")
+        elif output:
+            if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous and a.flags.writeable):
+                raise TypeError(f"{what}: an output buffer must be a writeable C-contiguous float64 numpy array "
+                                "(it is filled in place)")
         else:
             a = np.ascontiguousarray(a, dtype=np.float64)
-        if a.size if not _is_torch(a) else a.numel():
-            pass
         size = a.numel() if _is_torch(a) else a.size
         if size != self.batch * n:
             raise ValueError(f"{what}: expected {self.batch}x{n} values, got {size}")
         return a
+
+    def _follow_stream(self, *tensors):
+        """`stream="torch"`: put the handle on torch's current stream of its device (a no-op when it already is
+        there), so that device evaluations are ordered with the surrounding torch work."""
+        if self._stream_mode != "torch" or not any(_is_torch(t) for t in tensors if t is not None):
+            return
+        import torch
+        ptr = int(torch.cuda.current_stream(self.device).cuda_stream) or 1   # 0 = legacy default stream = cudaStreamLegacy (1)
+        if ptr != self._stream_set:
+            _lib.check(self._lib.ctd_set_stream(self._h, C.c_void_p(ptr)))
+            self._stream_set = ptr
 
     def evaluate(self, what: int, x, y=None, obj_weight: float = 1.0, out=None):
         """One fused kernel launch for the outputs selected by `what` (CONS|JAC|HESS|GRAD|OBJ subset).
@@ -212,7 +236,8 @@ class DOCP:
                             (JAC, "jac", self.nnzj), (HESS, "hess", self.nnzh)):
             if what & bit:
                 buf = out.get(key)
-                res[key] = self._check_in(buf, n, key) if buf is not None else self._empty_like(x, n)
+                res[key] = self._check_in(buf, n, key, output=True) if buf is not None else self._empty_like(x, n)
+        self._follow_stream(x)
         fn = self._lib.ctd_eval_dev if dev else self._lib.ctd_eval
         _lib.check(fn(self._h, int(what), _ptr(x), _ptr(y), float(obj_weight), _ptr(res.get("obj")),
                       _ptr(res.get("grad")), _ptr(res.get("cons")), _ptr(res.get("jac")), _ptr(res.get("hess"))))
@@ -232,9 +257,10 @@ class DOCP:
                             (JAC, "jac", self.nnzj), (HESS, "hess", self.nnzh)):
             if what & bit:
                 buf = out.get(key)
-                res[key] = self._check_in(buf, n, key) if buf is not None else self._empty_like(x, n)
+                res[key] = self._check_in(buf, n, key, output=True) if buf is not None else self._empty_like(x, n)
         if viol is None:
             viol = torch.empty(self.batch, dtype=torch.float64, device=x.device)
+        self._follow_stream(x)
         _lib.check(self._lib.ctd_eval_norms_dev(self._h, int(what), _ptr(x), _ptr(y), float(obj_weight),
                                                 _ptr(res.get("obj")), _ptr(res.get("grad")), _ptr(res.get("cons")),
                                                 _ptr(res.get("jac")), _ptr(res.get("hess")), _ptr(viol)))
@@ -254,7 +280,8 @@ class DOCP:
                             (JAC, "jac", self.nnzj), (HESS, "hess", self.nnzh)):
             if what & bit:
                 buf = out.get(key)
-                res[key] = self._check_in(buf, n, key) if buf is not None else self._empty_like(x, n)
+                res[key] = self._check_in(buf, n, key, output=True) if buf is not None else self._empty_like(x, n)
+        self._follow_stream(x)   # (resolved once, here: the callable keeps issuing on that stream)
         fn = self._lib.ctd_eval_dev if dev else (self._lib.ctd_eval if wait else self._lib.ctd_eval_async)
         args = (self._h, int(what), _ptr(x), _ptr(y), C.c_double(float(obj_weight)), _ptr(res.get("obj")),
                 _ptr(res.get("grad")), _ptr(res.get("cons")), _ptr(res.get("jac")), _ptr(res.get("hess")))
@@ -281,9 +308,10 @@ class DOCP:
                             (JAC, "jac", self.nnzj), (HESS, "hess", self.nnzh)):
             if what & bit:
                 buf = out.get(key)
-                res[key] = self._check_in(buf, n, key) if buf is not None else self._empty_like(x, n)
+                res[key] = self._check_in(buf, n, key, output=True) if buf is not None else self._empty_like(x, n)
         if viol is None:
             viol = torch.empty(self.batch, dtype=torch.float64, device=x.device)
+        self._follow_stream(x)
         fn = self._lib.ctd_eval_norms_dev
         args = (self._h, int(what), _ptr(x), _ptr(y), C.c_double(float(obj_weight)), _ptr(res.get("obj")),
                 _ptr(res.get("grad")), _ptr(res.get("cons")), _ptr(res.get("jac")), _ptr(res.get("hess")), _ptr(viol))
@@ -303,6 +331,7 @@ class DOCP:
             import torch
             obj = torch.empty(self.batch, dtype=torch.float64, device=x.device)
             viol = torch.empty(self.batch, dtype=torch.float64, device=x.device)
+            self._follow_stream(x)
             _lib.check(self._lib.ctd_norms_dev(self._h, _ptr(x), _ptr(obj), _ptr(viol)))
         else:
             obj, viol = np.empty(self.batch), np.empty(self.batch)
@@ -315,6 +344,7 @@ class DOCP:
         c = self._check_in(c, self.ncon, "c")
         if viol is None:
             viol = torch.empty(self.batch, dtype=torch.float64, device=c.device)
+        self._follow_stream(c)
         _lib.check(self._lib.ctd_violation_dev(self._h, _ptr(c), _ptr(viol)))
         return viol
 
@@ -340,6 +370,7 @@ class DOCP:
                 out[k] = np.zeros(shp)
             if int(np.prod(shp)) > 0:
                 setattr(sol, k, out[k].data_ptr() if _is_torch(x) else out[k].ctypes.data)
+        self._follow_stream(x)
         fn = self._lib.ctd_unpack_dev if _is_torch(x) else self._lib.ctd_unpack
         _lib.check(fn(self._h, _ptr(x), _ptr(y), C.byref(sol)))
         return out
@@ -368,6 +399,7 @@ class DOCP:
         else:
             x = np.empty(self._shape(self.nvar))
             fn = self._lib.ctd_pack
+        self._follow_stream(*given)
         _lib.check(fn(self._h, *[_ptr(a) for a in args], _ptr(x)))
         return x
 
@@ -409,6 +441,7 @@ class DOCP:
         captured into the caller's CUDA graphs."""
         ptr = getattr(stream, "cuda_stream", stream)
         _lib.check(self._lib.ctd_set_stream(self._h, C.c_void_p(int(ptr)) if ptr else None))
+        self._stream_mode, self._stream_set = "own", None   # an explicit choice: stop following torch's current stream
 
     @property
     def cuda_stream(self) -> int:

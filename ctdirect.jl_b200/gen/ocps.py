@@ -5,7 +5,8 @@ dynamics(t, x, u, v), lagrange(t, x, u, v), mayer(x0, xf, v), path(t, x, u, v), 
 box triplets (lb, index, ub) and the default initial guess.  `p` holds runtime parameters (one row per
 instance in batched mode).  Sources in the reference tree:
   goddard / goddard_all      test/problems/goddard.jl:7-49, 87-158
-  double_integrator_*        test/problems/double_integrator.jl:4-19, 40-56
+  double_integrator_*        test/problems/double_integrator.jl:4-19, 40-56, 79-99 (free t0 and tf)
+  beam                       test/problems/beam.jl:3-17
   stagewise_scalar           test/ci/test_discretization_stagewise.jl:1-14
   bolza_freetf               test/problems/bolza.jl:3-18
   vanderpol                  test/problems/vanderpol.jl:3-19
@@ -140,6 +141,29 @@ double_integrator_mintf = OCP(
     control_box=[(-1.0, 1, 1.0)], variable_box=[(0.05, 1, INF)],
 )
 
+# free initial AND final time, t0 -> max (test/problems/double_integrator.jl:79-99; swept over the six schemes at
+# grid_size 50 by test/ci/test_discretization.jl:74-80).  `0.01 <= tf - t0` is a function of the variable alone:
+# CTModels keeps it with the boundary constraints (functions of (x0, xf, v)), after the two conditions on x.
+double_integrator_freet0tf = OCP(
+    name="double_integrator_freet0tf", nx=2, nu=1, nv=2, params=[], t0=("var", 0), tf=("var", 1),
+    dynamics=lambda t, x, u, v, p: [x[1], u[0]],
+    mayer=lambda x0, xf, v, p: v[0], criterion="max",
+    boundary=lambda x0, xf, v, p: [x0[0], x0[1], xf[0], xf[1], v[1] - v[0]],
+    bc_lb=[0.0, 0.0, 1.0, 0.0, 0.01], bc_ub=[0.0, 0.0, 1.0, 0.0, INF],
+    control_box=[(-1.0, 1, 1.0)], variable_box=[(0.05, 1, 10.0), (0.05, 2, 10.0)],
+)
+
+# beam (from bocop), Lagrange cost with a state box (test/problems/beam.jl:3-17; swept over the six schemes by
+# test/ci/test_discretization.jl:66-72)
+beam = OCP(
+    name="beam", nx=2, nu=1, nv=0, params=[], t0=("const", 0.0), tf=("const", 1.0),
+    dynamics=lambda t, x, u, v, p: [x[1], u[0]],
+    lagrange=lambda t, x, u, v, p: u[0] ** 2,
+    boundary=lambda x0, xf, v, p: [x0[0], x0[1], xf[0], xf[1]],
+    bc_lb=[0.0, 1.0, 0.0, -1.0], bc_ub=[0.0, 1.0, 0.0, -1.0],
+    state_box=[(0.0, 1, 0.1)], control_box=[(-10.0, 1, 10.0)],
+)
+
 stagewise_scalar = OCP(
     name="stagewise_scalar", nx=1, nu=1, nv=0, params=[], t0=("const", 0.0), tf=("const", 1.0),
     dynamics=lambda t, x, u, v, p: [u[0]],
@@ -211,6 +235,7 @@ estimate_rotation_rate = OCP(
 )
 
 ALL = {o.name: o for o in (
-    goddard, goddard_all, double_integrator_minenergy, double_integrator_mintf, stagewise_scalar,
+    goddard, goddard_all, double_integrator_minenergy, double_integrator_mintf, double_integrator_freet0tf, beam,
+    stagewise_scalar,
     bolza_freetf, vanderpol, robot, estimate_initial_condition, estimate_rotation_rate,
 )}

@@ -167,6 +167,8 @@ void* orc_create(const char* problem, const char* scheme, int grid_size, const d
         ORC_P(GoddardAll)
         ORC_P(DoubleIntegratorMinEnergy)
         ORC_P(DoubleIntegratorMinTf)
+        ORC_P(DoubleIntegratorFreeT0Tf)
+        ORC_P(Beam)
         ORC_P(StagewiseScalar)
         ORC_P(BolzaFreeTf)
         ORC_P(VanDerPol)

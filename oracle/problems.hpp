@@ -6,7 +6,7 @@
 //   dynamics(r, t, x, u, v), lagrange(t, x, u, v), mayer(x0, xf, v),
 //   path(r, t, x, u, v), boundary(r, x0, xf, v), box triplets (lb, idx, ub).
 // Sources: reference test/problems/goddard.jl:7-49,87-158,
-//          test/problems/double_integrator.jl:4-19,40-56,
+//          test/problems/double_integrator.jl:4-19,40-56,79-99, test/problems/beam.jl:3-17,
 //          test/ci/test_discretization_stagewise.jl:1-14,
 //          test/problems/bolza.jl:3-18, test/problems/vanderpol.jl:3-19,
 //          test/problems/autonomous_system.jl:6-90.
@@ -198,6 +198,78 @@ struct DoubleIntegratorMinTf {
         m.variable_box = {{0.05, 1, INF}};
         m.bc_lb = {0, 0, 1, 0};
         m.bc_ub = {0, 0, 1, 0};
+        return m;
+    }
+};
+
+// ---------------------------------------------------------------------------
+// Double integrator with free t0 and tf, max t0: double_integrator.jl:79-99
+// (`0.01 <= tf - t0` depends on the variable only: a boundary constraint for CTModels, declared last)
+// ---------------------------------------------------------------------------
+struct DoubleIntegratorFreeT0Tf {
+    static constexpr const char* name = "double_integrator_freet0tf";
+    static constexpr int nx = 2, nu = 1, nv = 2, np = 0, nb = 5, npar = 0;
+    static constexpr bool free_t0 = true, free_tf = true, has_lagrange = false, has_mayer = true,
+                          is_max = true;
+    template <class T> static T t0(const T* v, const double*) { return v[0]; }
+    template <class T> static T tf(const T* v, const double*) { return v[1]; }
+    template <class T>
+    static void dynamics(T* r, const T&, const T* x, const T* u, const T*, const double*) {
+        r[0] = x[1];
+        r[1] = u[0];
+    }
+    template <class T> static T lagrange(const T&, const T*, const T*, const T*, const double*) { return T(0.0); }
+    template <class T> static T mayer(const T*, const T*, const T* v, const double*) { return v[0]; }
+    template <class T> static void path(T*, const T&, const T*, const T*, const T*, const double*) {}
+    template <class T>
+    static void boundary(T* r, const T* x0, const T* xf, const T* v, const double*) {
+        r[0] = x0[0];
+        r[1] = x0[1];
+        r[2] = xf[0];
+        r[3] = xf[1];
+        r[4] = v[1] - v[0];
+    }
+    static ProblemMeta meta() {
+        ProblemMeta m;
+        m.control_box = {{-1.0, 1, 1.0}};
+        m.variable_box = {{0.05, 1, 10.0}, {0.05, 2, 10.0}};
+        m.bc_lb = {0, 0, 1, 0, 0.01};
+        m.bc_ub = {0, 0, 1, 0, INF};
+        return m;
+    }
+};
+
+// ---------------------------------------------------------------------------
+// Beam (bocop), Lagrange cost, state and control boxes: beam.jl:3-17
+// ---------------------------------------------------------------------------
+struct Beam {
+    static constexpr const char* name = "beam";
+    static constexpr int nx = 2, nu = 1, nv = 0, np = 0, nb = 4, npar = 0;
+    static constexpr bool free_t0 = false, free_tf = false, has_lagrange = true, has_mayer = false,
+                          is_max = false;
+    template <class T> static T t0(const T*, const double*) { return T(0.0); }
+    template <class T> static T tf(const T*, const double*) { return T(1.0); }
+    template <class T>
+    static void dynamics(T* r, const T&, const T* x, const T* u, const T*, const double*) {
+        r[0] = x[1];
+        r[1] = u[0];
+    }
+    template <class T> static T lagrange(const T&, const T*, const T* u, const T*, const double*) { return sq(u[0]); }
+    template <class T> static T mayer(const T*, const T*, const T*, const double*) { return T(0.0); }
+    template <class T> static void path(T*, const T&, const T*, const T*, const T*, const double*) {}
+    template <class T>
+    static void boundary(T* r, const T* x0, const T* xf, const T*, const double*) {
+        r[0] = x0[0];
+        r[1] = x0[1];
+        r[2] = xf[0];
+        r[3] = xf[1];
+    }
+    static ProblemMeta meta() {
+        ProblemMeta m;
+        m.state_box = {{0.0, 1, 0.1}};
+        m.control_box = {{-10.0, 1, 10.0}};
+        m.bc_lb = {0, 1, 0, -1};
+        m.bc_ub = {0, 1, 0, -1};
         return m;
     }
 };

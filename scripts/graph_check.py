@@ -8,7 +8,7 @@ NS = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 ROUNDS = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 K = 600
 dev = torch.device("cuda", 0)
-docps = [ctd.DOCP("goddard", 100000, "midpoint") for _ in range(NS)]
+docps = [ctd.DOCP("goddard", 100000, "midpoint", stream="own") for _ in range(NS)]
 d0 = docps[0]
 streams = [torch.cuda.ExternalStream(d.cuda_stream, device=dev) for d in docps]
 rng = np.random.default_rng(0)

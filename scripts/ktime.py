@@ -9,7 +9,7 @@ scheme = sys.argv[2] if len(sys.argv) > 2 else "midpoint"
 N = int(sys.argv[3]) if len(sys.argv) > 3 else 100000
 batch = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 mode = sys.argv[5] if len(sys.argv) > 5 else "reference"
-d = ctd.DOCP(problem, N, scheme, batch=batch, pattern_mode=mode)
+d = ctd.DOCP(problem, N, scheme, batch=batch, pattern_mode=mode, stream="own")
 dev = torch.device("cuda", 0)
 rng = np.random.default_rng(0)
 x0 = d.initial_guess()
@@ -29,7 +29,7 @@ for s in range(nsets):
     sets.append((x, y, out))
 stream = torch.cuda.ExternalStream(d.cuda_stream, device=dev)
 NS = int(os.environ.get("KTIME_STREAMS", "1"))           # independent evaluations in flight
-extra = [ctd.DOCP(problem, N, scheme, batch=batch, pattern_mode=mode) for _ in range(NS - 1)]
+extra = [ctd.DOCP(problem, N, scheme, batch=batch, pattern_mode=mode, stream="own") for _ in range(NS - 1)]
 handles = [d] + extra
 streams = [torch.cuda.ExternalStream(h.cuda_stream, device=dev) for h in handles]
 # reference floor: a device-to-device copy moving the same number of bytes as the fused evaluation

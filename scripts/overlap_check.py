@@ -8,7 +8,7 @@ F = ctd.CONS | ctd.JAC | ctd.HESS
 dev = torch.device("cuda", 0)
 rng = np.random.default_rng(0)
 def make(nsets):
-    d = ctd.DOCP("goddard", N, "midpoint")
+    d = ctd.DOCP("goddard", N, "midpoint", stream="own")
     x0 = d.initial_guess()
     calls = []
     keep = []

@@ -8,7 +8,7 @@ import ctdirect_b200 as ctd
 PROB = sys.argv[3] if len(sys.argv) > 3 else "goddard"
 SCH = sys.argv[4] if len(sys.argv) > 4 else "midpoint"
 NN = int(sys.argv[5]) if len(sys.argv) > 5 else 100000
-d = ctd.DOCP(PROB, NN, SCH)
+d = ctd.DOCP(PROB, NN, SCH, stream="own")
 dev = torch.device("cuda", 0)
 rng = np.random.default_rng(0)
 x = torch.from_numpy(d.initial_guess() * (1 + 1e-3 * rng.uniform(-1, 1, d.nvar))).to(dev)

@@ -57,6 +57,29 @@ def column_scale(structure, ref, n, symmetric=False):
     return cmax[cols]
 
 
+def hess_scale(o, x, y, sigma, h_ref):
+    """Per-entry tolerance floor for Lagrangian-Hessian values: the larger of the column scale and the sum of the
+    MAGNITUDES of the contributions that are added up to form the entry, one contribution per constraint-row
+    type of a step (state equations, stage equations, path constraints: `o.cblock` of them) and step parity,
+    plus the boundary rows and the cost.  An entry is a sum over rows with multipliers of either sign: at a 3-stage Gauss-Legendre
+    step of Goddard three stage contributions of -2249.4, -522.2 and +2772.8 leave 1.147, and 1e-12 of THAT is
+    below one ulp of the terms.  `o` is the oracle model (test infrastructure)."""
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    terms = np.zeros_like(np.asarray(h_ref, dtype=np.float64))
+    nstep = o.N * o.cblock
+    for r in range(o.cblock):
+        for parity in (0, 1):   # neighbouring steps add into the same entries of the block they share
+            yy = np.zeros_like(y)
+            sl = slice(r + parity * o.cblock, nstep, 2 * o.cblock)
+            yy[sl] = y[sl]
+            terms += np.abs(o.derivs(x, yy, 0.0, want=("hess",))[2])
+    yy = np.zeros_like(y)
+    yy[nstep:] = y[nstep:]
+    terms += np.abs(o.derivs(x, yy, sigma, want=("hess",))[2])
+    return np.maximum(column_scale(o.hess_structure(), h_ref, o.nvar, symmetric=True), terms)
+
+
 WORST = {}   # kind ("jac", "hess", ...) -> (largest pure relative error seen, where)
 
 

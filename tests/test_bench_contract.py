@@ -38,3 +38,17 @@ def test_gpu_arm_fails_loudly_without_a_device():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True,
                        timeout=300, cwd=ROOT)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_reference_arm_batched_metric_with_more_than_one_rank():
+    """At N > 1 both arms report the batched metric (BASELINE.json: "batched evals/s at 1/2/4/8 B200")."""
+    env = dict(os.environ, RANK="0", LOCAL_RANK="0", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"].startswith("batched evals/s") and d["scaling"] == "strong"
+    assert d["n_gpus"] == 2 and d["value"] > 0 and "4096" in d["config"]["workload"]
+    assert d["cpu_baseline"]["kind"] == "port" and "64 of the 4096 instances" in d["cpu_baseline"]["sample"]
