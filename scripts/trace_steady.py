@@ -53,3 +53,18 @@ print(f"period (dep_resolved K - dep_resolved K-1): {(np.median(b[1][:, 7]) - np
 for a_, b_ in ((7, 1), (1, 2), (2, 3), (3, 4), (4, 6)):
     v = (b[1][:, b_] - b[1][:, a_]) / 1e3
     print(f"  K: {names[a_]:>20s} -> {names[b_]:20s} p50 {np.median(v):6.2f} p90 {np.percentile(v, 90):6.2f} max {v.max():6.2f}")
+
+# per-SM view of launch K (slot 5 holds %smid)
+tk = b[1]
+sm = tk[:, 5].astype(int)
+dep = np.median(tk[:, 7])
+life = (tk[:, 6] - dep) / 1e3
+cnt = np.bincount(sm, minlength=148)
+print("warps per SM: min", cnt[cnt > 0].min(), "max", cnt.max(), "SMs used", int((cnt > 0).sum()))
+for n in sorted(set(cnt[cnt > 0])):
+    sel = np.isin(sm, np.where(cnt == n)[0])
+    print(f"  SMs with {n:2d} tile warps: {int((cnt == n).sum()):3d} SMs; warp end after dep_resolved: p50 {np.median(life[sel]):5.2f} p90 {np.percentile(life[sel], 90):5.2f} max {life[sel].max():5.2f}")
+sm_last = np.array([life[sm == q].max() if (sm == q).any() else 0 for q in range(148)])
+print("last warp per SM (us after dep_resolved): min", sm_last[sm_last > 0].min().round(2), "p50", np.median(sm_last[sm_last > 0]).round(2), "max", sm_last.max().round(2))
+slow = np.argsort(-sm_last)[:8]
+print("slowest SMs:", [(int(q), int(cnt[q]), float(sm_last[q].round(2))) for q in slow])
