@@ -562,9 +562,21 @@ def leg_batched(cx, ctd):
         legs["all-gather of evaluation k overlaps the kernel of evaluation k+1, both issued by the library "
              "(ctd_gather_norms_dev on the handle's communication stream, 2 slots)"] = \
             timed_b(lambda: npipe.submit(ALL, tx, ty, bout), npipe.drain)
+        ppipe = None
+        try:
+            from ctdirect_b200.batch import PeerNormsPipeline
+            ppipe = PeerNormsPipeline(bd, rank, world, b"", depth=2, n_instances=bl * world)   # (communicator already joined)
+        except Exception as ex:   # no peer access between the GPUs of this box: the NCCL schedules stand
+            print(f"[bench] fused peer gather unavailable: {ex}", file=sys.stderr)
+        ok = cx.max_over_ranks(0.0 if ppipe is not None else 1.0) == 0.0
+        if ok:
+            legs["kernel with fused peer-memory gather, then wait for all ranks (ctd_eval_gather_dev + ctd_peer_wait)"] = \
+                timed_b(lambda: ppipe.submit(ALL, tx, ty, bout, serial=True), ppipe.drain)
+            legs["kernel with fused peer-memory gather; the norms of evaluation k are awaited after evaluation k+1 is queued "
+                 "(ctd_eval_gather_dev, 2 slots)"] = timed_b(lambda: ppipe.submit(ALL, tx, ty, bout), ppipe.drain)
     best_how = min(legs, key=lambda k_: legs[k_])
     best = legs[best_how]
-    serial_best = min(v for k_, v in legs.items() if k_.startswith("kernel then"))
+    serial_best = min(v for k_, v in legs.items() if k_.startswith("kernel then") or "then wait for all ranks" in k_)
     ach = bbytes / (kms * 1e-3 / bsteps) / 1e9
     res = {"workload": batched_workload_text(world), "steps": bsteps, "scaling": "strong",
            "batched_evals_per_s": bsteps / (best * 1e-3), "instance_evals_per_s": B_TOTAL * bsteps / (best * 1e-3),

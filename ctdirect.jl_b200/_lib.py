@@ -56,6 +56,9 @@ SIGNATURES = {
     "ctd_eval": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_double] + [C.c_void_p] * 5),
     "ctd_eval_async": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_double] + [C.c_void_p] * 5),
     "ctd_eval_dev": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_double] + [C.c_void_p] * 5),
+    "ctd_peer_init": (C.c_int, [_H]),
+    "ctd_eval_gather_dev": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_double] + [C.c_void_p] * 4 + [C.c_int32]),
+    "ctd_peer_wait": (C.c_int, [_H, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "ctd_eval_norms_dev": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_double] + [C.c_void_p] * 6),
     "ctd_norms_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ctd_violation_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p]),

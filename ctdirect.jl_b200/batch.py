@@ -200,6 +200,66 @@ class NativeNormsPipeline:
             self.docp.comm_wait(s)
 
 
+class PeerNormsPipeline:
+    """The norm gather fused into the evaluation kernel over NVLink peer memory: one C call per step issues the
+    evaluation, whose reduction epilogue stores every instance's (objective, violation) into the gather buffer of
+    every rank (ctd_eval_gather_dev); `result(slot)` enqueues the wait for all ranks' arrival flags (a one-warp
+    kernel) and returns the (world, 2, batch) view.  No collective call, no second stream.
+
+        pipe = PeerNormsPipeline(docp, rank, world, unique_id)
+        slot = pipe.submit(what, x, y, out)      # evaluation k; its norms travel while evaluation k+1 runs
+        norms = pipe.result(slot)                # valid on the handle's stream
+    A slot is reused `depth` steps later; every rank must have waited for it by then (`submit` does, like
+    NativeNormsPipeline)."""
+
+    def __init__(self, docp, rank: int, world: int, unique_id: bytes, depth: int = 2, n_instances: Optional[int] = None):
+        if not (1 <= depth <= 4):
+            raise ValueError("depth must be 1..4 (CTD_COMM_SLOTS)")
+        if n_instances is not None and docp.batch * world != n_instances:
+            raise ValueError(f"shards must have the same size on every rank: {n_instances} instances over {world} ranks "
+                             f"with {docp.batch} here")
+        self.docp, self.world, self.depth, self.k = docp, world, depth, 0
+        if not getattr(docp, "comm_world", None):
+            docp.comm_init(unique_id, rank, world)
+        docp.peer_init()
+        self._bound = {}
+        self._pending = [False] * depth
+        self._view = [None] * depth
+
+    def submit(self, what: int, x, y=None, out=None, obj_weight: float = 1.0, serial: bool = False) -> int:
+        s = self.k % self.depth
+        self.k += 1
+        # (no host-side wait for the slot's previous round: the launch itself waits, in its first CTA, until every rank --
+        #  this one included -- has copied that round out; whoever reads a slot does so through result() before the
+        #  slot comes round again)
+        key = (s, what, x.data_ptr(), 0 if y is None else y.data_ptr(), obj_weight,
+               tuple(sorted((k, v.data_ptr()) for k, v in (out or {}).items() if k != "obj")))
+        call = self._bound.get(key)
+        if call is None:
+            o = {k: v for k, v in (out or {}).items() if k != "obj"}
+            call = self.docp.bind_gather(what, x, y, obj_weight, out=o, slot=s)[0]
+            self._bound[key] = call
+        call()
+        if serial:
+            self._view[s] = self.docp.peer_wait(s)                     # on the evaluation stream: what follows sees the norms
+        else:
+            self._view[s] = self.docp.peer_wait(s, overlapped=True)    # beside the next evaluation
+            self._pending[s] = True
+        return s
+
+    def result(self, slot: int):
+        if self._pending[slot]:
+            self.docp.comm_wait(slot)
+            self._pending[slot] = False
+        return self._view[slot]
+
+    def drain(self):
+        for s in range(self.depth):
+            if self._pending[s]:
+                self.docp.comm_wait(s)
+                self._pending[s] = False
+
+
 def bind_to_gpu_numa_node(device_index: int) -> dict:
     """Pin the calling process to the CPUs of the NUMA node its GPU hangs off, so that the pinned host
     buffers it allocates afterwards (first touch) and the threads that feed the GPU sit next to the GPU's PCIe

@@ -301,4 +301,23 @@ int ctd_comm_wait(ctd_handle h, int32_t slot) {
     return guarded([&] { h->m->comm_wait(slot); });
 }
 
+int ctd_peer_init(ctd_handle h) {
+    if (int e = check(h)) return e;
+    return guarded([&] { h->m->peer_init(); });
+}
+
+int ctd_eval_gather_dev(ctd_handle h, int what, const double* x, const double* y, double obj_weight, double* g,
+                        double* c, double* jvals, double* hvals, int32_t slot) {
+    if (int e = check(h)) return e;
+    return guarded([&] { h->m->eval_gather_dev(what, x, y, obj_weight, g, c, jvals, hvals, slot); });
+}
+
+int ctd_peer_wait(ctd_handle h, int32_t slot, int32_t overlapped, const double** gathered) {
+    if (int e = check(h)) return e;
+    return guarded([&] {
+        const double* p = h->m->peer_wait(slot, overlapped != 0);
+        if (gathered) *gathered = p;
+    });
+}
+
 }  // extern "C"

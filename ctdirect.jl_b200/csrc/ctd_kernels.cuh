@@ -68,6 +68,20 @@ struct EvalArgs {
     double* viol;                 // [batch] max(lcon - c, c - ucon, 0) per instance, or nullptr
     double* partials;             // [batch][ctas][NREDX]
     unsigned int* counters;       // [batch]
+    // fused norm gather over peer memory (multi-GPU batches, ctd_eval_gather_dev; peer_base == nullptr otherwise): as
+    // soon as an instance is reduced, its (objective, violation) go into the gather buffer of EVERY rank as two
+    // self-validating 16-byte records {bits(v), bits(v) ^ key} (NVLink peer stores, posted: no fence, no flag, no
+    // counter).  `key` changes with every launch, so the consumer (ctd_peer_wait_kernel) tells a record of this round
+    // from what the slot held before, and a torn read never validates.
+    double* const* peer_base;     // [peer_world] base of every rank's gather buffer (peer-mapped device pointers)
+    long long peer_rec;           // offset (doubles) of this rank's records [2][batch] for the slot in use
+    unsigned long long peer_key, peer_epoch;
+    int peer_world;
+    // slot recycling: a rank acknowledges a round when its consumer has copied the slot out (ctd_peer_wait_kernel);
+    // the first CTA of the launch waits for every rank's acknowledgement of the slot's previous round in the LOCAL ack
+    // table (normally long there) and opens the gate for the pushers of this launch
+    const unsigned long long* peer_ack_local;
+    unsigned long long* peer_gate;
     // edge tables (identical for every instance)
     const int* edge_map;
     const long long* edge_pos;    // destination position of every edge-buffer entry
@@ -430,6 +444,18 @@ __device__ void edge_cta(const EvalArgs& a, const double* __restrict__ x, const 
     for (int k = tid; k < ne; k += T) spos[k] = __ldg(a.edge_pos + k);
     for (int k = tid; k < EDGE_LAYERS * ne; k += T) buf[k] = 0.0;
     pdl_entry();
+    if (a.peer_base && blockIdx.y == 0 && tid < 32) {   // slot recycling of the fused gather (see EvalArgs)
+        if (tid < a.peer_world) {
+            for (int spin = 0; spin < (1 << 23); ++spin) {   // (bounded: ~2 s; a dead rank must not hang this one)
+                unsigned long long ak;
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(ak) : "l"(a.peer_ack_local + tid) : "memory");
+                if (ak + 1 >= a.peer_epoch) break;
+                __nanosleep(200);
+            }
+        }
+        __syncwarp();
+        if (tid == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(a.peer_gate), "l"(a.peer_epoch) : "memory");
+    }
     __syncthreads();
     {
         // warp roles: the step elements of all edge tasks run side by side in the lanes of one warp
@@ -694,19 +720,40 @@ __device__ __forceinline__ void publish_reduction(const EvalArgs& a, const doubl
                 for (int j = 0; j < 16; ++j) acc[k] = comb(k, acc[k], t[j]);
             }
         }
+        double violv = 0.0;
 #pragma unroll
         for (int k = 0; k < NR; ++k) {
             double v = acc[k];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v = comb(k, v, __shfl_xor_sync(0xffffffffu, v, o));
             if (lane == 0) {
-                if (C::WV && k == C::R_V) { if (a.viol) a.viol[inst] = v; }
+                if (C::WV && k == C::R_V) { violv = v; if (a.viol) a.viol[inst] = v; }
                 else if (C::RH && k < C::R_G) { if (a.hvv_pos[k - C::R_H] >= 0) hvals[a.hvv_pos[k - C::R_H]] = v; }
                 else if (C::RG && k < C::R_O) grad[a.nvar - E::NV + (k - C::R_G)] = v;
                 else if (C::RO && a.obj) a.obj[inst] = v;
             }
         }
         if (lane == 0) a.counters[inst] = 0u;
+        if constexpr (C::WV) {
+            if (a.peer_base && lane == 0) {
+                // ---- fused gather: the two records of this instance go to every rank (see EvalArgs).  The objective was
+                //      summed above or written by the boundary job of the instance's edge CTA, whose ticket this CTA has seen.
+                const long long nb = (long long)gridDim.y;
+                const unsigned long long ob = (unsigned long long)__double_as_longlong(a.obj ? __ldcg(a.obj + inst) : 0.0);
+                const unsigned long long vb = (unsigned long long)__double_as_longlong(violv);
+                for (int spin = 0; spin < (1 << 23); ++spin) {   // the gate of this launch (opened by its first CTA)
+                    unsigned long long g;
+                    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(g) : "l"(a.peer_gate) : "memory");
+                    if (g >= a.peer_epoch) break;
+                    __nanosleep(200);
+                }
+                for (int pr_ = 0; pr_ < a.peer_world; ++pr_) {
+                    double* rec = a.peer_base[pr_] + a.peer_rec;
+                    asm volatile("st.global.v2.u64 [%0], {%1, %2};" :: "l"(rec + 2 * inst), "l"(ob), "l"(ob ^ a.peer_key) : "memory");
+                    asm volatile("st.global.v2.u64 [%0], {%1, %2};" :: "l"(rec + 2 * (nb + inst)), "l"(vb), "l"(vb ^ a.peer_key) : "memory");
+                }
+            }
+        }
     }
 }
 

@@ -626,6 +626,14 @@ void Model::sync() {
     if (dev_ready_) {
         CTD_CUDA(cudaSetDevice(device_));
         CTD_CUDA(cudaStreamSynchronize(stream_));
+        if (d_peer_err_) {
+            int e = 0;
+            CTD_CUDA(cudaMemcpy(&e, d_peer_err_, sizeof(int), cudaMemcpyDeviceToHost));
+            if (e) {
+                cudaMemset(d_peer_err_, 0, sizeof(int));
+                throw CtdError{-8, "ctd_peer_wait: rank " + std::to_string(e - 1) + " did not deliver its norms within 5 s"};
+            }
+        }
     }
 }
 
@@ -674,6 +682,10 @@ void Model::eval_dev(int flags, const double* x, const double* y, double sigma, 
     if ((flags & F_GRAD) && !grad) throw CtdError{-2, "grad is NULL"};
     EvalArgs a = base_args();
     a.x = x; a.y = y; a.sigma = sigma; a.obj = obj; a.grad = grad; a.c = c; a.jvals = jvals; a.hvals = hvals; a.viol = viol;
+    if (peer_push_) {   // ctd_eval_gather_dev: the reduction epilogue also pushes the norms to every rank
+        if (!(flags & F_VIOL)) throw CtdError{-6, "the fused gather needs the in-kernel violation norm (light elements)"};
+        peer_args(a);
+    }
     // warps per CTA: large CTAs for a single instance (a 1e5-step grid is one wave and CTA launch rate
     // matters), small CTAs for batches (many waves: resources are released per CTA, and the tiles of
     // an instance rarely fill a large CTA)

@@ -122,6 +122,11 @@ class Model {
     void gather_norms_dev(const double* local, double* gathered, int slot);
     void comm_wait(int slot);
     int comm_world() const { return comm_world_; }
+    // fused norm gather over peer memory (ctd_comm.cu)
+    void peer_init();
+    void eval_gather_dev(int flags, const double* x, const double* y, double sigma, double* grad, double* c, double* jvals,
+                         double* hvals, int slot);
+    const double* peer_wait(int slot, bool overlapped);   // enqueues the consumer; returns the [world][2][batch] rows of the slot
 
   private:
     void build_patterns();
@@ -166,6 +171,19 @@ class Model {
     cudaStream_t comm_stream_ = nullptr;
     cudaEvent_t ev_issue_ = nullptr, ev_gathered_[kCommSlots] = {};
     bool slot_used_[kCommSlots] = {};
+    // peer-memory gather
+    struct PeerPush { int slot; unsigned long long epoch; };
+    void peer_destroy();
+    size_t peer_records() const;
+    size_t peer_results() const;
+    void peer_args(EvalArgs& a) const;
+    double* peer_local_ = nullptr;            // this rank's gather buffer (values, then arrival flags)
+    std::vector<double*> peer_base_;          // every rank's buffer as mapped here
+    double** d_peer_base_ = nullptr;
+    unsigned long long* d_peer_gate_ = nullptr;
+    int* d_peer_err_ = nullptr;
+    unsigned long long peer_epoch_[kCommSlots] = {};
+    const PeerPush* peer_push_ = nullptr;     // set while eval_gather_dev builds its launch
 };
 
 void nccl_unique_id(char* id);   // kNcclIdBytes bytes

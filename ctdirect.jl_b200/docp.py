@@ -435,6 +435,56 @@ class DOCP:
         """Make this handle's stream wait until the gather that last used `slot` has landed."""
         _lib.check(self._lib.ctd_comm_wait(self._h, int(slot)))
 
+    # ---- fused norm gather over peer memory (ctd_peer_* of the C ABI) -----------------------------------------
+    def peer_init(self):
+        """Map every rank's gather buffer into every rank (after `comm_init`; all ranks call it)."""
+        _lib.check(self._lib.ctd_peer_init(self._h))
+        self._peer_views = {}
+
+    def bind_gather(self, what: int, x, y=None, obj_weight: float = 1.0, out=None, slot: int = 0):
+        """`bind_with_norms` whose launch also pushes (objective, violation) of every instance into slot `slot` of
+        every rank's gather buffer (ctd_eval_gather_dev).  Returns (callable, result dict)."""
+        x = self._check_in(x, self.nvar, "x")
+        y = self._check_in(y, self.ncon, "y")
+        if not _is_torch(x) or not (what & CONS) or not (what & OBJ):
+            raise TypeError("bind_gather needs CUDA tensors and CONS, OBJ among the outputs")
+        out = dict(out or {})
+        res = {}
+        for bit, key, n in ((GRAD, "grad", self.nvar), (CONS, "cons", self.ncon), (JAC, "jac", self.nnzj), (HESS, "hess", self.nnzh)):
+            if what & bit:
+                buf = out.get(key)
+                res[key] = self._check_in(buf, n, key, output=True) if buf is not None else self._empty_like(x, n)
+        self._follow_stream(x)
+        fn = self._lib.ctd_eval_gather_dev
+        args = (self._h, int(what), _ptr(x), _ptr(y), C.c_double(float(obj_weight)), _ptr(res.get("grad")),
+                _ptr(res.get("cons")), _ptr(res.get("jac")), _ptr(res.get("hess")), C.c_int32(int(slot)))
+        keep = (x, y, res)
+
+        def call(_fn=fn, _args=args, _keep=keep):
+            code = _fn(*_args)
+            if code != 0:
+                _lib.check(code)
+
+        return call, res
+
+    def peer_wait(self, slot: int = 0, overlapped: bool = False):
+        """Enqueue the consumer of `slot` (waits for all ranks' norms, copies them out, acknowledges the round) on this
+        handle's stream, or with `overlapped` on its communication stream (`comm_wait(slot)` then joins it); returns the
+        (world, 2, batch) CUDA tensor view of the slot."""
+        import torch
+        ptr = C.c_void_p()
+        _lib.check(self._lib.ctd_peer_wait(self._h, C.c_int32(int(slot)), C.c_int32(1 if overlapped else 0), C.byref(ptr)))
+        view = self._peer_views.get(slot)
+        if view is None or view[0] != ptr.value:
+            class _Dev:   # a foreign device pointer as a tensor (CUDA array interface)
+                pass
+            d = _Dev()
+            d.__cuda_array_interface__ = {"shape": (self.comm_world, 2, self.batch), "typestr": "<f8",
+                                          "data": (int(ptr.value), False), "version": 3, "strides": None}
+            view = (ptr.value, torch.as_tensor(d, device=torch.device("cuda", self.device)))
+            self._peer_views[slot] = view
+        return view[1]
+
     def set_stream(self, stream=None):
         """Run this handle's work on a caller-owned CUDA stream (a `torch.cuda.Stream`, a raw cudaStream_t as int,
         or None for the handle's own stream): evaluations then follow the caller's stream order and can be

@@ -204,6 +204,25 @@ CTD_API int ctd_comm_init(ctd_handle h, const char id[CTD_NCCL_ID_BYTES], int32_
 CTD_API int ctd_gather_norms_dev(ctd_handle h, const double* local, double* gathered, int32_t slot);
 CTD_API int ctd_comm_wait(ctd_handle h, int32_t slot);
 
+/* ---- fused gather over peer memory (NVLink): the same exchange without a collective call.  After ctd_comm_init,
+ * ctd_peer_init maps a gather buffer of every rank into every other rank (CUDA IPC handles exchanged over the
+ * communicator; all ranks call it).  ctd_eval_gather_dev is ctd_eval_norms_dev whose reduction epilogue stores the
+ * (objective, violation) of every instance straight into slot `slot` of EVERY rank's buffer and raises this rank's
+ * arrival flag there when its shard is complete (CTD_CONS and CTD_OBJ must be among the outputs; light elements).
+ * ctd_peer_wait enqueues the consumer -- a one-CTA kernel that polls the slot's records of all ranks until they
+ * validate, copies them out and acknowledges the round to every rank -- and returns the slot's rows: world x 2 x batch
+ * doubles, rank-major like ctd_gather_norms_dev.  overlapped = 0: on the handle's stream (what follows on the stream
+ * sees the rows: the serial schedule); overlapped = 1: on the handle's communication stream; the work issued so
+ * far is NOT awaited: the records are keyed by the launch, the consumer may poll from any time on, and the evaluation
+ * stream keeps its evaluations back to back -- ctd_comm_wait(h, slot) joins it (the pipelined schedule).
+ * A slot may be pushed again only after its ctd_peer_wait has been issued on every rank (a launch that pushes waits,
+ * in its first CTA, for the acknowledgements of the slot's previous round; 4 slots).  A rank that never delivers is
+ * reported by ctd_sync after 5 s.  Not capturable into CUDA graphs (the launch carries an epoch and a key). */
+CTD_API int ctd_peer_init(ctd_handle h);
+CTD_API int ctd_eval_gather_dev(ctd_handle h, int what, const double* x, const double* y, double obj_weight, double* g,
+                                double* c, double* jvals, double* hvals, int32_t slot);
+CTD_API int ctd_peer_wait(ctd_handle h, int32_t slot, int32_t overlapped, const double** gathered);
+
 #ifdef __cplusplus
 }
 #endif

@@ -397,7 +397,7 @@ def test_native_norm_gather_single_rank(ctd):
     d.synchronize()
 
 
-def _native_gather_worker(rank, world, port, q):
+def _native_gather_worker(rank, world, port, q, kind="native", rounds=3):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -406,18 +406,18 @@ def _native_gather_worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)   # only carries the 128-byte NCCL id
     try:
         import ctdirect_b200 as ctd
-        from ctdirect_b200.batch import NativeNormsPipeline, broadcast_unique_id, shard_range
+        from ctdirect_b200.batch import NativeNormsPipeline, PeerNormsPipeline, broadcast_unique_id, shard_range
         B, N = 8, 120
         rng = np.random.default_rng(3)
         par = np.tile(np.array([310.0, 500.0, 2.0, 3.5]), (B, 1))
         par[:, 3] = rng.uniform(1.0, 3.5, B)
         lo, hi = shard_range(B, world, rank)
         d = ctd.DOCP("goddard", N, "midpoint", params=par[lo:hi], batch=hi - lo, device=rank)
-        pipe = NativeNormsPipeline(d, rank, world, broadcast_unique_id(), depth=2)
+        pipe = (PeerNormsPipeline if kind == "peer" else NativeNormsPipeline)(d, rank, world, broadcast_unique_id(), depth=2)
         dev = torch.device("cuda", rank)
         x_all = np.tile(d.initial_guess(), (B, 1)) * (1 + 1e-3 * rng.uniform(-1, 1, (B, d.nvar)))
         res = []
-        for k in range(3):
+        for k in range(rounds):
             xk = torch.from_numpy(np.ascontiguousarray(x_all[lo:hi] * (1 + 1e-4 * k))).to(dev)
             s = pipe.submit(ctd.CONS | ctd.OBJ, xk)
             g = pipe.result(s)
@@ -461,6 +461,41 @@ def test_native_norm_gather_two_ranks(ctd):
             g = out[rank][k]                    # (world, 2, 4)
             assert_close(g[:, 0, :].reshape(-1), obj, scale=1.0, what=f"rank {rank} evaluation {k}: objectives")
             assert_close(g[:, 1, :].reshape(-1), viol, scale=1.0, what=f"rank {rank} evaluation {k}: violations")
+
+
+@pytest.mark.gpu
+def test_peer_memory_gather_two_ranks(ctd):
+    """The gather fused into the evaluation kernel (NVLink peer stores from the reduction epilogue, ctd_eval_gather_dev):
+    over 7 rounds on 2 slots (every slot recycled three times) each rank holds the rows of both shards, bit-identical
+    to a single-process evaluation of the whole batch.  Skipped on a one-GPU box."""
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    R = 7
+    procs = [mpc.Process(target=_native_gather_worker, args=(r, 2, port, q, "peer", R)) for r in range(2)]
+    for p_ in procs:
+        p_.start()
+    out = dict(q.get(timeout=180) for _ in range(2))
+    for p_ in procs:
+        p_.join(timeout=60)
+        assert p_.exitcode == 0
+    B, N = 8, 120
+    rng = np.random.default_rng(3)
+    par = np.tile(np.array([310.0, 500.0, 2.0, 3.5]), (B, 1))
+    par[:, 3] = rng.uniform(1.0, 3.5, B)
+    d = ctd.DOCP("goddard", N, "midpoint", params=par, batch=B)
+    x_all = np.tile(d.initial_guess(), (B, 1)) * (1 + 1e-3 * rng.uniform(-1, 1, (B, d.nvar)))
+    for k in range(R):
+        obj, viol = d.norms(np.ascontiguousarray(x_all * (1 + 1e-4 * k)))
+        for rank in (0, 1):
+            g = out[rank][k]                    # (world, 2, 4)
+            assert np.array_equal(g[:, 0, :].reshape(-1), obj), f"rank {rank} round {k}: objectives"
+            assert np.array_equal(g[:, 1, :].reshape(-1), viol), f"rank {rank} round {k}: violations"
 
 
 @pytest.mark.gpu
