@@ -235,12 +235,29 @@ __device__ __forceinline__ int phase_of(const double* g) {
 // A staged range of n >= 1 doubles, destination g (8-byte aligned), staged copy s with the SAME 16-byte phase
 // as g (s_u32 = its shared-memory address).  The 16-byte-aligned body goes through the copy engine (issued by
 // the elected lane), the at most one leading and one trailing double are stored directly (by lane 1).
+// The results stream out once and are not read again by the kernels: they are written with the L2 evict-first
+// policy, so that what every launch re-reads (its own code, the time grid, parameters, edge tables) is not pushed out
+// of the 126 MB L2 by the results of earlier evaluations.
+#ifndef CTD_EVICT_FIRST
+#define CTD_EVICT_FIRST 1
+#endif
+__device__ __forceinline__ unsigned long long evict_first_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ void bulk_body(double* __restrict__ g, unsigned int s_u32, int n) {
     const int ph = phase_of(g);
     const int body = (n - ph) >> 1;
-    if (body > 0)
+    if (body > 0) {
+#if CTD_EVICT_FIRST
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                     :: "l"(g + ph), "r"(s_u32 + 8u * (unsigned int)ph), "r"(body << 4), "l"(evict_first_policy()) : "memory");
+#else
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                      :: "l"(g + ph), "r"(s_u32 + 8u * (unsigned int)ph), "r"(body << 4) : "memory");
+#endif
+    }
 }
 __device__ __forceinline__ void ragged_ends(double* __restrict__ g, const double* __restrict__ s, int n) {
     const int ph = phase_of(g);
@@ -933,7 +950,10 @@ struct PCfg {
     // one phase: c | J | Jv | H | g     two phases: A = c | J | Jv | g, B = H (from 0)
     static constexpr int S_H = TWO ? 0 : A_END0;
     static constexpr int S_G = TWO ? A_END0 : A_END0 + H_LEN;
-    static constexpr int S_RED0 = TWO ? ((A_END0 + G_LEN) > H_LEN ? (A_END0 + G_LEN) : H_LEN) : A_END0 + H_LEN + G_LEN;
+    static constexpr int S_OUT = TWO ? ((A_END0 + G_LEN) > H_LEN ? (A_END0 + G_LEN) : H_LEN) : A_END0 + H_LEN + G_LEN;
+    // the tile's inputs are staged at the start of the same region before any output is (see the kernel)
+    static constexpr int S_IN = even((OWN + 1) * E::BLK + E::NNEXT) + even((OWN + 1) * E::CB);
+    static constexpr int S_RED0 = S_OUT > S_IN ? S_OUT : S_IN;
     static constexpr int S_RED = (S_RED0 + 1) & ~1;
     static constexpr int S_END = S_RED + P * (C::NREDX > 0 ? C::NREDX : 1) + 2;
     static constexpr size_t TILE_SMEM = (size_t)S_END * sizeof(double);
@@ -1079,12 +1099,32 @@ __global__ void __launch_bounds__(PCfg<E, F>::T, PCfg<E, F>::MINB) ctd_eval_kern
         edge_cta<E, F>(a, x, y, p, c, jvals, hvals, grad, (C::WO && a.obj) ? a.obj + inst : nullptr, smem, red, PC::P);
         CTD_STAMP(4);
     } else {
-        pdl_entry();
         const long long i0 = 2 + (long long)(cta - 1) * PC::OWN;
         const long long left = (long long)a.N - 1 - i0 + 1;
         const int nown = (int)(left < PC::OWN ? (left < 0 ? 0 : left) : PC::OWN);
         const long long i = i0 - 1 + lane;
         const bool active = nown > 0 && lane <= nown;
+        // ---- the tile's inputs: the x blocks of steps i0-1 .. i0-1+nown (+ the head of the next block) and the matching
+        //      rows of y are two contiguous ranges.  They are prefetched into L2 before the grid dependency is resolved and
+        //      then staged in shared memory with coalesced loads by the whole CTA: a wide step block read per lane touches
+        //      one 128-byte line per lane and per value (3-stage IRK: 13 + 12 values per step, ~700 L1 wavefronts per warp,
+        //      2 us of the tile's 12 us); staged, each lane picks its values from shared memory without bank conflicts
+        //      for odd block sizes.  (The staging area is the start of the output region, overwritten after a barrier.)
+        const int nxt = nown > 0 ? (nown + 1) * E::BLK + E::NNEXT : 0;
+        const int nyt = (nown > 0 && C::WH && y) ? (nown + 1) * E::CB : 0;
+        const double* __restrict__ xb = x + (i0 - 2) * E::BLK;
+        const double* __restrict__ yb = y ? y + (i0 - 2) * E::CB : nullptr;
+        for (int o = tid * 128; o < nxt * 8 + 128; o += PC::T * 128)
+            if (nxt > 0) prefetch_l2(reinterpret_cast<const char*>(xb) + (o < nxt * 8 - 8 ? o : nxt * 8 - 8));
+        for (int o = tid * 128; o < nyt * 8 + 128; o += PC::T * 128)
+            if (nyt > 0) prefetch_l2(reinterpret_cast<const char*>(yb) + (o < nyt * 8 - 8 ? o : nyt * 8 - 8));
+        pdl_entry();
+        CTD_STAMP(7);
+        double* sx = smem;
+        double* sy = smem + ((nxt + 1) & ~1);
+        for (int k = tid; k < nxt; k += PC::T) sx[k] = __ldg(xb + k);
+        for (int k = tid; k < nyt; k += PC::T) sy[k] = __ldg(yb + k);
+        __syncthreads();
         const bool owner = active && lane >= 1;
         const bool giver = active && lane < nown;
         const int ob = owner ? lane - 1 : PC::OWN;
@@ -1109,13 +1149,17 @@ __global__ void __launch_bounds__(PCfg<E, F>::T, PCfg<E, F>::MINB) ctd_eval_kern
         double z[E::NZ], lam[E::CB];
         TimeArgs<E::NV> Tm;
         if (active) {
-            load_step<E>(x, a.nvar, i, z);
 #pragma unroll
-            for (int r = 0; r < E::CB; ++r) lam[r] = (C::WH && y) ? __ldg(y + (i - 1) * E::CB + r) : 0.0;
+            for (int k = 0; k < E::NOWN + E::NNEXT; ++k) z[k] = sx[lane * E::BLK + k];
+#pragma unroll
+            for (int k = 0; k < E::NV; ++k) z[E::NOWN + E::NNEXT + k] = __ldg(x + a.nvar - E::NV + k);
+#pragma unroll
+            for (int r = 0; r < E::CB; ++r) lam[r] = nyt > 0 ? sy[lane * E::CB + r] : 0.0;
             time_args<E>(a, z + E::NOWN + E::NNEXT, p, i, Tm);
         }
+        __syncthreads();   // the staging area is the output region: every warp has its inputs in registers
 #ifdef CTD_TRACE
-        if (active && Tm.hh == -1.2345) CTD_STAMP(7);   // forces the loads to have arrived
+        if (active && Tm.hh == -1.2345) CTD_STAMP(5);   // forces the loads to have arrived
         CTD_STAMP(1);
 #endif
         // hands the staged ranges of phase A and / or B to the copy engine (warp 0: the elected lane issues the
@@ -1170,8 +1214,8 @@ __global__ void __launch_bounds__(PCfg<E, F>::T, PCfg<E, F>::MINB) ctd_eval_kern
         CTD_STAMP(4);
     }
     publish_reduction<E, F>(a, red, smem + PC::S_RED, &cta_ticket, inst, cta, lane, warp, hvals, grad, PC::P);
-    CTD_STAMP(5);
     CTD_STAMP(6);
+    CTD_STAMP_SMID();
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -6,8 +6,9 @@
  *   src/DOCP_data.jl:176-214) -> ctd_dims -> ctd_info -> ctd_bounds -> ctd_x0 -> ctd_jac_structure / ctd_hess_structure
  *   -> ctd_obj, ctd_grad, ctd_cons, ctd_jac_coord, ctd_hess_coord (host pointers, as Ipopt calls them) -> ctd_eval
  *   (the fused call) -> ctd_unpack.
- * It checks that the fused call reproduces the separate callbacks bit for bit and writes everything to a binary file
- * that tests/test_julia_shim_sequence.py compares with the oracle.
+ * It writes the results of the separate callbacks AND of the fused call to a binary file that
+ * tests/test_julia_shim_sequence.py compares with the oracle (the two come from different kernels: same values within
+ * rounding, checked here only coarsely).
  *
  *   julia_shim_sequence <problem> <scheme> <N> <pattern_mode> <x.bin> <y.bin> <out.bin>
  */
@@ -38,7 +39,14 @@ static double* read_doubles(const char* path, int64_t n) {
     return a;
 }
 
-static int same(const double* a, const double* b, int64_t n) { return memcmp(a, b, sizeof(double) * (size_t)n) == 0; }
+static int close_enough(const double* a, const double* b, int64_t n) {   /* coarse: 1e-9 of the largest magnitude */
+    double m = 0.0, e = 0.0;
+    for (int64_t k = 0; k < n; ++k) {
+        if (fabs(a[k]) > m) m = fabs(a[k]);
+        if (fabs(a[k] - b[k]) > e) e = fabs(a[k] - b[k]);
+    }
+    return e <= 1e-9 * (m > 1.0 ? m : 1.0);
+}
 
 int main(int argc, char** argv) {
     if (argc != 8) {
@@ -85,8 +93,9 @@ int main(int argc, char** argv) {
     /* eval_all!: one fused launch */
     double f2 = 0.0, *g2 = malloc(8 * nvar), *c2 = malloc(8 * (ncon + 1)), *jv2 = malloc(8 * (nnzj + 1)), *hv2 = malloc(8 * (nnzh + 1));
     CHECK(ctd_eval(h, CTD_CONS | CTD_JAC | CTD_HESS | CTD_GRAD | CTD_OBJ, x, y, sigma, &f2, g2, c2, jv2, hv2));
-    if (!(memcmp(&f, &f2, 8) == 0 && same(g, g2, nvar) && same(c, c2, ncon) && same(jv, jv2, nnzj) && same(hv, hv2, nnzh))) {
-        fprintf(stderr, "the fused call does not reproduce the separate callbacks bit for bit\n");
+    if (!(close_enough(&f, &f2, 1) && close_enough(g, g2, nvar) && close_enough(c, c2, ncon) && close_enough(jv, jv2, nnzj) &&
+          close_enough(hv, hv2, nnzh))) {
+        fprintf(stderr, "the fused call and the separate callbacks disagree\n");
         return 4;
     }
     /* unpack_solution: time, state, control, variable, costate, path_dual, boundary_dual */
@@ -108,6 +117,7 @@ int main(int argc, char** argv) {
     fwrite(jr, 8, nnzj, o); fwrite(jc, 8, nnzj, o); fwrite(hr, 8, nnzh, o); fwrite(hc, 8, nnzh, o);
     fwrite(&f, 8, 1, o); fwrite(g, 8, nvar, o); fwrite(c, 8, ncon, o); fwrite(jv, 8, nnzj, o); fwrite(hv, 8, nnzh, o);
     fwrite(tm, 8, (size_t)N + 1, o); fwrite(st, 8, (size_t)(N + 1) * nx, o);
+    fwrite(&f2, 8, 1, o); fwrite(g2, 8, nvar, o); fwrite(c2, 8, ncon, o); fwrite(jv2, 8, nnzj, o); fwrite(hv2, 8, nnzh, o);
     fclose(o);
     CHECK(ctd_destroy(h));
     printf("ok %s %s N=%d nvar=%lld ncon=%lld nnzj=%lld nnzh=%lld\n", argv[1], argv[2], N, (long long)nvar, (long long)ncon,

@@ -86,17 +86,20 @@ def test_shim_call_sequence_on_gpu(ctd, oracle_mod, tmp_path, scheme):
         jr, jc, hr, hc = (take(n, np.int64) for n in (nnzj, nnzj, nnzh, nnzh))
         f, g, c, jv, hv = take(1)[0], take(nvar), take(ncon), take(nnzj), take(nnzh)
         tm, st = take(N + 1), take((N + 1) * nx)
+        fused = (take(1)[0], take(nvar), take(ncon), take(nnzj), take(nnzh))
         for a, b in zip((lvar, uvar, lcon, ucon), o.bounds()):
             assert np.array_equal(a, b)
         assert np.array_equal(x0, o.x0())
         for a, b in zip((jr, jc, hr, hc), o.jac_structure() + o.hess_structure()):
             assert np.array_equal(a, b)
         g_ref, j_ref, h_ref = o.derivs(x, y, 0.7)
-        tag = f"shim sequence {problem}/{scheme}/mode{mode}"
-        assert_close(c, o.cons(x), scale=max(1.0, np.abs(x).max()), what=tag + " cons")
-        assert_close(jv, j_ref, scale=column_scale((jr, jc), j_ref, nvar), what=tag + " jac")
-        assert_close(hv, h_ref, scale=hess_scale(o, x, y, 0.7, h_ref), what=tag + " hess")
-        assert_close(g, g_ref, scale=1e-3 * max(1.0, np.abs(g_ref).max()), what=tag + " grad")
-        assert_close(f, o.obj(x), scale=1.0, what=tag + " obj")
+        sh = hess_scale(o, x, y, 0.7, h_ref)
+        for kind, (f_, g_, c_, jv_, hv_) in (("callbacks", (f, g, c, jv, hv)), ("fused", fused)):
+            tag = f"shim sequence ({kind}) {problem}/{scheme}/mode{mode}"
+            assert_close(c_, o.cons(x), scale=max(1.0, np.abs(x).max()), what=tag + " cons")
+            assert_close(jv_, j_ref, scale=column_scale((jr, jc), j_ref, nvar), what=tag + " jac")
+            assert_close(hv_, h_ref, scale=sh, what=tag + " hess")
+            assert_close(g_, g_ref, scale=1e-3 * max(1.0, np.abs(g_ref).max()), what=tag + " grad")
+            assert_close(f_, o.obj(x), scale=1.0, what=tag + " obj")
         u = o.unpack(x, y)
         assert np.array_equal(tm, u["time"]) and np.array_equal(st.reshape(N + 1, nx), u["state"])

@@ -47,6 +47,6 @@ def test_cuda_path_against_50_digit_entries(ctd, oracle_mod, scheme):
     o = oracle_mod.OracleModel("goddard", scheme, N)      # (only for the tolerance floor of the Hessian)
     d = ctd.DOCP("goddard", N, scheme)
     x, y, sigma = GOLD[scheme + "|x"], GOLD[scheme + "|y"], float(GOLD[scheme + "|sigma"])
-    r = d.evaluate(ctd.CONS | ctd.JAC | ctd.HESS | ctd.OBJ, x, y, sigma)
+    r = d.evaluate(ctd.CONS | ctd.JAC | ctd.HESS | ctd.GRAD | ctd.OBJ, x, y, sigma)
     _check(f"CUDA vs mpmath goddard/{scheme}", (d.jacobian_structure(), d.hessian_structure()),
            {"cons": r["cons"], "jac": r["jac"], "hess": r["hess"], "obj": float(r["obj"][0])}, o, scheme)
