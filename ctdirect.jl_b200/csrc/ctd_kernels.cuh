@@ -116,8 +116,20 @@ struct Cfg {
     // nothing to stage, the tiles store the zeros of their column blocks directly; SG: gradient staged
     static constexpr bool GZ = WG && E::NG_OWN == 0 && E::NG_NEXT == 0 && E::NG_V == 0;
     static constexpr bool SG = WG && !GZ;
-    static constexpr int PER_STEP_A = (WC ? E::CB : 0) + (WJ ? E::J_BLOCK + NJV : 0) + (SG ? E::BLK : 0);
-    static constexpr int PER_STEP_B = WH ? E::H_BLOCK : 0;
+    // Row stride of the staged Hessian block.  Every lane writes its own row, so a stride of H_BLOCK doubles puts the 16
+    // lanes of a half-warp on (H_BLOCK mod 16) bank pairs: 104 doubles (3-stage IRK of a 3-state problem) = 8 mod 16, an
+    // 8-way conflict on every one of the 104 stores (ncu: 1.4 M shared-memory bank conflicts per launch; phase B of the
+    // parts kernel spends more time replaying stores than computing).  An odd stride is conflict-free, an even stride
+    // 2 * odd costs two passes: even block sizes whose half is even are padded to the next 2 * odd, and the rows then
+    // leave as one bulk copy each.
+    static constexpr int pad_stride(int n) { return (n % 2 == 1 || (n / 2) % 2 == 1) ? n : n + 2; }
+    static constexpr int HS = pad_stride(E::H_BLOCK);
+    static constexpr bool H_PADDED = HS != E::H_BLOCK;
+    // the same for the Jacobian block (stagewise 3-stage IRK of a 3-state problem: 192 doubles = 0 mod 16, a 16-way conflict)
+    static constexpr int JS = pad_stride(E::J_BLOCK);
+    static constexpr bool J_PADDED = JS != E::J_BLOCK;
+    static constexpr int PER_STEP_A = (WC ? E::CB : 0) + (WJ ? JS + NJV : 0) + (SG ? E::BLK : 0);
+    static constexpr int PER_STEP_B = WH ? HS : 0;
     static constexpr int PER_STEP = PER_STEP_A > PER_STEP_B ? PER_STEP_A : PER_STEP_B;
     // WPC = the LARGEST number of warps per CTA a launch may use (the host picks blockDim per launch,
     // see Model::eval_dev): 8 while a CTA's staged tiles stay below 72 KB, fewer for wide elements
@@ -159,12 +171,12 @@ struct Cfg {
     // (OWN + 1 blocks each: the last one is a dump block, written by the halo lane's "own" values and
     // the last lane's "next" values, so that the sinks store without predicates or branches)
     static constexpr int S_J = S_C + (WC ? even((OWN + 1) * E::CB) : 0);
-    static constexpr int S_JV = S_J + (WJ ? even((OWN + 1) * E::J_BLOCK) : 0);
+    static constexpr int S_JV = S_J + (WJ ? even((OWN + 1) * JS) : 0);
     static constexpr int JV_ONE = even((OWN + 1) * E::JV_STRIDE);
     static constexpr int S_G = S_JV + (WJ ? NV * JV_ONE : 0);
     static constexpr int A_END = S_G + (SG ? even((OWN + 1) * E::BLK) : 0);
     static constexpr int S_H = 0;
-    static constexpr int B_END = WH ? even((OWN + 1) * E::H_BLOCK) : 0;
+    static constexpr int B_END = WH ? even((OWN + 1) * HS) : 0;
     static constexpr int WARP_DOUBLES = ((A_END > B_END ? A_END : B_END) + 1) & ~1;
     static constexpr int S_RED = WPC * WARP_DOUBLES;
     static constexpr int S_END = S_RED + WPC * (NREDX > 0 ? NREDX : 1) + 2;
@@ -606,9 +618,9 @@ __device__ __forceinline__ void tile_phase(const EvalArgs& a, double* __restrict
     const int ob = s.owner ? lane - 1 : C::OWN;   // own block (dump block for the halo lane)
     const int nb = s.giver ? lane : C::OWN;       // next block (dump block for the last lane)
     s.c_ = sC + ob * E::CB;
-    s.jo_ = sJ + ob * E::J_BLOCK;
-    s.jn_ = sJ + nb * E::J_BLOCK;
-    s.ho_ = sH + ob * E::H_BLOCK;
+    s.jo_ = sJ + ob * C::JS;
+    s.jn_ = sJ + nb * C::JS;
+    s.ho_ = sH + ob * C::HS;
     s.go_ = sG + ob * E::BLK;
     if constexpr (PJ && C::NV > 0) {
 #pragma unroll
@@ -628,7 +640,7 @@ __device__ __forceinline__ void tile_phase(const EvalArgs& a, double* __restrict
         if (active) {
             if constexpr (PH) {
 #pragma unroll
-                for (int n = 0; n < E::NH_NEXT; ++n) sH[nb * E::H_BLOCK + E::H_NEXT(n, 2)] += s.hn_[n];
+                for (int n = 0; n < E::NH_NEXT; ++n) sH[nb * C::HS + E::H_NEXT(n, 2)] += s.hn_[n];
             }
             if constexpr (PG) {
 #pragma unroll
@@ -645,26 +657,39 @@ __device__ __forceinline__ void tile_phase(const EvalArgs& a, double* __restrict
         if (elect_one()) {
             if constexpr (PC) bulk_body(gC, smem_u32(sC), nown * E::CB);
             if constexpr (PJ) {
-                bulk_body(gJ, smem_u32(sJ), nown * E::J_BLOCK);
+                if constexpr (!C::J_PADDED) bulk_body(gJ, smem_u32(sJ), nown * E::J_BLOCK);
                 if constexpr (C::NV > 0) {
 #pragma unroll
                     for (int k = 0; k < C::NV; ++k) bulk_body(gJV[k], smem_u32(sJV[k]), nown * E::JV_STRIDE);
                 }
             }
-            if constexpr (PH) bulk_body(gH, smem_u32(sH), nown * E::H_BLOCK);
+            if constexpr (PH && !C::H_PADDED) bulk_body(gH, smem_u32(sH), nown * E::H_BLOCK);
             if constexpr (PG) bulk_body(gG, smem_u32(sG), nown * E::BLK);
             bulk_commit();
+        }
+        if constexpr ((PH && C::H_PADDED) || (PJ && C::J_PADDED)) {   // padded rows: lane l hands row l over (block size even: every row has the tile's phase)
+            if (lane < nown) {
+                if constexpr (PH && C::H_PADDED) {
+                    bulk_body(gH + lane * E::H_BLOCK, smem_u32(sH + lane * C::HS), E::H_BLOCK);
+                    ragged_ends(gH + lane * E::H_BLOCK, sH + lane * C::HS, E::H_BLOCK);
+                }
+                if constexpr (PJ && C::J_PADDED) {
+                    bulk_body(gJ + lane * E::J_BLOCK, smem_u32(sJ + lane * C::JS), E::J_BLOCK);
+                    ragged_ends(gJ + lane * E::J_BLOCK, sJ + lane * C::JS, E::J_BLOCK);
+                }
+                bulk_commit();
+            }
         }
         if (lane == 1) {
             if constexpr (PC) ragged_ends(gC, sC, nown * E::CB);
             if constexpr (PJ) {
-                ragged_ends(gJ, sJ, nown * E::J_BLOCK);
+                if constexpr (!C::J_PADDED) ragged_ends(gJ, sJ, nown * E::J_BLOCK);
                 if constexpr (C::NV > 0) {
 #pragma unroll
                     for (int k = 0; k < C::NV; ++k) ragged_ends(gJV[k], sJV[k], nown * E::JV_STRIDE);
                 }
             }
-            if constexpr (PH) ragged_ends(gH, sH, nown * E::H_BLOCK);
+            if constexpr (PH && !C::H_PADDED) ragged_ends(gH, sH, nown * E::H_BLOCK);
             if constexpr (PG) ragged_ends(gG, sG, nown * E::BLK);
         }
     }
@@ -921,8 +946,8 @@ struct PCfg {
     // two phases like the one-warp kernel (A: constraints + Jacobian + gradient, B: Hessian, same shared
     // memory) when both are requested: a 3-stage IRK step stages 290 doubles, 186 at a time with two phases
     static constexpr bool TWO = CTD_PARTS_TWO_PHASE && C::WJ && C::WH;
-    static constexpr int PER_A = (C::WC ? E::CB : 0) + (C::WJ ? E::J_BLOCK + C::NJV : 0) + (C::WG ? E::BLK : 0);
-    static constexpr int PER_B = C::WH ? E::H_BLOCK : 0;
+    static constexpr int PER_A = (C::WC ? E::CB : 0) + (C::WJ ? C::JS + C::NJV : 0) + (C::WG ? E::BLK : 0);
+    static constexpr int PER_B = C::WH ? C::HS : 0;
     static constexpr int PER_STEP = TWO ? (PER_A > PER_B ? PER_A : PER_B) : PER_A + PER_B;
     static constexpr int FIT = PER_STEP > 0 ? (C::SMEM_MAX - 2048) / (PER_STEP * 8) - 1 : 31;
     // tiles of 24..30 steps when that lets 5 CTAs share an SM (44 KB each) instead of 4
@@ -934,7 +959,7 @@ struct PCfg {
     // cap: the Hessian-only kernel of a 3-stage IRK otherwise takes 248 registers = 4 CTAs per SM = 592 of the
     // 645 tiles of a 2e4-step grid resident, i.e. a second wave (the same code is spill-free in 168 registers
     // inside the two-phase kernel).  Elements outside that class keep the full register file.
-    static constexpr int PER7 = (E::CB + E::J_BLOCK + C::NJV) > E::H_BLOCK ? (E::CB + E::J_BLOCK + C::NJV) : E::H_BLOCK;
+    static constexpr int PER7 = (E::CB + C::JS + C::NJV) > C::HS ? (E::CB + C::JS + C::NJV) : C::HS;
     static constexpr int FIT5_7 = (44 * 1024) / (PER7 * 8) - 1;
     static constexpr bool FIVE7 = FIT5_7 >= 24 && FIT5_7 < CTD_PART_OWN;
     static constexpr int MINB = (FIVE || (FIVE7 && PER_STEP * 8 * (OWN + 1) <= 44 * 1024)) ? 5 : 1;
@@ -942,10 +967,10 @@ struct PCfg {
     static constexpr int even(int n) { return (n + 3) & ~1; }
     static constexpr int S_C = 0;
     static constexpr int S_J = S_C + (C::WC ? even((OWN + 1) * E::CB) : 0);
-    static constexpr int S_JV = S_J + (C::WJ ? even((OWN + 1) * E::J_BLOCK) : 0);
+    static constexpr int S_JV = S_J + (C::WJ ? even((OWN + 1) * C::JS) : 0);
     static constexpr int JV_ONE = even((OWN + 1) * E::JV_STRIDE);
     static constexpr int A_END0 = S_JV + (C::WJ ? C::NV * JV_ONE : 0);
-    static constexpr int H_LEN = C::WH ? even((OWN + 1) * E::H_BLOCK) : 0;
+    static constexpr int H_LEN = C::WH ? even((OWN + 1) * C::HS) : 0;
     static constexpr int G_LEN = C::WG ? even((OWN + 1) * E::BLK) : 0;
     // one phase: c | J | Jv | H | g     two phases: A = c | J | Jv | g, B = H (from 0)
     static constexpr int S_H = TWO ? 0 : A_END0;
@@ -1029,9 +1054,9 @@ __device__ __forceinline__ void run_part(const EvalArgs& a, const double* z, con
     s.red = red;
     s.owner = owner;
     s.c_ = sC + ob * E::CB;
-    s.jo_ = sJ + ob * E::J_BLOCK;
-    s.jn_ = sJ + nb * E::J_BLOCK;
-    s.ho_ = sH + ob * E::H_BLOCK;
+    s.jo_ = sJ + ob * C::JS;
+    s.jn_ = sJ + nb * C::JS;
+    s.ho_ = sH + ob * C::HS;
     s.go_ = sG + ob * E::BLK;
     if constexpr (S::WJ && C::NV > 0) {
 #pragma unroll
@@ -1051,7 +1076,7 @@ __device__ __forceinline__ void run_part(const EvalArgs& a, const double* z, con
         if constexpr (S::WH) {
 #pragma unroll
             for (int n = 0; n < E::NH_NEXT; ++n)
-                if (S::mine(PC::O_HN + n)) sH[nb * E::H_BLOCK + E::H_NEXT(n, 2)] += s.hn_[n];
+                if (S::mine(PC::O_HN + n)) sH[nb * C::HS + E::H_NEXT(n, 2)] += s.hn_[n];
         }
         if constexpr (S::WG) {
 #pragma unroll
@@ -1118,12 +1143,17 @@ __global__ void __launch_bounds__(PCfg<E, F>::T, PCfg<E, F>::MINB) ctd_eval_kern
             if (nxt > 0) prefetch_l2(reinterpret_cast<const char*>(xb) + (o < nxt * 8 - 8 ? o : nxt * 8 - 8));
         for (int o = tid * 128; o < nyt * 8 + 128; o += PC::T * 128)
             if (nyt > 0) prefetch_l2(reinterpret_cast<const char*>(yb) + (o < nyt * 8 - 8 ? o : nyt * 8 - 8));
+        double si = 0.0, sp = 0.0;   // normalized times of this thread's step (immutable: read before the grid dependency)
+        if (active) { si = grid_point(a, i - 1); sp = grid_point(a, i); }
         pdl_entry();
         CTD_STAMP(7);
         double* sx = smem;
         double* sy = smem + ((nxt + 1) & ~1);
         for (int k = tid; k < nxt; k += PC::T) sx[k] = __ldg(xb + k);
         for (int k = tid; k < nyt; k += PC::T) sy[k] = __ldg(yb + k);
+        double vv[E::NV > 0 ? E::NV : 1];
+#pragma unroll
+        for (int k = 0; k < E::NV; ++k) vv[k] = __ldg(x + a.nvar - E::NV + k);
         __syncthreads();
         const bool owner = active && lane >= 1;
         const bool giver = active && lane < nown;
@@ -1152,10 +1182,10 @@ __global__ void __launch_bounds__(PCfg<E, F>::T, PCfg<E, F>::MINB) ctd_eval_kern
 #pragma unroll
             for (int k = 0; k < E::NOWN + E::NNEXT; ++k) z[k] = sx[lane * E::BLK + k];
 #pragma unroll
-            for (int k = 0; k < E::NV; ++k) z[E::NOWN + E::NNEXT + k] = __ldg(x + a.nvar - E::NV + k);
+            for (int k = 0; k < E::NV; ++k) z[E::NOWN + E::NNEXT + k] = vv[k];
 #pragma unroll
             for (int r = 0; r < E::CB; ++r) lam[r] = nyt > 0 ? sy[lane * E::CB + r] : 0.0;
-            time_args<E>(a, z + E::NOWN + E::NNEXT, p, i, Tm);
+            time_args_s<E>(si, sp, z + E::NOWN + E::NNEXT, p, Tm);
         }
         __syncthreads();   // the staging area is the output region: every warp has its inputs in registers
 #ifdef CTD_TRACE
@@ -1174,7 +1204,7 @@ __global__ void __launch_bounds__(PCfg<E, F>::T, PCfg<E, F>::MINB) ctd_eval_kern
                 if (pa) {
                     if constexpr (C::WC) range(gC, sC, nown * E::CB);
                     if constexpr (C::WJ) {
-                        range(gJ, sJ, nown * E::J_BLOCK);
+                        if constexpr (!C::J_PADDED) range(gJ, sJ, nown * E::J_BLOCK);
                         if constexpr (C::NV > 0) {
 #pragma unroll
                             for (int k = 0; k < C::NV; ++k) range(gJV[k], sJV[k], nown * E::JV_STRIDE);
@@ -1183,9 +1213,26 @@ __global__ void __launch_bounds__(PCfg<E, F>::T, PCfg<E, F>::MINB) ctd_eval_kern
                     if constexpr (C::WG) range(gG, sG, nown * E::BLK);
                 }
                 if (pb) {
-                    if constexpr (C::WH) range(gH, sH, nown * E::H_BLOCK);
+                    if constexpr (C::WH && !C::H_PADDED) range(gH, sH, nown * E::H_BLOCK);
                 }
                 if (leader) bulk_commit();
+                if constexpr ((C::WH && C::H_PADDED) || (C::WJ && C::J_PADDED)) {   // padded rows: lane l hands row l over (see Cfg::HS)
+                    if (lane < nown) {
+                        if constexpr (C::WH && C::H_PADDED) {
+                            if (pb) {
+                                bulk_body(gH + lane * E::H_BLOCK, smem_u32(sH + lane * C::HS), E::H_BLOCK);
+                                ragged_ends(gH + lane * E::H_BLOCK, sH + lane * C::HS, E::H_BLOCK);
+                            }
+                        }
+                        if constexpr (C::WJ && C::J_PADDED) {
+                            if (pa) {
+                                bulk_body(gJ + lane * E::J_BLOCK, smem_u32(sJ + lane * C::JS), E::J_BLOCK);
+                                ragged_ends(gJ + lane * E::J_BLOCK, sJ + lane * C::JS, E::J_BLOCK);
+                            }
+                        }
+                        bulk_commit();
+                    }
+                }
             }
         };
         if constexpr (!PC::TWO) {
