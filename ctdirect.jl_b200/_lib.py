@@ -72,6 +72,9 @@ SIGNATURES = {
     "ctd_stream": (C.c_void_p, [_H]),
     "ctd_set_stream": (C.c_int, [_H, C.c_void_p]),
     "ctd_launch_count": (C.c_int64, [_H]),
+    "ctd_counters": (C.c_int, [_H, C.POINTER(C.c_int64)]),
+    "ctd_reset_counters": (C.c_int, [_H]),
+    "ctd_stats_json": (C.c_int64, [_H, C.c_char_p, C.c_int64]),
     "ctd_kkt_nnz": (C.c_int64, [_H]),
     "ctd_kkt_structure": (C.c_int, [_H, _ip, _ip]),
     "ctd_kkt_assemble_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -1,4 +1,7 @@
 // extern "C" entry points declared in include/ctdirect_b200.h.
+#include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <cstring>
 #include <exception>
 #include <string>
@@ -10,8 +13,31 @@ using namespace ctd;
 
 static_assert(CTD_COMM_SLOTS == kCommSlots && CTD_NCCL_ID_BYTES == kNcclIdBytes, "header and model disagree");
 
+// Per-handle call statistics (the NLPModels `Counters` of the reference's models): one count per
+// callback kind, incremented by every entry point that produces that output, fused or not.
+struct CallStats {
+    std::atomic<int64_t> n[CTD_N_COUNTERS];
+    std::atomic<int64_t> host_ns;   // wall time spent inside the blocking host-buffer calls
+    CallStats() { reset(); }
+    void reset() {
+        for (auto& c : n) c.store(0, std::memory_order_relaxed);
+        host_ns.store(0, std::memory_order_relaxed);
+    }
+    void count(int what, bool host, bool batched_norms = false) {
+        if (what & CTD_OBJ) n[CTD_NEVAL_OBJ]++;
+        if (what & CTD_GRAD) n[CTD_NEVAL_GRAD]++;
+        if (what & CTD_CONS) n[CTD_NEVAL_CONS]++;
+        if (what & CTD_JAC) n[CTD_NEVAL_JAC]++;
+        if (what & CTD_HESS) n[CTD_NEVAL_HESS]++;
+        n[CTD_NCALL_EVAL]++;
+        if (host) n[CTD_NCALL_HOST]++;
+        if (batched_norms) n[CTD_NCALL_NORMS]++;
+    }
+};
+
 struct ctd_model_s {
     Model* m;
+    CallStats stats;
 };
 
 namespace {
@@ -88,7 +114,8 @@ int ctd_create(const ctd_desc* d, ctd_handle* out) {
         if (d->pattern_mode < 0 || d->pattern_mode > 2) throw CtdError{-2, "pattern_mode must be 0, 1 or 2"};
         Model* m = new Model(*reg, d->grid_size, d->time_grid, d->n_time_grid, d->params, d->n_params,
                              d->batch < 1 ? 1 : d->batch, d->device);
-        *out = new ctd_model_s{m};
+        *out = new ctd_model_s;
+        (*out)->m = m;
     });
 }
 
@@ -150,24 +177,31 @@ int ctd_hess_structure(ctd_handle h, int64_t* rows, int64_t* cols) {
 int ctd_eval(ctd_handle h, int what, const double* x, const double* y, double obj_weight, double* f, double* g,
              double* c, double* jvals, double* hvals) {
     if (int e = check(h)) return e;
-    return guarded([&] { h->m->eval_host(what, x, y, obj_weight, f, g, c, jvals, hvals); });
+    const auto t0 = std::chrono::steady_clock::now();
+    const int rc = guarded([&] { h->m->eval_host(what, x, y, obj_weight, f, g, c, jvals, hvals); });
+    h->stats.count(what, true);
+    h->stats.host_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
 }
 
 int ctd_eval_async(ctd_handle h, int what, const double* x, const double* y, double obj_weight, double* f, double* g,
                    double* c, double* jvals, double* hvals) {
     if (int e = check(h)) return e;
+    h->stats.count(what, true);
     return guarded([&] { h->m->eval_host(what, x, y, obj_weight, f, g, c, jvals, hvals, false); });
 }
 
 int ctd_eval_dev(ctd_handle h, int what, const double* x, const double* y, double obj_weight, double* f,
                  double* g, double* c, double* jvals, double* hvals) {
     if (int e = check(h)) return e;
+    h->stats.count(what, false);
     return guarded([&] { h->m->eval_dev(what, x, y, obj_weight, f, g, c, jvals, hvals); });
 }
 
 int ctd_eval_norms_dev(ctd_handle h, int what, const double* x, const double* y, double obj_weight, double* f,
                        double* g, double* c, double* jvals, double* hvals, double* viol) {
     if (int e = check(h)) return e;
+    h->stats.count(what, false, true);
     return guarded([&] { h->m->eval_dev(what, x, y, obj_weight, f, g, c, jvals, hvals, viol); });
 }
 
@@ -257,6 +291,43 @@ int64_t ctd_launch_count(ctd_handle h) {
     return h->m->launches();
 }
 
+int ctd_counters(ctd_handle h, int64_t out[CTD_N_COUNTERS]) {
+    if (int e = check(h)) return e;
+    if (!out) return fail(-2, "ctd_counters: NULL argument");
+    for (int i = 0; i < CTD_N_COUNTERS; ++i) out[i] = h->stats.n[i].load(std::memory_order_relaxed);
+    return 0;
+}
+
+int ctd_reset_counters(ctd_handle h) {
+    if (int e = check(h)) return e;
+    h->stats.reset();
+    return 0;
+}
+
+int64_t ctd_stats_json(ctd_handle h, char* buf, int64_t buflen) {
+    if (check(h)) return -1;
+    const ElemInfo& f = h->m->info();
+    const CallStats& st = h->stats;
+    char tmp[1024];
+    const int n = std::snprintf(
+        tmp, sizeof(tmp),
+        "{\"problem\": \"%s\", \"scheme\": \"%s\", \"grid_size\": %lld, \"batch\": %lld, \"nvar\": %lld, \"ncon\": %lld, "
+        "\"nnzj\": %lld, \"nnzh\": %lld, \"neval_obj\": %lld, \"neval_grad\": %lld, \"neval_cons\": %lld, "
+        "\"neval_jac\": %lld, \"neval_hess\": %lld, \"calls\": %lld, \"host_calls\": %lld, \"norm_calls\": %lld, "
+        "\"kernel_launches\": %lld, \"host_call_seconds\": %.9f}",
+        f.problem.c_str(), f.scheme.c_str(), (long long)h->m->N(), (long long)h->m->batch(), (long long)h->m->nvar(),
+        (long long)h->m->ncon(), (long long)h->m->nnzj(), (long long)h->m->nnzh(), (long long)st.n[CTD_NEVAL_OBJ].load(),
+        (long long)st.n[CTD_NEVAL_GRAD].load(), (long long)st.n[CTD_NEVAL_CONS].load(), (long long)st.n[CTD_NEVAL_JAC].load(),
+        (long long)st.n[CTD_NEVAL_HESS].load(), (long long)st.n[CTD_NCALL_EVAL].load(), (long long)st.n[CTD_NCALL_HOST].load(),
+        (long long)st.n[CTD_NCALL_NORMS].load(), (long long)h->m->launches(), 1e-9 * (double)st.host_ns.load());
+    if (buf && buflen > 0) {
+        const size_t k = std::min<size_t>((size_t)n, (size_t)buflen - 1);
+        std::memcpy(buf, tmp, k);
+        buf[k] = 0;
+    }
+    return (int64_t)n + 1;
+}
+
 int64_t ctd_kkt_nnz(ctd_handle h) {
     if (check(h)) return -1;
     int64_t n = -1;
@@ -309,6 +380,7 @@ int ctd_peer_init(ctd_handle h) {
 int ctd_eval_gather_dev(ctd_handle h, int what, const double* x, const double* y, double obj_weight, double* g,
                         double* c, double* jvals, double* hvals, int32_t slot) {
     if (int e = check(h)) return e;
+    h->stats.count(what, false, true);
     return guarded([&] { h->m->eval_gather_dev(what, x, y, obj_weight, g, c, jvals, hvals, slot); });
 }
 

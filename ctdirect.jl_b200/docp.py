@@ -501,6 +501,27 @@ class DOCP:
     def launch_count(self) -> int:
         return int(self._lib.ctd_launch_count(self._h))
 
+    COUNTER_NAMES = ("neval_obj", "neval_grad", "neval_cons", "neval_jac", "neval_hess", "calls", "host_calls",
+                     "norm_calls")
+
+    def counters(self) -> dict:
+        """The library's per-handle call counters (`ctd_counters`): what `NLPModels.Counters` hold for the
+        reference's models (printed by test/benchmark.jl:81-125)."""
+        out = np.zeros(len(self.COUNTER_NAMES), dtype=np.int64)
+        _lib.check(self._lib.ctd_counters(self._h, out.ctypes.data_as(C.POINTER(C.c_int64))))
+        return dict(zip(self.COUNTER_NAMES, (int(v) for v in out)))
+
+    def reset_counters(self) -> None:
+        _lib.check(self._lib.ctd_reset_counters(self._h))
+
+    def stats(self) -> dict:
+        """Counters, model sizes, kernel launches and the wall time of the blocking host calls (`ctd_stats_json`)."""
+        import json
+        n = int(self._lib.ctd_stats_json(self._h, None, 0))
+        buf = C.create_string_buffer(n)
+        self._lib.ctd_stats_json(self._h, buf, n)
+        return json.loads(buf.value.decode())
+
     # ---- the reference's builder seam ---------------------------------------------------------------
     def nlp_model(self, initial_guess=None):
         if self._nlp is None or initial_guess is not None:

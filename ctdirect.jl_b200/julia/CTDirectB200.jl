@@ -363,6 +363,21 @@ kkt_assemble!(nlp, hvals, jvals, dx, dc, kvals) =
     check(ccall((:ctd_kkt_assemble_dev, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
                 nlp.handle.ptr, hvals, jvals, dx, dc, kvals))
 
+"The library's own per-handle counters (`ctd_counters`): (neval_obj, neval_grad, neval_cons, neval_jac, neval_hess, calls, host_calls, norm_calls)."
+function library_counters(nlp)
+    out = zeros(Int64, 8)
+    check(ccall((:ctd_counters, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}), nlp.handle.ptr, out))
+    return NamedTuple{(:neval_obj, :neval_grad, :neval_cons, :neval_jac, :neval_hess, :calls, :host_calls, :norm_calls)}(Tuple(out))
+end
+
+"Counters, sizes, kernel launches and host-call wall time of the handle as a JSON string (`ctd_stats_json`)."
+function library_stats_json(nlp)
+    n = ccall((:ctd_stats_json, LIB), Int64, (Ptr{Cvoid}, Ptr{UInt8}, Int64), nlp.handle.ptr, C_NULL, 0)
+    buf = Vector{UInt8}(undef, n)
+    ccall((:ctd_stats_json, LIB), Int64, (Ptr{Cvoid}, Ptr{UInt8}, Int64), nlp.handle.ptr, buf, n)
+    return unsafe_string(pointer(buf))
+end
+
 # ---- batched scenarios on several GPUs: the library's own NCCL communicator (include/ctdirect_b200.h) ----
 "128 bytes created by ONE rank; broadcast them to every rank (MPI, Distributed, a file) before `comm_init!`."
 function nccl_unique_id()

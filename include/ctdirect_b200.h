@@ -168,6 +168,23 @@ CTD_API int ctd_set_stream(ctd_handle h, void* stream);
 /* number of kernel launches issued through this handle so far */
 CTD_API int64_t ctd_launch_count(ctd_handle h);
 
+/* Per-handle call counters: what NLPModels.Counters hold for the reference's models (neval_obj, neval_grad, neval_cons,
+ * neval_jac, neval_hess; printed by the reference's benchmark, test/benchmark.jl:81-125).  Every entry point that
+ * produces an output counts it -- a fused ctd_eval(CTD_CONS | CTD_JAC | CTD_HESS) adds one to each of the three.
+ * ctd_stats_json writes the counters, the model's sizes, the kernel launches and the wall time spent inside the
+ * blocking host-buffer calls as one JSON object; it returns the size needed (with the final NUL), like
+ * ctd_list_models. */
+enum {
+    CTD_NEVAL_OBJ = 0, CTD_NEVAL_GRAD = 1, CTD_NEVAL_CONS = 2, CTD_NEVAL_JAC = 3, CTD_NEVAL_HESS = 4,
+    CTD_NCALL_EVAL = 5,  /* evaluation calls of any kind */
+    CTD_NCALL_HOST = 6,  /* of which with host buffers */
+    CTD_NCALL_NORMS = 7, /* of which with the per-instance violation norm (batched) */
+    CTD_N_COUNTERS = 8
+};
+CTD_API int ctd_counters(ctd_handle h, int64_t out[CTD_N_COUNTERS]);
+CTD_API int ctd_reset_counters(ctd_handle h);
+CTD_API int64_t ctd_stats_json(ctd_handle h, char* buf, int64_t buflen);
+
 /* ---- KKT assembly.  Lower triangle, CSC, of
  *        K = [ H + diag(dx)       .      ]      (nvar + ncon columns)
  *            [ J              -diag(dc)  ]

@@ -622,3 +622,29 @@ def test_cuda_path_against_committed_regression_vectors(ctd):
         assert_close(r["hess"], z[tag + "|hess"], scale=hess_scale(o, x, y, 0.75, z[tag + "|hess"]), what=tag + " hess")
         assert_close(r["grad"], z[tag + "|grad"], scale=1e-3, what=tag + " grad")
         assert_close(r["obj"], z[tag + "|obj"], scale=1.0, what=tag + " obj")
+
+
+@pytest.mark.gpu
+def test_library_call_counters(ctd):
+    """The per-handle counters of the C library (ctd_counters / ctd_stats_json) follow NLPModels.Counters: every
+    entry point counts the outputs it produced, fused or not (reference: the counters printed by test/benchmark.jl:81-125)."""
+    import torch
+    d = ctd.DOCP("goddard", 40, "midpoint")
+    nlp = d.nlp_model()
+    x, y = synthetic_point(d, seed=5)
+    assert d.counters() == dict.fromkeys(d.COUNTER_NAMES, 0)
+    nlp.obj(x); nlp.grad(x); nlp.cons(x); nlp.cons(x); nlp.jac_coord(x); nlp.hess_coord(x, y)
+    nlp.eval_all(x, y)
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    d.evaluate(ctd.CONS | ctd.JAC, xd, yd)
+    d.synchronize()
+    c = d.counters()
+    # grad evaluates the objective along with the gradient (ctd_grad = CTD_GRAD | CTD_OBJ)
+    assert c == {"neval_obj": 3, "neval_grad": 2, "neval_cons": 4, "neval_jac": 3, "neval_hess": 2,
+                 "calls": 8, "host_calls": 7, "norm_calls": 0}, c
+    s = d.stats()
+    assert s["problem"] == "goddard" and s["scheme"] == "midpoint" and s["grid_size"] == 40
+    assert (s["nvar"], s["ncon"], s["nnzj"], s["nnzh"]) == (d.nvar, d.ncon, d.nnzj, d.nnzh)
+    assert s["neval_cons"] == 4 and s["kernel_launches"] == d.launch_count >= 8 and s["host_call_seconds"] > 0
+    d.reset_counters()
+    assert d.counters() == dict.fromkeys(d.COUNTER_NAMES, 0)
