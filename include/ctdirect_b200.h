@@ -44,7 +44,7 @@ typedef struct ctd_model_s* ctd_handle;
 #define CTD_PATTERN_CORRECTED 1 /* adds the entries the reference omits        */
 #define CTD_PATTERN_OPTIMIZED 2 /* detected structural pattern (the reference's `:optimized` backend:
                                    SparseConnectivityTracer over the closures, collocation.jl:131-134);
-                                   compiled for a subset of the (problem, scheme) pairs            */
+                                   compiled for every (problem, scheme) pair                       */
 
 /* output selection bits of ctd_eval / ctd_eval_dev */
 #define CTD_CONS 1
