@@ -244,7 +244,8 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ int phase_of(const double* g) {
     return (int)(((unsigned int)reinterpret_cast<unsigned long long>(g) >> 3) & 1u);
 }
-// A staged range of n >= 1 doubles, destination g (8-byte aligned), staged copy s with the SAME 16-byte phase
+// A staged range of n doubles (n = 0: nothing -- a v column without per-step entries, an empty Hessian block of a
+// detected pattern), destination g (8-byte aligned), staged copy s with the SAME 16-byte phase
 // as g (s_u32 = its shared-memory address).  The 16-byte-aligned body goes through the copy engine (issued by
 // the elected lane), the at most one leading and one trailing double are stored directly (by lane 1).
 // The results stream out once and are not read again by the kernels: they are written with the L2 evict-first
@@ -259,6 +260,7 @@ __device__ __forceinline__ unsigned long long evict_first_policy() {
     return pol;
 }
 __device__ __forceinline__ void bulk_body(double* __restrict__ g, unsigned int s_u32, int n) {
+    if (n <= 0) return;
     const int ph = phase_of(g);
     const int body = (n - ph) >> 1;
     if (body > 0) {
@@ -272,6 +274,7 @@ __device__ __forceinline__ void bulk_body(double* __restrict__ g, unsigned int s
     }
 }
 __device__ __forceinline__ void ragged_ends(double* __restrict__ g, const double* __restrict__ s, int n) {
+    if (n <= 0) return;
     const int ph = phase_of(g);
     if (ph) g[0] = s[0];
     if ((n - ph) & 1) g[n - 1] = s[n - 1];

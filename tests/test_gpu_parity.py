@@ -636,11 +636,11 @@ def test_library_call_counters(ctd):
     nlp.obj(x); nlp.grad(x); nlp.cons(x); nlp.cons(x); nlp.jac_coord(x); nlp.hess_coord(x, y)
     nlp.eval_all(x, y)
     xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
-    d.evaluate(ctd.CONS | ctd.JAC, xd, yd)
+    d.evaluate(ctd.CONS | ctd.JAC | ctd.HESS, xd, yd)
     d.synchronize()
     c = d.counters()
     # grad evaluates the objective along with the gradient (ctd_grad = CTD_GRAD | CTD_OBJ)
-    assert c == {"neval_obj": 3, "neval_grad": 2, "neval_cons": 4, "neval_jac": 3, "neval_hess": 2,
+    assert c == {"neval_obj": 3, "neval_grad": 2, "neval_cons": 4, "neval_jac": 3, "neval_hess": 3,
                  "calls": 8, "host_calls": 7, "norm_calls": 0}, c
     s = d.stats()
     assert s["problem"] == "goddard" and s["scheme"] == "midpoint" and s["grid_size"] == 40
