@@ -16,7 +16,7 @@ class Desc(C.Structure):
     _fields_ = [
         ("problem", C.c_char_p), ("scheme", C.c_char_p), ("grid_size", C.c_int32), ("time_grid", _dp),
         ("n_time_grid", C.c_int32), ("params", _dp), ("n_params", C.c_int32), ("pattern_mode", C.c_int32),
-        ("batch", C.c_int32), ("device", C.c_int32),
+        ("batch", C.c_int32), ("device", C.c_int32), ("control_steps", C.c_int32),
     ]
 
 
@@ -65,6 +65,8 @@ SIGNATURES = {
     "ctd_norms": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ctd_unpack": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.POINTER(Solution)]),
     "ctd_unpack_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.POINTER(Solution)]),
+    "ctd_control_steps": (C.c_int32, [_H]),
+    "ctd_control_time": (C.c_int, [_H, _dp, _dp]),
     "ctd_pack": (C.c_int, [_H] + [C.c_void_p] * 5),
     "ctd_pack_dev": (C.c_int, [_H] + [C.c_void_p] * 5),
     "ctd_set_params": (C.c_int, [_H, _dp, C.c_int32]),

@@ -96,16 +96,27 @@ int ctd_create(const ctd_desc* d, ctd_handle* out) {
         if (!scheme.empty() && scheme[0] == ':') scheme = scheme.substr(1);
         if (scheme == "euler_explicit" || scheme == "euler_forward") scheme = "euler";
         if (scheme == "euler_backward") scheme = "euler_implicit";
+        int pattern_mode = d->pattern_mode;
+        if (d->control_steps > 1) {   // DirectShooting: src/direct_shooting.jl:55-71
+            if (scheme != "midpoint")
+                throw CtdError{-5, "control_steps > 1 is compiled for the midpoint scheme only (direct_shooting.jl:16)"};
+            scheme = "midpoint_cs" + std::to_string(d->control_steps);
+            pattern_mode = 2;
+        } else if (d->control_steps < 0) {
+            throw CtdError{-2, "control_steps must be >= 0"};
+        }
         for (const Registration& r : registry()) {
             if (r.info.scheme == scheme) scheme_known = true;
             if (r.info.problem == d->problem) problem_known = true;
             if (r.info.problem == d->problem && r.info.scheme == scheme) {
-                if (r.info.pattern_mode == d->pattern_mode) reg = &r;
+                if (r.info.pattern_mode == pattern_mode) reg = &r;
                 // a pair without quirks is only compiled in reference mode: both manual modes coincide
-                else if (!reg && r.info.pattern_mode == 0 && d->pattern_mode != 2) reg = &r;
+                else if (!reg && r.info.pattern_mode == 0 && pattern_mode != 2) reg = &r;
             }
         }
         if (!reg) {
+            if (!scheme_known && d->control_steps > 1)
+                throw CtdError{-5, "control_steps = " + std::to_string(d->control_steps) + " is not compiled in (2, 3, 10 are)"};
             if (!scheme_known)  // same wording as the reference's error, DOCP_data.jl:343-348
                 throw CtdError{-4, std::string("Unknown discretization method: ") + d->scheme};
             if (!problem_known) throw CtdError{-5, std::string("unknown problem: ") + d->problem};
@@ -250,6 +261,28 @@ int ctd_unpack_dev(ctd_handle h, const double* x, const double* y, const ctd_sol
     return guarded([&] {
         h->m->unpack_dev(x, y, o->time, o->state, o->control, o->variable, o->costate, o->path_dual, o->boundary_dual);
     });
+}
+
+int32_t ctd_control_steps(ctd_handle h) {
+    if (check(h)) return -1;
+    return h->m->info().control_steps;
+}
+
+int ctd_control_time(ctd_handle h, const double* time, double* control_time) {
+    if (int e = check(h)) return e;
+    if (!time || !control_time) return fail(-2, "ctd_control_time: NULL argument");
+    const int64_t N = h->m->N(), cs = h->m->info().control_steps, B = h->m->batch();
+    for (int64_t b = 0; b < B; ++b) {
+        const double* T = time + b * (N + 1);
+        double* tc = control_time + b * (N * cs + 1);
+        int64_t k = 0;
+        for (int64_t i = 0; i < N; ++i) {
+            const double h_i = T[i + 1] - T[i];
+            for (int64_t j = 0; j < cs; ++j) tc[k++] = T[i] + (double)j * h_i / (double)cs;   // DOCP_data.jl:562
+        }
+        tc[k] = T[N];
+    }
+    return 0;
 }
 
 int ctd_pack(ctd_handle h, const double* state, const double* control, const double* variable,

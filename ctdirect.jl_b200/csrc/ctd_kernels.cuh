@@ -1302,7 +1302,20 @@ __global__ void __launch_bounds__(128) ctd_unpack_kernel(const UnpackArgs a) {
 #pragma unroll
         for (int k = 0; k < E::NX; ++k) a.state[(inst * (N + 1) + i - 1) * E::NX + k] = __ldg(x + (i - 1) * E::BLK + k);
     }
-    if constexpr (E::NU > 0) {
+    if constexpr (E::NU > 0 && E::CONTROL_STEPS > 1) {
+        // N * control_steps + 1 rows: every control of every step, then u(tf) = the FIRST control of the last step
+        // (getter(:control), common.jl:82-99 with get_OCP_control_at_time_step(data, docp, N+1), l.140-155)
+        if (a.control) {
+            double* out = a.control + inst * (N * E::CONTROL_STEPS + 1) * E::NU;
+            if (i <= N) {
+#pragma unroll
+                for (int k = 0; k < E::CONTROL_STEPS * E::NU; ++k) out[(i - 1) * E::CONTROL_STEPS * E::NU + k] = __ldg(x + (i - 1) * E::BLK + E::NX + k);
+            } else {
+#pragma unroll
+                for (int k = 0; k < E::NU; ++k) out[N * E::CONTROL_STEPS * E::NU + k] = __ldg(x + (N - 1) * E::BLK + E::NX + k);
+            }
+        }
+    } else if constexpr (E::NU > 0) {
         if (a.control) {
             double* out = a.control + (inst * (N + 1) + i - 1) * E::NU;
             if constexpr (E::STAGEWISE) {
@@ -1384,8 +1397,11 @@ __global__ void __launch_bounds__(128) ctd_pack_kernel(const PackArgs a) {
                     }
             }
         } else if (a.control && (i <= N || E::FINAL_CONTROL)) {
+            // the node's control for every control step of the time step (DOCP_variables.jl:138-140)
 #pragma unroll
-            for (int k = 0; k < E::NU; ++k) xb[E::NX + k] = a.control[(inst * (N + 1) + i - 1) * E::NU + k];
+            for (int j = 0; j < E::CONTROL_STEPS; ++j)
+#pragma unroll
+                for (int k = 0; k < E::NU; ++k) xb[E::NX + j * E::NU + k] = a.control[(inst * (N + 1) + i - 1) * E::NU + k];
         }
     }
     if (i == 1) {

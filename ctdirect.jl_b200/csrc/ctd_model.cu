@@ -334,7 +334,8 @@ void Model::variable_bounds(double* lvar, double* uvar) const {
     box_to_dense(f.nx, f.meta.state_box, xl, xu);
     box_to_dense(f.nu, f.meta.control_box, ul, uu);
     box_to_dense(f.nv, f.meta.variable_box, vl, vu);
-    const int ncopies = f.stagewise ? f.stage : 1;  // one control per stage: irk_stagewise.jl:250-300
+    // one control per stage (irk_stagewise.jl:250-300) or per control step (DOCP_variables.jl:44)
+    const int ncopies = f.stagewise ? f.stage : f.control_steps;
     for (int64_t i = 0; i <= N_; ++i) {
         const int64_t o = i * f.blk;
         for (int k = 0; k < f.nx; ++k) { lvar[o + k] = xl[k]; uvar[o + k] = xu[k]; }
@@ -362,7 +363,7 @@ void Model::constraint_bounds(double* lcon, double* ucon) const {
 void Model::initial_guess(double* x0) const {
     const ElemInfo& f = reg_.info;
     std::fill(x0, x0 + nvar_, 0.1);  // DOCP_variables.jl:126
-    const int ncopies = f.stagewise ? f.stage : 1;
+    const int ncopies = f.stagewise ? f.stage : f.control_steps;   // DOCP_variables.jl:138
     for (int64_t i = 0; i <= N_; ++i) {
         const int64_t o = i * f.blk;
         if (!f.meta.init_state.empty())
@@ -854,7 +855,8 @@ void Model::unpack_host(const double* x, const double* y, double* time, double* 
     ensure_staging();
     const ElemInfo& f = reg_.info;
     const size_t b = (size_t)batch_, n1 = (size_t)N_ + 1;
-    const size_t sz[7] = {b * n1, b * n1 * f.nx, b * n1 * f.nu, b * f.nv, b * N_ * f.nx, b * n1 * f.np, b * f.nb};
+    const size_t nc = (size_t)N_ * f.control_steps + 1;   // rows of the control array (common.jl:82-99)
+    const size_t sz[7] = {b * n1, b * n1 * f.nx, b * nc * f.nu, b * f.nv, b * N_ * f.nx, b * n1 * f.np, b * f.nb};
     double* host[7] = {time, state, control, variable, costate, path_dual, boundary_dual};
     double* dev[7] = {nullptr};
     size_t total = 0;

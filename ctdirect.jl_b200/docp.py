@@ -46,6 +46,19 @@ class Collocation:
 
 
 @dataclass
+class DirectShooting:
+    """DirectShooting discretizer options (src/direct_shooting.jl:12-41): `control_steps` controls per time step,
+    midpoint rule.  `discretize(ocp, DirectShooting(grid_size=50, control_steps=10))`."""
+    grid_size: int = 250
+    control_steps: int = 1
+    scheme: str = "midpoint"
+    time_grid = None            # DOCP(ocp, grid_size, control_steps, scheme, nothing): direct_shooting.jl:63-64
+
+    def __post_init__(self):
+        self.scheme = str(self.scheme).lstrip(":")
+
+
+@dataclass
 class Meta:
     """Subset of NLPModels' NLPModelMeta that CTDirect's builders fill (src/collocation.jl:137-149)."""
     nvar: int
@@ -78,7 +91,7 @@ class DOCP:
 
     def __init__(self, ocp, grid_size: int = 250, scheme: str = "midpoint", time_grid=None, params=None,
                  pattern_mode: str = "reference", batch: int = 1, device: int = 0, disc_method: Optional[str] = None,
-                 stream: str = "torch"):
+                 stream: str = "torch", control_steps: int = 1):
         if stream not in ("torch", "own"):
             raise ValueError("stream must be 'torch' (follow torch's current stream) or 'own'")
         self._stream_mode, self._stream_set = stream, None
@@ -98,6 +111,9 @@ class DOCP:
         d.pattern_mode = {"reference": 0, "corrected": 1, "optimized": 2}[pattern_mode]
         d.batch = int(batch)
         d.device = int(device)
+        d.control_steps = int(control_steps)
+        if int(control_steps) > 1:
+            pattern_mode = "optimized"     # the only pattern DirectShooting has (direct_shooting.jl:101-137)
         h = C.c_void_p()
         _lib.check(lib.ctd_create(C.byref(d), C.byref(h)))
         self._h = h
@@ -112,6 +128,7 @@ class DOCP:
          self.step_constraints_block, self.batch) = (int(q) for q in info[:9])
         self.free_t0, self.free_tf, self.lagrange, self.mayer, self.max = (bool(q) for q in info[9:14])
         self.npar, self.stage = int(info[14]), int(info[15])
+        self.control_steps = int(lib.ctd_control_steps(h))
         self._nlp = None
 
     # convenient aliases
@@ -355,7 +372,7 @@ class DOCP:
         x = self._check_in(x, self.nvar, "x")
         y = self._check_in(y, self.ncon, "y")
         N, B = self.steps, self.batch
-        shapes = {"time": (N + 1,), "state": (N + 1, self.NLP_x), "control": (N + 1, self.NLP_u),
+        shapes = {"time": (N + 1,), "state": (N + 1, self.NLP_x), "control": (N * self.control_steps + 1, self.NLP_u),
                   "variable": (self.NLP_v,), "costate": (N, self.NLP_x), "path_dual": (N + 1, self.path_cons),
                   "boundary_dual": (self.boundary_cons,)}
         keys = [k for k in shapes if (want is None or k in want)
@@ -373,6 +390,13 @@ class DOCP:
         self._follow_stream(x)
         fn = self._lib.ctd_unpack_dev if _is_torch(x) else self._lib.ctd_unpack
         _lib.check(fn(self._h, _ptr(x), _ptr(y), C.byref(sol)))
+        return out
+
+    def control_time(self, time):
+        """T_control of build_OCP_solution (src/DOCP_data.jl:555-566) from the `time` array of `unpack`."""
+        t = np.ascontiguousarray(time.cpu().numpy() if _is_torch(time) else time, dtype=np.float64)
+        out = np.empty(t.shape[:-1] + (self.steps * self.control_steps + 1,))
+        _lib.check(self._lib.ctd_control_time(self._h, t.ctypes.data_as(_lib._dp), out.ctypes.data_as(_lib._dp)))
         return out
 
     def pack(self, state=None, control=None, variable=None, stage_control=None):
@@ -587,6 +611,8 @@ class B200NLPModel:
 def discretize(ocp, discretizer: Optional[Collocation] = None, **kwargs) -> DOCP:
     """CTDirect.discretize(ocp, Collocation(...)) (src/CTDirect.jl:31-50)."""
     d = discretizer or Collocation()
+    if isinstance(d, DirectShooting):
+        return DOCP(ocp, grid_size=d.grid_size, scheme=d.scheme, control_steps=d.control_steps, **kwargs)
     return DOCP(ocp, grid_size=d.grid_size, scheme=d.scheme, time_grid=d.time_grid, **kwargs)
 
 

@@ -170,9 +170,10 @@ def build_step_element(ocp: OCP, scheme: str, pattern_mode: str = "reference") -
     cost = sp.Integer(0)
     inter, icode = [], []
     zn = [f"z{a}" for a in range(L.nz)]
-    if scheme == "midpoint":
+    if pat.is_midpoint(scheme):
         # midpoint.jl:54-66: ts = 0.5*(ti + tip1), xs = 0.5*(xi + xip1)
-        ui = z[nx:nx + nu]
+        ncs = L.control_steps
+        us = [z[nx + j * nu:nx + (j + 1) * nu] for j in range(ncs)]
         tsm = sp.Symbol("m_t")
         inter.append((tsm, half * (ti + tp)))
         icode.append("const double m_t = CTD_MUL(0.5, CTD_ADD(ti, tp));")
@@ -182,10 +183,30 @@ def build_step_element(ocp: OCP, scheme: str, pattern_mode: str = "reference") -
             xs.append(sk)
             inter.append((sk, half * (xi[k] + xn[k])))
             icode.append(f"const double m_x{k} = CTD_MUL(0.5, CTD_ADD({zn[k]}, {zn[L.n_own + k]}));")
-        f = dyn(tsm, xs, ui)
-        rows = [xn[k] - (xi[k] + h * f[k]) for k in range(nx)]
-        cost = h * lag(tsm, xs, ui)
-        u_node = ui
+        if ncs == 1:
+            f = dyn(tsm, xs, us[0])
+            rows = [xn[k] - (xi[k] + h * f[k]) for k in range(nx)]
+            cost = h * lag(tsm, xs, us[0])
+        else:
+            # several controls per step (midpoint.jl:57-65,98-113,145-154): hi = (tip1 - ti) / control_steps; EVERY
+            # sub-step evaluates the dynamics at the midpoint (ts, xs) of the whole step, with its own control, and the
+            # state is advanced sub-step by sub-step; the running cost uses the sub-step midpoints tij = ti + (j - 0.5) hi
+            hs = sp.Symbol("m_h")
+            inter.append((hs, h / ncs))
+            icode.append(f"const double m_h = hh / {float(ncs)!r};")
+            rows = list(xi)
+            for j in range(ncs):
+                f = dyn(tsm, xs, us[j])
+                rows = [rows[k] + hs * f[k] for k in range(nx)]
+            rows = [xn[k] - rows[k] for k in range(nx)]
+            cost = sp.Integer(0)
+            if ocp.lagrange:
+                for j in range(ncs):
+                    tij = sp.Symbol(f"m_t{j}")
+                    inter.append((tij, ti + (j + half) * h / ncs))   # in terms of h: intermediates do not nest
+                    icode.append(f"const double m_t{j} = CTD_ADD(ti, CTD_MUL({j + 0.5!r}, m_h));")
+                    cost = cost + hs * lag(tij, xs, us[j])
+        u_node = us[0]       # path constraints read the first control of the step (common.jl:140-155, j = 1)
     elif scheme in ("euler", "euler_implicit"):
         # euler.jl:79-159: f at (t_i, x_i, U_i) (explicit) or at (t_{i+1}, x_{i+1}, U_i) (implicit)
         ui = z[nx:nx + nu]
@@ -403,7 +424,7 @@ def _fpath_symbols(ocp: OCP, scheme: str, L, ts, p):
         _, Bw, _ = butcher_symbols(L.stage)
         u = [sum(Bw[j] * ublk[j * nu + k] for j in range(L.stage)) for k in range(nu)]
     else:
-        u = ublk
+        u = ublk[:nu]      # u(tf) = first control of the last step (common.jl:140-155)
     rows = [sp.sympify(e) for e in ocp.path(ts.ti, x, u, v, p)] if d.np else []
     return z, rows
 
@@ -520,7 +541,7 @@ def build_final_path(ocp: OCP, scheme: str, E: StepElement) -> EdgeElement:
         _, Bw, _ = butcher_symbols(L.stage)
         u = [sum(Bw[j] * ublk[j * nu + k] for j in range(L.stage)) for k in range(nu)]
     else:
-        u = ublk
+        u = ublk[:nu]
     ts = E.ts
     rows = [sp.sympify(e) for e in ocp.path(ts.ti, x, u, v, E.p)] if d.np else []
     D = Differ(z, cb + nx, nv, TimeSyms(ts.ti, ts.tp, ts.h, ts.dti, {}, {}))

@@ -126,11 +126,19 @@ def _cons_lines(ocp: OCP, E: el.StepElement):
     xi = z[0:nx]
     xn = z[L.n_own:L.n_own + nx]
     out = []
-    if E.scheme == "midpoint":
+    if pat.is_midpoint(E.scheme) and L.control_steps == 1:
         # midpoint.jl:139  c = xip1 - (xi + hi*f(ts, xs, ui, v))
         out += _dyn_lines(ocp, "c_", "m_t", [f"m_x{k}" for k in range(nx)], z[nx:nx + nu], vs, E.p)
         for k in range(nx):
             out.append(f"s.template c<{k}>(CTD_SUB({xn[k]}, CTD_ADD({xi[k]}, CTD_MUL(hh, c_f{k}))));")
+    elif pat.is_midpoint(E.scheme):
+        # midpoint.jl:145-154  x_next = xi; x_next += hi * f(ts, xs, u_ij, v) for j = 1..control_steps; c = xip1 - x_next
+        acc = list(xi)
+        for j in range(L.control_steps):
+            out += _dyn_lines(ocp, f"c{j}_", "m_t", [f"m_x{k}" for k in range(nx)], z[nx + j * nu:nx + (j + 1) * nu], vs, E.p)
+            acc = [f"CTD_ADD({acc[k]}, CTD_MUL(m_h, c{j}_f{k}))" for k in range(nx)]
+        for k in range(nx):
+            out.append(f"s.template c<{k}>(CTD_SUB({xn[k]}, {acc[k]}));")
     elif E.scheme in ("euler", "euler_implicit"):
         # euler.jl:140-159  c = xip1 - (xi + hi*f), f at node i (explicit) or node i+1 (implicit)
         if E.scheme == "euler":
@@ -217,7 +225,7 @@ def emit_pair(ocp: OCP, scheme: str, pattern_mode: str = "reference") -> str:
     o.append(f"struct {name} {{\n")
     o.append(f"  static constexpr const char* PROBLEM = \"{ocp.name}\";\n  static constexpr const char* SCHEME = \"{scheme}\";\n")
     o.append(f"  static constexpr int SCHEME_ID = {scheme_id}, PATTERN_MODE = {['reference', 'corrected', 'optimized'].index(pattern_mode)};\n")
-    o.append(f"  static constexpr int NX = {d.nx}, NU = {d.nu}, NV = {d.nv}, NP = {d.np}, NB = {d.nb}, NPAR = {ocp.npar}, STAGE = {s};\n")
+    o.append(f"  static constexpr int NX = {d.nx}, NU = {d.nu}, NV = {d.nv}, NP = {d.np}, NB = {d.nb}, NPAR = {ocp.npar}, STAGE = {s}, CONTROL_STEPS = {L.control_steps};\n")
     b = lambda x: "true" if x else "false"
     o.append(f"  static constexpr bool FREE_T0 = {b(ocp.free_t0)}, FREE_TF = {b(ocp.free_tf)}, LAGRANGE = {b(d.lagrange)}, "
              f"MAYER = {b(d.mayer)}, IS_MAX = {b(ocp.criterion == 'max')}, IRK = {b(L.irk)}, STAGEWISE = {b(L.stagewise)}, "

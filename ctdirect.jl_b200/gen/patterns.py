@@ -26,7 +26,18 @@ SCHEMES = {
     "gauss_legendre_3": (3, True, True, False),
     "euler": (0, False, False, False),            # explicit Euler, src/ode/euler.jl
     "euler_implicit": (0, False, False, False),   # implicit Euler, src/ode/euler.jl (explicit=false)
+    # midpoint rule with several controls per time step (the DirectShooting discretizer: src/direct_shooting.jl:55-71,
+    # midpoint.jl:20,57-65,98-113,145-154); the number of control steps is a compile-time constant of the element
+    "midpoint_cs2": (0, False, False, False),
+    "midpoint_cs3": (0, False, False, False),
+    "midpoint_cs10": (0, False, False, False),
 }
+
+CONTROL_STEPS = {"midpoint_cs2": 2, "midpoint_cs3": 3, "midpoint_cs10": 10}
+
+
+def is_midpoint(scheme: str) -> bool:
+    return scheme == "midpoint" or scheme in CONTROL_STEPS
 
 
 @dataclass
@@ -51,7 +62,8 @@ class Layout:
         d = self.dims
         self.stage, self.irk, self.stagewise, self.final_control = SCHEMES[self.scheme]
         s = self.stage
-        self.control_block = d.nu * s if self.stagewise else d.nu
+        self.control_steps = CONTROL_STEPS.get(self.scheme, 1)
+        self.control_block = d.nu * s if self.stagewise else d.nu * self.control_steps   # midpoint.jl:20
         self.step_block = d.nx + self.control_block + (s * d.nx if self.irk else 0)
         self.eqs_block = d.nx * (1 + s) if self.irk else d.nx
         self.cblock = self.eqs_block + d.np
@@ -106,7 +118,7 @@ def jacobian_pattern(L: Layout, pattern_mode: str = "reference"):
         co = (i - 1) * cb
         vo = (i - 1) * B
         dyn0, dyn1 = co + 1, co + nx
-        if L.scheme == "midpoint":
+        if is_midpoint(L.scheme):
             T.block(dyn0, dyn1, vo + 1, vo + B + nx)
             T.block(co + nx + 1, co + cb, vo + 1, vo + nx + nu)
             T.block(co + 1, co + cb, v0, v1)
@@ -169,7 +181,7 @@ def hessian_pattern(L: Layout, pattern_mode: str = "reference"):
     T.block(v0, v1, v0, v1)
     for i in range(1, N + 1):
         vo = (i - 1) * B
-        if L.scheme == "midpoint":
+        if is_midpoint(L.scheme):
             T.block(vo + 1, vo + B + nx, vo + 1, vo + B + nx)
             T.block(vo + 1, vo + B + nx, v0, v1, sym=True)
         elif L.scheme in ("euler", "euler_implicit"):
@@ -207,7 +219,7 @@ def hessian_pattern(L: Layout, pattern_mode: str = "reference"):
             T.block(xf0, xf1, v0, v1, sym=True)
         T.block(uf0, uf1, v0, v1, sym=True)
         T.block(1, nx, xf0, xf1, sym=True)
-    elif L.scheme in ("midpoint", "euler", "euler_implicit"):
+    elif is_midpoint(L.scheme) or L.scheme in ("euler", "euler_implicit"):
         T.block(1, nx, xf0, xf1, sym=True)  # quirk Q4: always (midpoint.jl:286-291, euler.jl:345-350)
     else:
         if d.mayer or d.nb > 0:

@@ -37,6 +37,7 @@ struct CtdDesc
     pattern_mode::Int32
     batch::Int32
     device::Int32
+    control_steps::Int32     # > 1: the DirectShooting discretizer (src/direct_shooting.jl:55-71), midpoint only
 end
 
 last_error() = unsafe_string(ccall((:ctd_last_error, LIB), Cstring, ()))
@@ -73,14 +74,15 @@ mutable struct Handle
 end
 
 function create_handle(problem::AbstractString, scheme::AbstractString; grid_size::Integer, normalized_grid=nothing,
-                       params=nothing, pattern_mode::Integer=0, device::Integer=0)
+                       params=nothing, pattern_mode::Integer=0, device::Integer=0, control_steps::Integer=1)
     h = Ref{Ptr{Cvoid}}(C_NULL)
     tg = normalized_grid === nothing ? Float64[] : Vector{Float64}(normalized_grid)
     par = params === nothing ? Float64[] : Vector{Float64}(params)
     GC.@preserve problem scheme tg par begin
         desc = CtdDesc(Base.unsafe_convert(Cstring, problem), Base.unsafe_convert(Cstring, scheme), Int32(grid_size),
                        isempty(tg) ? C_NULL : pointer(tg), Int32(length(tg)),
-                       isempty(par) ? C_NULL : pointer(par), Int32(length(par)), Int32(pattern_mode), Int32(1), Int32(device))
+                       isempty(par) ? C_NULL : pointer(par), Int32(length(par)), Int32(pattern_mode), Int32(1), Int32(device),
+                       Int32(control_steps))
         check(ccall((:ctd_create, LIB), Cint, (Ref{CtdDesc}, Ref{Ptr{Cvoid}}), desc, h))
     end
     hd = Handle(h[], Dict{Symbol,Float64}())
@@ -149,10 +151,10 @@ Replaces `ADNLPModels.ADNLPModel!(f, x0, lvar, uvar, c!, lcon, ucon; ...)` of sr
 `scheme` is a library scheme name (`scheme_name`) or the reference's symbol (`:midpoint`, `:gauss_legendre_3`, ...).
 """
 function B200DOCPModel(problem::AbstractString, scheme; grid_size::Integer=250, normalized_grid=nothing,
-                       params=nothing, x0=nothing, pattern_mode::Integer=0, device::Integer=0)
+                       params=nothing, x0=nothing, pattern_mode::Integer=0, device::Integer=0, control_steps::Integer=1)
     sch = String(scheme)
     hd = create_handle(problem, sch; grid_size=grid_size, normalized_grid=normalized_grid, params=params,
-                       pattern_mode=pattern_mode, device=device)
+                       pattern_mode=pattern_mode, device=device, control_steps=control_steps)
     return B200DOCPModel(handle_meta(hd, "CTDirectB200:$problem:$sch"; x0=x0), Counters(), hd)
 end
 
@@ -220,10 +222,11 @@ end
 devptr(v) = reinterpret(Ptr{Cvoid}, pointer(v))
 
 function B200DOCPModelGPU(::Type{V}, problem::AbstractString, scheme; grid_size::Integer=250, normalized_grid=nothing,
-                          params=nothing, x0=nothing, pattern_mode::Integer=0, device::Integer=0) where {V}
+                          params=nothing, x0=nothing, pattern_mode::Integer=0, device::Integer=0,
+                          control_steps::Integer=1) where {V}
     sch = String(scheme)
     hd = create_handle(problem, sch; grid_size=grid_size, normalized_grid=normalized_grid, params=params,
-                       pattern_mode=pattern_mode, device=device)
+                       pattern_mode=pattern_mode, device=device, control_steps=control_steps)
     mh = handle_meta(hd, "CTDirectB200:$problem:$sch:gpu"; x0=x0)
     meta = NLPModelMeta{Float64,V}(mh.nvar; ncon=mh.ncon, x0=V(mh.x0), lvar=V(mh.lvar), uvar=V(mh.uvar), lcon=V(mh.lcon),
                                    ucon=V(mh.ucon), nnzj=mh.nnzj, nnzh=mh.nnzh, minimize=mh.minimize, name=mh.name)
@@ -295,11 +298,14 @@ does not give `s` back bit for bit.  The dimensions the library derives are chec
 function b200_model_builder(problem::AbstractString, docp; device_vector=nothing, params=nothing)
     return function build_b200_model(initial_guess=nothing; backend=:b200, kwargs...)
         sch = scheme_name(docp.discretization)
-        docp.time.control_steps == 1 || error("CTDirectB200: control_steps > 1 (DirectShooting) has no compiled kernel")
+        # DirectShooting (src/direct_shooting.jl:55-71): docp.time.control_steps controls per step, midpoint only; the
+        # library then uses the detected pattern whatever `backend` says (there is no :manual pattern for it)
+        cs = docp.time.control_steps
+        (cs == 1 || sch == "midpoint") || error("CTDirectB200: control_steps > 1 is compiled for the midpoint scheme only")
         x0 = initial_guess isa AbstractVector ? initial_guess : nothing     # an NLP vector; else the library's __initial_guess
         args = (problem, sch)
         kw = (grid_size=docp.time.steps, normalized_grid=docp.time.normalized_grid, params=params, x0=x0,
-              pattern_mode=pattern_mode(backend))
+              pattern_mode=pattern_mode(backend), control_steps=cs)
         nlp = device_vector === nothing ? B200DOCPModel(args...; kw...) : B200DOCPModelGPU(device_vector, args...; kw...)
         (nlp.meta.nvar == docp.dim_NLP_variables && nlp.meta.ncon == docp.dim_NLP_constraints) ||
             error("CTDirectB200: the library's model ($(nlp.meta.nvar), $(nlp.meta.ncon)) does not match the DOCP " *
@@ -319,9 +325,10 @@ given by NAME: no CTDirect DOCP object is needed, the library holds the discreti
 strictly increasing grid; it is normalised like DOCPtime does (src/DOCP_data.jl:186-196).
 """
 function direct_transcription(problem::AbstractString; grid_size::Integer=250, disc_method::Symbol=:midpoint, scheme::Symbol=disc_method,
-                              time_grid=nothing, init=nothing, params=nothing, backend::Symbol=:manual, device_vector=nothing)
+                              time_grid=nothing, init=nothing, params=nothing, backend::Symbol=:manual, device_vector=nothing,
+                              control_steps::Integer=1)
     kw = (grid_size=time_grid === nothing ? grid_size : length(time_grid) - 1, normalized_grid=time_grid, params=params,
-          x0=init, pattern_mode=pattern_mode(backend))
+          x0=init, pattern_mode=pattern_mode(backend), control_steps=control_steps)
     return device_vector === nothing ? B200DOCPModel(problem, scheme; kw...) : B200DOCPModelGPU(device_vector, problem, scheme; kw...)
 end
 

@@ -65,6 +65,12 @@ typedef struct ctd_desc {
     int32_t pattern_mode;     /* CTD_PATTERN_*                                                               */
     int32_t batch;            /* number of independent instances (>= 1)                                      */
     int32_t device;           /* CUDA device ordinal                                                         */
+    int32_t control_steps;    /* controls per time step: 0 or 1 = collocation (collocation.jl:65); > 1 = the
+                                 DirectShooting discretizer (src/direct_shooting.jl:55-71: DOCP(ocp, grid_size,
+                                 control_steps, :midpoint, nothing)).  scheme must be "midpoint"; the only pattern
+                                 is the detected one (pattern_mode is ignored: DirectShooting hands no :manual
+                                 pattern to ADNLPModels, direct_shooting.jl:101-137).  Compiled for 2, 3 (every
+                                 problem with a control) and 10 (goddard, double_integrator_minenergy, vanderpol) */
 } ctd_desc;
 
 /* DOCP(ocp, grid_size, control_steps, scheme, time_grid) + __variables_bounds! + __constraints_bounds!
@@ -137,7 +143,7 @@ CTD_API int ctd_violation_dev(ctd_handle h, const double* c, double* viol);
 typedef struct ctd_solution {
     double* time;          /* (N+1)        time grid t0 + s (tf - t0), DOCP_data.jl:437-458          */
     double* state;         /* (N+1) x nx   val = :state                                               */
-    double* control;       /* (N+1) x nu   val = :control (final control duplicated where aliased)    */
+    double* control;       /* (N * control_steps + 1) x nu   val = :control (final control duplicated where aliased) */
     double* variable;      /* nv           val = :variable                                            */
     double* costate;       /* N x nx       val = :costate: multipliers of the state equations         */
     double* path_dual;     /* (N+1) x np   val = :mult_path_constraints divided by the step length    */
@@ -145,6 +151,11 @@ typedef struct ctd_solution {
 } ctd_solution;
 CTD_API int ctd_unpack(ctd_handle h, const double* x, const double* y, const ctd_solution* out);
 CTD_API int ctd_unpack_dev(ctd_handle h, const double* x, const double* y, const ctd_solution* out);
+/* controls per time step of the handle (1 for collocation) and T_control of build_OCP_solution
+ * (src/DOCP_data.jl:555-566): control_time[N * control_steps + 1] from the time[N+1] that ctd_unpack returned
+ * (host arrays, one instance after the other). */
+CTD_API int32_t ctd_control_steps(ctd_handle h);
+CTD_API int ctd_control_time(ctd_handle h, const double* time, double* control_time);
 /* Initial guess / warm start, the inverse of ctd_unpack: __initial_guess (src/DOCP_variables.jl:122-145,
  * irk_stagewise.jl:302-335) from SAMPLED data -- x = 0.1 everywhere, then variable, state[(N+1) x nx] at the
  * nodes and control[(N+1) x nu] through the setters of src/ode/common.jl:184-225 (final control only where

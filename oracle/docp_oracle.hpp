@@ -44,6 +44,11 @@ enum SchemeId {
     GL3_STAGEWISE = 6,    // :gauss_legendre_3  irk_stagewise.jl
     EULER_EXPLICIT = 7,   // :euler | :euler_explicit | :euler_forward   src/ode/euler.jl
     EULER_IMPLICIT = 8,   // :euler_implicit | :euler_backward           src/ode/euler.jl
+    // midpoint with several controls per time step: the DirectShooting discretizer (src/direct_shooting.jl:55-71 ->
+    // DOCP(ocp, grid_size, control_steps, :midpoint, nothing); midpoint.jl:20,57-65,98-113,145-154)
+    MIDPOINT_CS2 = 9,
+    MIDPOINT_CS3 = 10,
+    MIDPOINT_CS10 = 11,
 };
 
 inline int scheme_from_name(const std::string& s) {
@@ -57,19 +62,26 @@ inline int scheme_from_name(const std::string& s) {
     if (s == "gauss_legendre_3") return GL3_STAGEWISE;
     if (s == "euler" || s == "euler_explicit" || s == "euler_forward") return EULER_EXPLICIT;   // DOCP_data.jl:315
     if (s == "euler_implicit" || s == "euler_backward") return EULER_IMPLICIT;                  // DOCP_data.jl:318
+    if (s == "midpoint_cs2") return MIDPOINT_CS2;
+    if (s == "midpoint_cs3") return MIDPOINT_CS3;
+    if (s == "midpoint_cs10") return MIDPOINT_CS10;
     return -1;
 }
 
 template <int SCH> struct SchemeTraits;
-template <> struct SchemeTraits<TRAPEZE> { static constexpr int stage = 0; static constexpr bool irk = false, stagewise = false, final_control = true; };
-template <> struct SchemeTraits<MIDPOINT> { static constexpr int stage = 0; static constexpr bool irk = false, stagewise = false, final_control = false; };
-template <> struct SchemeTraits<GL1_CONST> { static constexpr int stage = 1; static constexpr bool irk = true, stagewise = false, final_control = false; };
-template <> struct SchemeTraits<GL2_CONST> { static constexpr int stage = 2; static constexpr bool irk = true, stagewise = false, final_control = false; };
-template <> struct SchemeTraits<GL3_CONST> { static constexpr int stage = 3; static constexpr bool irk = true, stagewise = false, final_control = false; };
-template <> struct SchemeTraits<GL2_STAGEWISE> { static constexpr int stage = 2; static constexpr bool irk = true, stagewise = true, final_control = false; };
-template <> struct SchemeTraits<GL3_STAGEWISE> { static constexpr int stage = 3; static constexpr bool irk = true, stagewise = true, final_control = false; };
-template <> struct SchemeTraits<EULER_EXPLICIT> { static constexpr int stage = 0; static constexpr bool irk = false, stagewise = false, final_control = false; };
-template <> struct SchemeTraits<EULER_IMPLICIT> { static constexpr int stage = 0; static constexpr bool irk = false, stagewise = false, final_control = false; };
+template <> struct SchemeTraits<TRAPEZE> { static constexpr int stage = 0; static constexpr bool irk = false, stagewise = false, final_control = true; static constexpr int control_steps = 1; static constexpr bool midpoint = false; };
+template <> struct SchemeTraits<MIDPOINT> { static constexpr int stage = 0; static constexpr bool irk = false, stagewise = false, final_control = false; static constexpr int control_steps = 1; static constexpr bool midpoint = true; };
+template <> struct SchemeTraits<GL1_CONST> { static constexpr int stage = 1; static constexpr bool irk = true, stagewise = false, final_control = false; static constexpr int control_steps = 1; static constexpr bool midpoint = false; };
+template <> struct SchemeTraits<GL2_CONST> { static constexpr int stage = 2; static constexpr bool irk = true, stagewise = false, final_control = false; static constexpr int control_steps = 1; static constexpr bool midpoint = false; };
+template <> struct SchemeTraits<GL3_CONST> { static constexpr int stage = 3; static constexpr bool irk = true, stagewise = false, final_control = false; static constexpr int control_steps = 1; static constexpr bool midpoint = false; };
+template <> struct SchemeTraits<GL2_STAGEWISE> { static constexpr int stage = 2; static constexpr bool irk = true, stagewise = true, final_control = false; static constexpr int control_steps = 1; static constexpr bool midpoint = false; };
+template <> struct SchemeTraits<GL3_STAGEWISE> { static constexpr int stage = 3; static constexpr bool irk = true, stagewise = true, final_control = false; static constexpr int control_steps = 1; static constexpr bool midpoint = false; };
+template <> struct SchemeTraits<EULER_EXPLICIT> { static constexpr int stage = 0; static constexpr bool irk = false, stagewise = false, final_control = false; static constexpr int control_steps = 1; static constexpr bool midpoint = false; };
+template <int CS> struct MidpointControlSteps { static constexpr int stage = 0; static constexpr bool irk = false, stagewise = false, final_control = false; static constexpr int control_steps = CS; static constexpr bool midpoint = true; };
+template <> struct SchemeTraits<MIDPOINT_CS2> : MidpointControlSteps<2> {};
+template <> struct SchemeTraits<MIDPOINT_CS3> : MidpointControlSteps<3> {};
+template <> struct SchemeTraits<MIDPOINT_CS10> : MidpointControlSteps<10> {};
+template <> struct SchemeTraits<EULER_IMPLICIT> { static constexpr int stage = 0; static constexpr bool irk = false, stagewise = false, final_control = false; static constexpr int control_steps = 1; static constexpr bool midpoint = false; };
 
 // Butcher tableaux, computed from the same expressions as irk.jl:41-43,78-80,116-122
 struct Butcher {
@@ -216,7 +228,8 @@ struct Docp {
     using ST = SchemeTraits<SCH>;
     static constexpr int nx = P::nx, nu = P::nu, nv = P::nv, np = P::np, nb = P::nb;
     static constexpr int s = ST::stage;
-    static constexpr int control_block = ST::stagewise ? nu * s : nu;       // irk_stagewise.jl:138
+    static constexpr int control_steps = ST::control_steps;                 // DOCP_data.jl:149
+    static constexpr int control_block = ST::stagewise ? nu * s : nu * control_steps;   // irk_stagewise.jl:138, midpoint.jl:20
     static constexpr int step_block = nx + control_block + (ST::irk ? s * nx : 0);
     static constexpr int eqs_block = ST::irk ? nx * (1 + s) : nx;           // irk.jl:144
     static constexpr int cblock = eqs_block + np;
@@ -320,15 +333,28 @@ struct Docp {
         T xi[nx], xip1[nx];
         load(a, state_off(i), nx, xi);
         load(a, state_off(i + 1), nx, xip1);
-        if constexpr (SCH == MIDPOINT) {
-            // setWorkArray midpoint.jl:47-72 + stepStateConstraints! midpoint.jl:124-141
+        if constexpr (ST::midpoint) {
+            // setWorkArray midpoint.jl:47-72 + stepStateConstraints! midpoint.jl:124-156
             T ts = 0.5 * (ti + tip1);
             T xs[nx], u[nu > 0 ? nu : 1], f[nx];
             for (int k = 0; k < nx; ++k) xs[k] = 0.5 * (xi[k] + xip1[k]);
-            load(a, control_off(i), nu, u);
-            P::template dynamics<T>(f, ts, xs, u, v, p);
-            T hi = (tip1 - ti) / 1.0;  // control_steps == 1
-            for (int k = 0; k < nx; ++k) c[k] = xip1[k] - (xi[k] + hi * f[k]);
+            T hi = (tip1 - ti) / (double)control_steps;
+            if constexpr (control_steps == 1) {
+                load(a, control_off(i), nu, u);
+                P::template dynamics<T>(f, ts, xs, u, v, p);
+                for (int k = 0; k < nx; ++k) c[k] = xip1[k] - (xi[k] + hi * f[k]);
+            } else {
+                // midpoint.jl:145-154: every sub-step uses the dynamics at (ts, xs) of the WHOLE step (the work array
+                // of l.57-65) with its own control; x_next = xi; x_next += hi * work_j
+                T x_next[nx];
+                for (int k = 0; k < nx; ++k) x_next[k] = xi[k];
+                for (int j = 1; j <= control_steps; ++j) {
+                    load(a, control_off(i, j), nu, u);
+                    P::template dynamics<T>(f, ts, xs, u, v, p);
+                    for (int k = 0; k < nx; ++k) x_next[k] = x_next[k] + hi * f[k];
+                }
+                for (int k = 0; k < nx; ++k) c[k] = xip1[k] - x_next[k];
+            }
         } else if constexpr (SCH == EULER_EXPLICIT || SCH == EULER_IMPLICIT) {
             // setWorkArray euler.jl:79-104 (f at node i, or at node i+1 for the implicit rule) +
             // stepStateConstraints! euler.jl:140-159
@@ -431,14 +457,28 @@ struct Docp {
         T ti = time_at(a, i), tip1 = time_at(a, i + 1);
         T xi[nx];
         load(a, state_off(i), nx, xi);
-        if constexpr (SCH == MIDPOINT) {
+        if constexpr (ST::midpoint) {
             T xip1[nx], xs[nx], u[nu > 0 ? nu : 1];
             load(a, state_off(i + 1), nx, xip1);
-            T hi = tip1 - ti;
-            T ts = 0.5 * (ti + tip1);
             for (int k = 0; k < nx; ++k) xs[k] = 0.5 * (xi[k] + xip1[k]);
-            load(a, control_off(i), nu, u);
-            return hi * P::template lagrange<T>(ts, xs, u, v, p);
+            if constexpr (control_steps == 1) {
+                T hi = tip1 - ti;
+                T ts = 0.5 * (ti + tip1);
+                load(a, control_off(i), nu, u);
+                return hi * P::template lagrange<T>(ts, xs, u, v, p);
+            } else {
+                // integral(): midpoint.jl:98-113 -- sub-step midpoints tij = ti + (j - 0.5) hi
+                T hi = (tip1 - ti) / (double)control_steps;
+                T value(0.0);
+                for (int j = 1; j <= control_steps; ++j) {
+                    T tij = ti + (j - 0.5) * hi;
+                    load(a, control_off(i, j), nu, u);
+                    T term = hi * P::template lagrange<T>(tij, xs, u, v, p);
+                    if (j == 1) value = term;
+                    else value = value + term;
+                }
+                return value;
+            }
         } else if constexpr (SCH == EULER_EXPLICIT || SCH == EULER_IMPLICIT) {
             // integral(): euler.jl:111-133
             T hi = tip1 - ti;
@@ -545,7 +585,8 @@ struct Docp {
             if (ST::stagewise) continue;
             // set_control_at_time_step!: common.jl:212-225 (final control only if the scheme has one)
             if (nu > 0 && (i <= N || ST::final_control))
-                for (int k = 0; k < nu; ++k) { lb[control_off(i) + k] = ul[k]; ub[control_off(i) + k] = uub[k]; }
+                for (int j = 1; j <= control_steps; ++j)      // DOCP_variables.jl:44
+                    for (int k = 0; k < nu; ++k) { lb[control_off(i, j) + k] = ul[k]; ub[control_off(i, j) + k] = uub[k]; }
         }
         if (ST::stagewise && nu > 0)
             for (int i = 1; i <= N; ++i)
@@ -566,7 +607,8 @@ struct Docp {
             if (!meta.init_state.empty())
                 for (int k = 0; k < nx; ++k) x0[state_off(i) + k] = meta.init_state[k];
             if (!ST::stagewise && nu > 0 && !meta.init_control.empty() && (i <= N || ST::final_control))
-                for (int k = 0; k < nu; ++k) x0[control_off(i) + k] = meta.init_control[k];
+                for (int j = 1; j <= control_steps; ++j)      // DOCP_variables.jl:138
+                    for (int k = 0; k < nu; ++k) x0[control_off(i, j) + k] = meta.init_control[k];
         }
         if (ST::stagewise && nu > 0 && !meta.init_control.empty())
             for (int i = 1; i <= N; ++i)
@@ -663,7 +705,7 @@ struct Docp {
             const int64_t c_offset = (i - 1) * cblock;
             const int64_t var_offset = (i - 1) * B;
             const int64_t dyn_start = c_offset + 1, dyn_end = c_offset + nx;
-            if constexpr (SCH == MIDPOINT) {
+            if constexpr (ST::midpoint) {
                 const int64_t xi_start = var_offset + 1, ui_end = var_offset + nx + nu;
                 const int64_t xip1_end = var_offset + B + nx;
                 L.add_block(dyn_start, dyn_end, xi_start, xip1_end);
@@ -746,7 +788,7 @@ struct Docp {
         L.add_block(v_start, v_end, v_start, v_end);
         for (int64_t i = 1; i <= N; ++i) {
             const int64_t var_offset = (i - 1) * B;
-            if constexpr (SCH == MIDPOINT) {
+            if constexpr (ST::midpoint) {
                 const int64_t xi_start = var_offset + 1, xip1_end = var_offset + B + nx;
                 L.add_block(xi_start, xip1_end, xi_start, xip1_end);
                 L.add_block(xi_start, xip1_end, v_start, v_end, true);
@@ -791,7 +833,7 @@ struct Docp {
             }
             L.add_block(uf_start, uf_end, v_start, v_end, true);
             L.add_block(1, nx, xf_start, xf_end, true);
-        } else if constexpr (SCH == MIDPOINT || SCH == EULER_EXPLICIT || SCH == EULER_IMPLICIT) {
+        } else if constexpr (ST::midpoint || SCH == EULER_EXPLICIT || SCH == EULER_IMPLICIT) {
             L.add_block(1, nx, xf_start, xf_end, true);  // always (quirk Q4): midpoint.jl:286-291, euler.jl:345-350
         } else {
             if (P::has_mayer || nb > 0) L.add_block(1, nx, xf_start, xf_end, true);

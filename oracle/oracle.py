@@ -55,6 +55,8 @@ def _load():
     lib.orc_derivs.argtypes = [C.c_void_p, _dp, _dp, C.c_double, _dp, _dp, _dp, _ip]
     lib.orc_unpack.argtypes = [C.c_void_p] + [_dp] * 9
     lib.orc_pack.argtypes = [C.c_void_p] + [_dp] * 5
+    lib.orc_control_steps.argtypes = [C.c_void_p]
+    lib.orc_control_time.argtypes = [C.c_void_p, _dp, _dp]
     lib.orc_set_threads.restype = C.c_int
     lib.orc_set_threads.argtypes = [C.c_int]
     _lib = lib
@@ -91,6 +93,7 @@ class OracleModel:
         lib.orc_flags(self._h, f)
         self.free_t0, self.free_tf, self.has_lagrange, self.has_mayer, self.is_max = (bool(v) for v in f)
         self.minimize = not self.is_max
+        self.control_steps = int(lib.orc_control_steps(self._h))   # > 1: the DirectShooting discretizer (midpoint_cs*)
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -153,11 +156,14 @@ class OracleModel:
         x = np.ascontiguousarray(x, dtype=np.float64)
         y = None if y is None else np.ascontiguousarray(y, dtype=np.float64)
         N = self.N
-        out = {"time": np.zeros(N + 1), "state": np.zeros((N + 1, self.nx)), "control": np.zeros((N + 1, self.nu)),
+        out = {"time": np.zeros(N + 1), "state": np.zeros((N + 1, self.nx)),
+               "control": np.zeros((N * self.control_steps + 1, self.nu)),
                "variable": np.zeros(self.nv), "costate": np.zeros((N, self.nx)),
                "path_dual": np.zeros((N + 1, self.np_)), "boundary_dual": np.zeros(self.nb)}
         self._lib.orc_unpack(self._h, _p(x), _p(y), *[_p(out[k]) for k in
                              ("time", "state", "control", "variable", "costate", "path_dual", "boundary_dual")])
+        out["control_time"] = np.zeros(N * self.control_steps + 1)
+        self._lib.orc_control_time(self._h, _p(x), _p(out["control_time"]))
         return out
 
     def pack(self, state=None, control=None, variable=None, stage_control=None):

@@ -27,6 +27,8 @@ struct ModelBase {
     virtual void cons(const double* x, double* c) = 0;
     virtual void derivs(const double* x, const double* y, double sigma, double* grad, double* jvals,
                         double* hvals, int64_t* dropped) = 0;
+    virtual int control_steps() const = 0;
+    virtual void control_time(const double* x, double* tc) = 0;
     virtual void unpack(const double* x, const double* y, double* time, double* state, double* control,
                         double* variable, double* costate, double* path_dual, double* boundary_dual) = 0;
     virtual void pack(const double* state, const double* control, const double* variable,
@@ -75,6 +77,18 @@ struct Model : ModelBase {
         d.derivatives(x, y, sigma, o);
         if (dropped) { dropped[0] = o.dropped_j; dropped[1] = o.dropped_h; }
     }
+    int control_steps() const override { return Docp<P, SCH>::control_steps; }
+    // T_control of build_OCP_solution (DOCP_data.jl:555-566): N * control_steps + 1 times
+    void control_time(const double* x, double* tc) override {
+        PlainAcc a{x};
+        const int N = d.N, cs = Docp<P, SCH>::control_steps;
+        int k = 0;
+        for (int i = 1; i <= N; ++i) {
+            const double ti = d.time_at(a, i), h_i = d.time_at(a, i + 1) - ti;
+            for (int j = 1; j <= cs; ++j) tc[k++] = ti + (j - 1) * h_i / cs;
+        }
+        tc[k] = d.time_at(a, N + 1);
+    }
     // getter() of src/ode/common.jl:7-104 + the normalisations of build_OCP_solution
     // (src/DOCP_data.jl:514-633): arrays are [node][component]; y may be NULL (then no duals)
     void unpack(const double* x, const double* y, double* time, double* state, double* control, double* variable,
@@ -87,9 +101,17 @@ struct Model : ModelBase {
             if (time) time[i - 1] = T[i - 1];
             if (state) for (int k = 0; k < P::nx; ++k) state[(i - 1) * P::nx + k] = x[d.state_off(i) + k];
             if (control && P::nu > 0) {
+                // getter(:control), common.jl:82-99: N * control_steps + 1 rows, the last one u(tf)
+                constexpr int cs = Docp<P, SCH>::control_steps;
                 double u[P::nu > 0 ? P::nu : 1];
-                d.get_control(a, i, u);
-                for (int k = 0; k < P::nu; ++k) control[(i - 1) * P::nu + k] = u[k];
+                if (cs == 1 || i == N + 1) {
+                    d.get_control(a, i, u);
+                    const int row = i == N + 1 ? N * cs : i - 1;
+                    for (int k = 0; k < P::nu; ++k) control[row * P::nu + k] = u[k];
+                } else {
+                    for (int j = 1; j <= cs; ++j)
+                        for (int k = 0; k < P::nu; ++k) control[((i - 1) * cs + (j - 1)) * P::nu + k] = x[d.control_off(i, j) + k];
+                }
             }
         }
         if (variable) for (int k = 0; k < P::nv; ++k) variable[k] = x[d.v_off() + k];
@@ -125,7 +147,9 @@ struct Model : ModelBase {
                         else if (control) x[d.stagecontrol_off(i, j) + k] = control[(i - 1) * P::nu + k];
                     }
             } else if (control && (i <= N || ST::final_control)) {
-                for (int k = 0; k < P::nu; ++k) x[(i - 1) * d.step_block + P::nx + k] = control[(i - 1) * P::nu + k];
+                // the node's control for every control step of the time step (DOCP_variables.jl:138-140)
+                for (int j = 1; j <= Docp<P, SCH>::control_steps; ++j)
+                    for (int k = 0; k < P::nu; ++k) x[d.control_off(i, j) + k] = control[(i - 1) * P::nu + k];
             }
         }
     }
@@ -143,6 +167,9 @@ ModelBase* make_for_problem(int sch, int N, const double* tg, int ntg, const dou
         case GL3_STAGEWISE: return new Model<P, GL3_STAGEWISE>(N, tg, ntg, par, npar, pm);
         case EULER_EXPLICIT: return new Model<P, EULER_EXPLICIT>(N, tg, ntg, par, npar, pm);
         case EULER_IMPLICIT: return new Model<P, EULER_IMPLICIT>(N, tg, ntg, par, npar, pm);
+        case MIDPOINT_CS2: return new Model<P, MIDPOINT_CS2>(N, tg, ntg, par, npar, pm);
+        case MIDPOINT_CS3: return new Model<P, MIDPOINT_CS3>(N, tg, ntg, par, npar, pm);
+        case MIDPOINT_CS10: return new Model<P, MIDPOINT_CS10>(N, tg, ntg, par, npar, pm);
     }
     return nullptr;
 }
@@ -204,6 +231,9 @@ void orc_unpack(void* h, const double* x, const double* y, double* time, double*
                 double* variable, double* costate, double* path_dual, double* boundary_dual) {
     static_cast<ModelBase*>(h)->unpack(x, y, time, state, control, variable, costate, path_dual, boundary_dual);
 }
+int orc_control_steps(void* h) { return static_cast<ModelBase*>(h)->control_steps(); }
+void orc_control_time(void* h, const double* x, double* tc) { static_cast<ModelBase*>(h)->control_time(x, tc); }
+
 void orc_pack(void* h, const double* state, const double* control, const double* variable,
               const double* stage_control, double* x) {
     static_cast<ModelBase*>(h)->pack(state, control, variable, stage_control, x);
