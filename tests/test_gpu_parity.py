@@ -255,10 +255,11 @@ def test_solution_unpacking(ctd, oracle_mod):
         x = o.x0() * (1 + 1e-2 * rng.uniform(-1, 1, o.nvar))
         y = rng.standard_normal(o.ncon)
         ref, got = o.unpack(x, y), d.unpack(x, y)
-        assert set(got) == set(ref)
-        for k in ref:
+        assert set(got) | {"control_time"} == set(ref)
+        for k in got:
             assert got[k].shape == ref[k].shape, (problem, scheme, k)
             assert np.array_equal(got[k], ref[k]), (problem, scheme, k)
+        assert np.array_equal(d.control_time(got["time"]), ref["control_time"])   # = time for collocation
         prim = d.unpack(x)                       # box multipliers use the same call without y
         assert set(prim) == {"time", "state", "control", "variable"}
     # batched, device tensors
@@ -271,7 +272,7 @@ def test_solution_unpacking(ctd, oracle_mod):
     d.synchronize()
     for b in range(B):
         ref = o.unpack(x[b], y[b])
-        for k in ref:
+        for k in got:
             assert np.array_equal(got[k][b].cpu().numpy(), ref[k]), (b, k)
 
 
