@@ -574,6 +574,11 @@ def leg_batched(cx, ctd):
                 timed_b(lambda: ppipe.submit(ALL, tx, ty, bout, serial=True), ppipe.drain)
             legs["kernel with fused peer-memory gather; the norms of evaluation k are awaited after evaluation k+1 is queued "
                  "(ctd_eval_gather_dev, 2 slots)"] = timed_b(lambda: ppipe.submit(ALL, tx, ty, bout), ppipe.drain)
+            # 4 slots: a launch that reuses a slot waits (in its first CTA) for every rank to have copied the slot's
+            # previous round out; with 4 slots that round lies 4 evaluations back and the ranks are coupled less tightly
+            ppipe4 = PeerNormsPipeline(bd, rank, world, b"", depth=4, n_instances=bl * world)
+            legs["kernel with fused peer-memory gather; the norms of evaluation k are awaited before its slot comes round again "
+                 "(ctd_eval_gather_dev, 4 slots)"] = timed_b(lambda: ppipe4.submit(ALL, tx, ty, bout), ppipe4.drain)
     best_how = min(legs, key=lambda k_: legs[k_])
     best = legs[best_how]
     serial_best = min(v for k_, v in legs.items() if k_.startswith("kernel then") or "then wait for all ranks" in k_)
