@@ -83,12 +83,19 @@ def build(force: bool = False, only=None, jobs: int | None = None, verbose: bool
             futs = [ex.submit(_compile, nvcc, s, o, list(extra), verbose) for s, o in tasks]
             for f in cf.as_completed(futs):
                 f.result()
-    if tasks or not os.path.exists(LIB) or force:
+    # relink also when the library on disk was linked from another set of objects (a --only build) or is older than one
+    stamp = os.path.join(OBJ, "linked_objects.txt")
+    wanted = "\n".join(sorted(os.path.basename(o) for o in objs))
+    stale = (not os.path.exists(stamp) or open(stamp).read() != wanted or
+             (os.path.exists(LIB) and any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs)))
+    if tasks or not os.path.exists(LIB) or force or stale:
         cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
                "-o", LIB, *objs, "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        with open(stamp, "w") as fh:
+            fh.write(wanted)
     return LIB
 
 
