@@ -730,19 +730,11 @@ void Model::eval_dev(int flags, const double* x, const double* y, double sigma, 
     const size_t edge_smem = sizeof(double) * (EDGE_LAYERS * ne_all + 2) + sizeof(int) * (edge_map_.size() + 2) +
                              sizeof(double) * (size_t)ntask_ * (size_t)lc.map_step + sizeof(long long) * (ne_all + 1);
     size_t smem = std::max(tile_smem, edge_smem);
-    // One-wave launches (the 2-warp CTAs above): the block scheduler fills SMs up to their resource limit -- 12 of
-    // these CTAs -- while others hold 8, and the fullest SM ends the kernel.  Asking for just enough shared memory that
-    // at most ceil(ctas / 148) CTAs fit on an SM spreads them evenly (measured, Goddard / midpoint, one stream: 5e4
-    // steps 6.76 -> 5.50 us, 7e4 8.41 -> 7.01, 9e4 8.94 -> 8.42, 1e5 9.14 -> 8.92; three streams unchanged).  Not below
-    // 6 CTAs per SM: the CTAs of the next (dependent) launch then no longer fit beside the running ones and the overlap
-    // of its prologue is lost (3e4 steps, 4 per SM: 5.53 -> 7.08 us).
-    static const size_t smem_min_env = getenv("CTD_SMEM_MIN") ? (size_t)atoll(getenv("CTD_SMEM_MIN")) : 0;   // tuning runs only
-    if (batch_ == 1 && !parts && wpc == 2 && wpc_env == 0 && smem_min_env == 0) {
-        const size_t per_sm = 228 * 1024, reserved = 1024;              // B200: shared memory per SM, per-CTA reservation
-        const size_t cap = ((size_t)a.ctas + 147) / 148;
-        const size_t floor_b = cap > 0 ? ((per_sm / cap - reserved - 256) & ~(size_t)127) : 0;
-        if (cap >= 6 && floor_b > smem && floor_b <= 64 * 1024) smem = floor_b;
-    }
+    // (tuning runs only: a shared-memory floor caps the CTAs resident per SM.  Capping a one-wave launch at
+    //  ceil(ctas / 148) per SM to spread it evenly was measured and NOT adopted: it helps when the inputs hit in L2
+    //  (4 rotating buffer sets: 9.02 -> 8.85 us) and hurts when they do not (6 sets: 9.72 -> 10.04, 8 sets: 9.94 -> 10.43;
+    //  bench.py: 9.54 -> 9.63), see DESIGN.md.)
+    static const size_t smem_min_env = getenv("CTD_SMEM_MIN") ? (size_t)atoll(getenv("CTD_SMEM_MIN")) : 0;
     if (smem_min_env > smem && batch_ == 1) smem = smem_min_env;
     // The dynamic shared-memory opt-in is an attribute of the KERNEL (per device, for the whole process), not
     // of this handle: another handle on the same element may have raised it already, and lowering it would

@@ -16,6 +16,7 @@ x0 = d.initial_guess()
 per = 8 * (d.nvar * 2 + 2 * d.ncon + d.nnzj + d.nnzh) * batch
 nsets = max(3, int(np.ceil(1.5 * 126e6 / per))) if per < 300e6 else 1
 NS_ = int(os.environ.get('KTIME_STREAMS', '1'))
+nsets = int(os.environ.get('KTIME_SETS', nsets))
 nsets = ((max(nsets, NS_) + NS_ - 1) // NS_) * NS_
 sets = []
 for s in range(nsets):
