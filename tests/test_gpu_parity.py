@@ -308,6 +308,32 @@ def test_every_output_entry_is_written_and_nothing_else(ctd):
                 assert np.all(np.isfinite(b[G:G + sizes[k]])), tag
 
 
+def test_guard_bands_every_compiled_model(ctd):
+    """The same own bounds check for EVERY compiled (problem, scheme, pattern mode) triple on a grid of several tiles,
+    fused evaluation: nothing outside the arrays, nothing left unwritten.  (A v column without per-step entries made
+    the tile epilogue store one double before its range: only an exhaustive sweep over the patterns finds that.)"""
+    import torch
+    SENT = -7.25e300
+    G = 64
+    ALL = ctd.CONS | ctd.JAC | ctd.HESS | ctd.GRAD | ctd.OBJ
+    for N, B in ((97, 1), (64, 3)):
+        for (p, s, m) in _models(ctd):
+            d = ctd.DOCP(p, N, s, batch=B, pattern_mode=m)
+            x, y = synthetic_point(d, seed=3, batch=B)
+            xd = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+            yd = torch.from_numpy(np.ascontiguousarray(y)).cuda()
+            sizes = {"obj": B, "grad": B * d.nvar, "cons": B * d.ncon, "jac": B * d.nnzj, "hess": B * d.nnzh}
+            big = {k: torch.full((n + 2 * G,), SENT, dtype=torch.float64, device="cuda") for k, n in sizes.items()}
+            out = {k: big[k][G:G + n].view((B, -1) if (B > 1 and k != "obj") else (-1,)) for k, n in sizes.items()}
+            d.evaluate(ALL, xd, yd, 0.9, out=out)
+            d.synchronize()
+            for k, n in sizes.items():
+                b = big[k].cpu().numpy()
+                tag = f"{p}/{s}/{m}/N={N}/B={B}/{k}"
+                assert np.all(b[:G] == SENT) and np.all(b[G + n:] == SENT), tag + ": wrote outside the array"
+                assert not np.any(b[G:G + n] == SENT), tag + ": entries left unwritten"
+
+
 def test_initial_guess_packing_roundtrip(ctd, oracle_mod):
     """__initial_guess from sampled data (src/DOCP_variables.jl:122-145, irk_stagewise.jl:302-335): bit-exact
     against the oracle's restatement of the setters; pack(unpack(x)) reproduces the node variables."""
