@@ -60,6 +60,7 @@ struct ElemInfo {
     bool free_t0 = false, free_tf = false, lagrange = false, mayer = false, is_max = false, irk = false,
          stagewise = false, final_control = false, synthetic = false;
     int ctrl_blk = 0, blk = 0, eqs = 0, cb = 0, nown = 0, nnext = 0, nz = 0;
+    bool path_shift = false; // implicit Euler with path constraints: a step's path rows are those of the NEXT node
     int control_steps = 1;   // controls per time step (DirectShooting: src/direct_shooting.jl:55-71, midpoint.jl:20)
     int j_block = 0, h_block = 0, j_first = 0, h_first = 0, jv_stride = 0, fp_nloc = 0, bc_nloc = 0;
     int n_dropped = 0;
@@ -90,6 +91,7 @@ inline ElemInfo make_elem_info() {
     f.synthetic = E::SYNTHETIC;
     f.ctrl_blk = E::CTRL_BLK; f.blk = E::BLK; f.eqs = E::EQS; f.cb = E::CB;
     f.control_steps = E::CONTROL_STEPS;
+    f.path_shift = E::PATH_SHIFT;
     f.nown = E::NOWN; f.nnext = E::NNEXT; f.nz = E::NZ;
     f.j_block = E::J_BLOCK; f.h_block = E::H_BLOCK; f.j_first = E::J_FIRST; f.h_first = E::H_FIRST;
     f.jv_stride = E::JV_STRIDE; f.fp_nloc = E::FP_NLOC; f.bc_nloc = E::BC_NLOC; f.n_dropped = E::N_DROPPED;

@@ -44,6 +44,7 @@ struct EdgeTask {
     int step;      // 1-based step index
     int own;       // writes its own column block, its constraint rows and its v-column rows
     int map_off;   // offset of this task's map inside edge_map
+    int next_rows; // E::PATH_SHIFT: writes the rows it holds of the NEXT step's block (the path rows of node step + 1)
 };
 
 struct EvalArgs {
@@ -89,6 +90,7 @@ struct EvalArgs {
     int ntask;
     EdgeTask task[MAX_TASKS];
     int fp_map_off, bc_map_off, nmap;
+    int ip_map_off;   // E::PATH_SHIFT: map of the initial-path job (path rows of node 1), laid out like the final-path map
     long long* trace;             // debug builds (-DCTD_TRACE): per-warp timestamps, else nullptr
 };
 
@@ -306,6 +308,8 @@ template <class E, int F, bool PC, bool PJ, bool PH, bool PG>
 struct TileSink {
     using C = Cfg<E, F>;
     double* c_;       // own constraint rows
+    double* cn_;      // rows of the NEXT step's block (E::PATH_SHIFT: the path rows of node i+1, see gen/elements.py)
+    double* jvn_[E::NV > 0 ? E::NV : 1];  // v columns, the next step's rows (E::PATH_SHIFT)
     double* jo_;      // own column block (Jacobian)
     double* jn_;      // next column block (Jacobian)
     double* jv_[E::NV > 0 ? E::NV : 1];  // v columns, this step's rows
@@ -318,14 +322,23 @@ struct TileSink {
 
     template <int R> __device__ __forceinline__ void c(double v) {
         if (PC) {
-            c_[R] = v;
-            if constexpr (C::WV) { if (owner) red[C::R_V] = nanmax(red[C::R_V], row_violation(E::CON_LB(R), E::CON_UB(R), v)); }
+            if constexpr (E::PATH_SHIFT && R >= E::EQS) {   // a row of the next step's block: the giver stores it
+                cn_[R] = v;
+                if constexpr (C::WV) { if (giver) red[C::R_V] = nanmax(red[C::R_V], row_violation(E::CON_LB(R), E::CON_UB(R), v)); }
+            } else {
+                c_[R] = v;
+                if constexpr (C::WV) { if (owner) red[C::R_V] = nanmax(red[C::R_V], row_violation(E::CON_LB(R), E::CON_UB(R), v)); }
+            }
         }
     }
     template <int N> __device__ __forceinline__ void jo(double v) { if (PJ) jo_[E::J_OWN(N, 2)] = v; }
     template <int N> __device__ __forceinline__ void jn(double v) { if (PJ) jn_[E::J_NEXT(N, 2)] = v; }
     template <int N> __device__ __forceinline__ void jv(double v) {
-        if (PJ) jv_[E::J_V(N, 1)][E::J_V(N, 2)] = v;
+        if (PJ) {
+            // slots >= JV_STRIDE lie in the next step's chunk of the column (shifted rows)
+            if constexpr (E::PATH_SHIFT && E::J_V(N, 2) >= E::JV_STRIDE) jvn_[E::J_V(N, 1)][E::J_V(N, 2) - E::JV_STRIDE] = v;
+            else jv_[E::J_V(N, 1)][E::J_V(N, 2)] = v;
+        }
     }
     template <int N> __device__ __forceinline__ void ho(double v) { if (PH) ho_[E::H_OWN(N, 2)] = v; }
     template <int N> __device__ __forceinline__ void hn(double v) { if (PH) hn_[N] = v; }
@@ -345,10 +358,12 @@ struct EdgeSink {
     double* st;       // staging block of this task: C::M_STEP doubles, laid out like the task's map
     bool sums;        // this task contributes to the global sums (it is not a halo re-evaluation)
     double* crow;     // destination of the constraint rows (global) or nullptr
+    double* crow_next;   // E::PATH_SHIFT: destination of the rows of the next step's block, or nullptr
     double* red;
     template <int R> __device__ __forceinline__ void c(double v) {
-        if (crow) {
-            crow[R] = v;
+        double* dst = (E::PATH_SHIFT && R >= E::EQS) ? crow_next : crow;
+        if (dst) {
+            dst[R] = v;
             if constexpr (C::WV) red[C::R_V] = nanmax(red[C::R_V], row_violation(E::CON_LB(R), E::CON_UB(R), v));
         }
     }
@@ -431,7 +446,8 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // boundary+Mayer element -- one warp each; the step elements of one phase run in the lanes of one warp.  Jobs whose values can land on the same entry
 // write to different layers of the edge buffer, which are summed in a fixed order when the buffer is
 // scattered (deterministic whatever the warp interleaving, and no atomics).
-constexpr int EDGE_LAYERS = 4;   // step tasks 0/2, step task 1, final path, boundary
+// layers: step tasks 0/2, step task 1, final path, boundary (+ the initial-path job of E::PATH_SHIFT elements)
+constexpr int edge_layers(bool path_shift) { return path_shift ? 5 : 4; }
 
 template <class E, int F, bool PA, bool PB>
 __device__ __forceinline__ void edge_step_job(const EvalArgs& a, const EdgeTask& tk, const double* __restrict__ x,
@@ -442,13 +458,19 @@ __device__ __forceinline__ void edge_step_job(const EvalArgs& a, const EdgeTask&
     double z[E::NZ], lam[E::CB];
     load_step<E>(x, a.nvar, tk.step, z);
 #pragma unroll
-    for (int r = 0; r < E::CB; ++r) lam[r] = (JH && y) ? __ldg(y + (long long)(tk.step - 1) * E::CB + r) : 0.0;
+    for (int r = 0; r < E::CB; ++r) {
+        if (E::PATH_SHIFT && r >= E::EQS)   // multipliers of the next node's path rows; those of node N+1 belong to the final-path element
+            lam[r] = (JH && y && tk.step < a.N) ? __ldg(y + (long long)tk.step * E::CB + r) : 0.0;
+        else
+            lam[r] = (JH && y) ? __ldg(y + (long long)(tk.step - 1) * E::CB + r) : 0.0;
+    }
     TimeArgs<E::NV> Tm;
     time_args<E>(a, z + E::NOWN + E::NNEXT, p, tk.step, Tm);
     EdgeSink<E, F> s;
     s.st = stage;
     s.sums = smap[tk.map_off + C::M_STEP] != 0;
     s.crow = (JC && tk.own) ? c + (long long)(tk.step - 1) * E::CB : nullptr;
+    s.crow_next = (E::PATH_SHIFT && JC && tk.next_rows) ? c + (long long)tk.step * E::CB : nullptr;
     s.red = red;
     if constexpr (JC || JJ || JH) E::template step<JC, JJ, JH>(z, Tm, p, lam, a.sigma, s);
     if constexpr (JG) E::grad_step(z, Tm, p, s);
@@ -466,6 +488,7 @@ __device__ void edge_cta(const EvalArgs& a, const double* __restrict__ x, const 
     const int tid = threadIdx.x;
     const int T = NW * 32;
     const int ne = a.ne_j + a.ne_h + a.ne_g;
+    constexpr int EDGE_LAYERS = edge_layers(E::PATH_SHIFT);
     int* smap = reinterpret_cast<int*>(buf + EDGE_LAYERS * ne);
     double* stage = buf + EDGE_LAYERS * ne + (a.nmap + 1) / 2;
     long long* spos = reinterpret_cast<long long*>(stage + a.ntask * C::M_STEP);
@@ -495,6 +518,7 @@ __device__ void edge_cta(const EvalArgs& a, const double* __restrict__ x, const 
         // boundary element take lane 0 of the next warps (round robin when the CTA has fewer warps).
         constexpr bool TWO = C::PHASE_A && C::PHASE_B;
         const int W_A = 0, W_B = TWO ? (1 % NW) : 0, W_FP = (TWO ? 2 : 1) % NW, W_BC = (TWO ? 3 : 2) % NW;
+        const int W_IP = (TWO ? 4 : 3) % NW;
         const int lane_ = tid & 31, warp_ = tid >> 5;
         if (lane_ < a.ntask) {
             const EdgeTask tk = a.task[lane_];
@@ -531,6 +555,29 @@ __device__ void edge_cta(const EvalArgs& a, const double* __restrict__ x, const 
                     s.buf = buf + 2 * ne;
                     s.map = smap + a.fp_map_off;
                     s.crow = C::WC ? c + N * E::CB : nullptr;
+                    s.red = red;
+                    E::template fpath<C::WC, C::WJ, C::WH>(z, Tm, p, lam, s);
+                }
+            }
+            if (warp_ == W_IP) {
+                // implicit Euler: path constraints of node 1, g(t_1, x_1, U_1, v) (euler.jl:66-69: u(t_1) = U_1) -- the
+                // step elements carry the path rows of nodes 2..N, the final-path element those of node N+1
+                if constexpr (E::PATH_SHIFT && (C::WC || C::WJ || C::WH)) {
+                    double z[E::FP_NLOC], lam[E::NP];
+#pragma unroll
+                    for (int k = 0; k < E::CTRL_BLK; ++k) z[k] = __ldg(x + E::NX + k);
+#pragma unroll
+                    for (int k = 0; k < E::NX; ++k) z[E::CTRL_BLK + k] = __ldg(x + k);
+#pragma unroll
+                    for (int k = 0; k < E::NV; ++k) z[E::FP_NLOC - E::NV + k] = __ldg(x + a.nvar - E::NV + k);
+#pragma unroll
+                    for (int r = 0; r < E::NP; ++r) lam[r] = (C::WH && y) ? __ldg(y + E::EQS + r) : 0.0;
+                    TimeArgs<E::NV> Tm;
+                    time_args<E>(a, z + E::FP_NLOC - E::NV, p, 1, Tm);
+                    EdgeElemSink<E, F, C::M_FP_J, C::M_FP_H, 0, false> s;
+                    s.buf = buf + 4 * ne;
+                    s.map = smap + a.ip_map_off;
+                    s.crow = C::WC ? c + E::EQS : nullptr;
                     s.red = red;
                     E::template fpath<C::WC, C::WJ, C::WH>(z, Tm, p, lam, s);
                 }
@@ -579,7 +626,11 @@ __device__ void edge_cta(const EvalArgs& a, const double* __restrict__ x, const 
     }
     __syncthreads();
     // ---- scatter the edge buffer (layers summed in a fixed order)
-    auto total = [&](int k) { return ((buf[k] + buf[ne + k]) + buf[2 * ne + k]) + buf[3 * ne + k]; };
+    auto total = [&](int k) {
+        const double t4 = ((buf[k] + buf[ne + k]) + buf[2 * ne + k]) + buf[3 * ne + k];
+        if constexpr (E::PATH_SHIFT) return t4 + buf[4 * ne + k];
+        else return t4;
+    };
     if constexpr (C::WJ)
         for (int k = tid; k < a.ne_j; k += T) jvals[spos[k]] = total(k);
     if constexpr (C::WH)
@@ -621,13 +672,17 @@ __device__ __forceinline__ void tile_phase(const EvalArgs& a, double* __restrict
     const int ob = s.owner ? lane - 1 : C::OWN;   // own block (dump block for the halo lane)
     const int nb = s.giver ? lane : C::OWN;       // next block (dump block for the last lane)
     s.c_ = sC + ob * E::CB;
+    s.cn_ = sC + nb * E::CB;
     s.jo_ = sJ + ob * C::JS;
     s.jn_ = sJ + nb * C::JS;
     s.ho_ = sH + ob * C::HS;
     s.go_ = sG + ob * E::BLK;
     if constexpr (PJ && C::NV > 0) {
 #pragma unroll
-        for (int k = 0; k < C::NV; ++k) s.jv_[k] = sJV[k] + ob * E::JV_STRIDE;
+        for (int k = 0; k < C::NV; ++k) {
+            s.jv_[k] = sJV[k] + ob * E::JV_STRIDE;
+            s.jvn_[k] = sJV[k] + nb * E::JV_STRIDE;
+        }
     }
     if (active) {
         if constexpr (PG) {
@@ -879,7 +934,7 @@ __device__ __forceinline__ void eval_body(const EvalArgs& a) {
 #pragma unroll
             for (int k = 0; k < E::NV; ++k) z[E::NOWN + E::NNEXT + k] = __ldg(x + a.nvar - E::NV + k);
 #pragma unroll
-            for (int r = 0; r < E::CB; ++r) lam[r] = ys ? __ldg(ys + r) : 0.0;
+            for (int r = 0; r < E::CB; ++r) lam[r] = ys ? __ldg(ys + r + ((E::PATH_SHIFT && r >= E::EQS) ? E::CB : 0)) : 0.0;
             time_args_s<E>(si, sp, z + E::NOWN + E::NNEXT, pr, Tm);
         }
 #ifdef CTD_TRACE
@@ -1100,6 +1155,7 @@ struct PartDispatch {
 
 template <class E, int F>
 __global__ void __launch_bounds__(PCfg<E, F>::T, PCfg<E, F>::MINB) ctd_eval_kernel_parts(const EvalArgs a) {
+    static_assert(!E::PATH_SHIFT, "shifted path rows (implicit Euler) are handled by the one-warp kernel only");
     using C = Cfg<E, F>;
     using PC = PCfg<E, F>;
     extern __shared__ __align__(16) double smem[];

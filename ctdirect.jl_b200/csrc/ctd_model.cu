@@ -233,7 +233,10 @@ void Model::build_patterns() {
             J.add(dyn0, dyn1, u0, vo + B + nx);
             J.add(dyn0, dyn1, v0, v1);
             J.add(p0, p1, vo + 1, vo + nx);
-            J.add(p0, p1, u0, u1);
+            if (euler_i && corrected && i >= 2)
+                J.add(p0, p1, u0 - B, u1 - B);   // node i reads the control of block i-1 (euler.jl:66-69)
+            else
+                J.add(p0, p1, u0, u1);
             J.add(p0, p1, v0, v1);
             H.add(u0, u1, u0, u1);
             H.add(u0, u1, v0, v1, true);
@@ -399,6 +402,7 @@ void Model::build_edge_tables() {
         task_[ntask_].step = step;
         task_[ntask_].own = own;
         task_[ntask_].map_off = ntask_ * lc.map_step;
+        task_[ntask_].next_rows = 0;
         ++ntask_;
     };
     add_task(1, 1);
@@ -407,7 +411,8 @@ void Model::build_edge_tables() {
     const bool step1_gives_next = (N <= 2);
     fp_map_off_ = ntask_ * lc.map_step;
     bc_map_off_ = fp_map_off_ + lc.map_fp;
-    edge_map_.assign(bc_map_off_ + lc.map_bc, -1);
+    ip_map_off_ = bc_map_off_ + lc.map_bc;      // initial-path job (shifted path rows only), laid out like the final-path map
+    edge_map_.assign(ip_map_off_ + (f.path_shift ? lc.map_fp : 0), -1);
 
     // edge position sets
     std::vector<int64_t> jpos, hpos, gpos;
@@ -465,12 +470,24 @@ void Model::build_edge_tables() {
         const bool own = task_[t].own != 0;
         const bool next = (i >= N - 1) && (i != 1 || step1_gives_next || N == 1);
         const int64_t row0 = (i - 1) * CB;
+        // Shifted rows (implicit Euler with path constraints): local rows >= eqs are the path rows of node i+1, i.e.
+        // rows of the NEXT step's block; those of node N+1 belong to the final-path element (no entry: -1).
+        auto shifted = [&](int r) { return f.path_shift && r >= f.eqs; };
+        auto grow = [&](int r) -> int64_t { return shifted(r) ? (i < N ? i * CB + r + 1 : -1) : row0 + r + 1; };
+        auto jfind = [&](int r, int64_t col) -> int64_t { const int64_t g = grow(r); return g < 0 ? -1 : jac_.find(g, col); };
+        task_[t].next_rows = (f.path_shift && next && i < N) ? 1 : 0;
         m[M_STEP] = own ? 1 : 0;
         if (own) {
             for (int n = 0; n < f.j_own.n; ++n)
-                m[M_JO + n] = slot_of(jpos, jac_.find(row0 + f.j_own(n, 0) + 1, gcol(i, f.j_own(n, 1))), 0);
-            for (int n = 0; n < f.j_v.n; ++n)
-                m[M_JV + n] = slot_of(jpos, jac_.find(row0 + f.j_v(n, 0) + 1, nvar_ - nv + f.j_v(n, 1) + 1), 0);
+                m[M_JO + n] = slot_of(jpos, jfind(f.j_own(n, 0), gcol(i, f.j_own(n, 1))), 0);
+        }
+        // v-column entries: the step's own rows if it owns them, the shifted rows if it gives to the next block
+        for (int n = 0; n < f.j_v.n; ++n) {
+            const int r = f.j_v(n, 0);
+            if (shifted(r) ? (next && i < N) : own)
+                m[M_JV + n] = slot_of(jpos, jfind(r, nvar_ - nv + f.j_v(n, 1) + 1), 0);
+        }
+        if (own) {
             for (int n = 0; n < f.h_own.n; ++n) {
                 const int64_t ga = gcol(i, f.h_own(n, 0)), gb = gcol(i, f.h_own(n, 1));
                 m[M_HO + n] = slot_of(hpos, hess_.find(std::max(ga, gb), std::min(ga, gb)), ne_j_);
@@ -479,7 +496,7 @@ void Model::build_edge_tables() {
         }
         if (next) {
             for (int n = 0; n < f.j_next.n; ++n)
-                m[M_JN + n] = slot_of(jpos, jac_.find(row0 + f.j_next(n, 0) + 1, gcol(i, f.j_next(n, 1))), 0);
+                m[M_JN + n] = slot_of(jpos, jfind(f.j_next(n, 0), gcol(i, f.j_next(n, 1))), 0);
             for (int n = 0; n < f.h_next.n; ++n) {
                 const int64_t ga = gcol(i, f.h_next(n, 0)), gb = gcol(i, f.h_next(n, 1));
                 m[M_HN + n] = slot_of(hpos, hess_.find(std::max(ga, gb), std::min(ga, gb)), ne_j_);
@@ -508,6 +525,29 @@ void Model::build_edge_tables() {
                 m[f.fp_j.n + n] = vv_edge ? slot_of(hpos, hvv_pos_[kk], ne_j_) : -2 - kk;
             } else {
                 const int64_t ga = fcol(a), gb = fcol(b);
+                m[f.fp_j.n + n] = slot_of(hpos, hess_.find(std::max(ga, gb), std::min(ga, gb)), ne_j_);
+            }
+        }
+    }
+    // initial-path job of shifted elements: the final-path code on (U_1 block, x_1, v), rows eqs.. of step 1
+    if (f.path_shift) {
+        int* m = edge_map_.data() + ip_map_off_;
+        const int cbk = f.ctrl_blk, nl = f.fp_nloc - f.nv;
+        auto icol = [&](int a) -> int64_t {
+            if (a >= nl) return nvar_ - nv + (a - nl) + 1;
+            if (a < cbk) return f.nx + a + 1;
+            return (a - cbk) + 1;
+        };
+        for (int n = 0; n < f.fp_j.n; ++n)
+            m[n] = slot_of(jpos, jac_.find(f.eqs + f.fp_j(n, 0) + 1, icol(f.fp_j(n, 1))), 0);
+        for (int n = 0; n < f.fp_h.n; ++n) {
+            const int a = f.fp_h(n, 0), b = f.fp_h(n, 1);
+            if (a >= nl && b >= nl) {
+                const int ka = std::max(a, b) - nl, kb = std::min(a, b) - nl;
+                const int kk = ka * (ka + 1) / 2 + kb;
+                m[f.fp_j.n + n] = vv_edge ? slot_of(hpos, hvv_pos_[kk], ne_j_) : -2 - kk;
+            } else {
+                const int64_t ga = icol(a), gb = icol(b);
                 m[f.fp_j.n + n] = slot_of(hpos, hess_.find(std::max(ga, gb), std::min(ga, gb)), ne_j_);
             }
         }
@@ -655,7 +695,7 @@ EvalArgs Model::base_args() const {
     a.ne_j = ne_j_; a.ne_h = ne_h_; a.ne_g = ne_g_;
     a.ntask = ntask_;
     for (int t = 0; t < MAX_TASKS; ++t) a.task[t] = task_[t];
-    a.fp_map_off = fp_map_off_; a.bc_map_off = bc_map_off_;
+    a.fp_map_off = fp_map_off_; a.bc_map_off = bc_map_off_; a.ip_map_off = ip_map_off_;
     a.nmap = (int)edge_map_.size();
     return a;
 }
@@ -727,7 +767,7 @@ void Model::eval_dev(int flags, const double* x, const double* y, double sigma, 
     // S_RED is only touched after the buffer has been scattered)
     // (layers, position maps, one staging block per step task, destination positions)
     const size_t ne_all = (size_t)ne_j_ + ne_h_ + ne_g_;
-    const size_t edge_smem = sizeof(double) * (EDGE_LAYERS * ne_all + 2) + sizeof(int) * (edge_map_.size() + 2) +
+    const size_t edge_smem = sizeof(double) * (edge_layers(reg_.info.path_shift) * ne_all + 2) + sizeof(int) * (edge_map_.size() + 2) +
                              sizeof(double) * (size_t)ntask_ * (size_t)lc.map_step + sizeof(long long) * (ne_all + 1);
     size_t smem = std::max(tile_smem, edge_smem);
     // (tuning runs only: a shared-memory floor caps the CTAs resident per SM.  Capping a one-wave launch at

@@ -147,7 +147,7 @@ class Model {
     std::vector<int64_t> edge_pos_;
     int ne_j_ = 0, ne_h_ = 0, ne_g_ = 0, ntask_ = 0;
     EdgeTask task_[MAX_TASKS];
-    int fp_map_off_ = 0, bc_map_off_ = 0;
+    int fp_map_off_ = 0, bc_map_off_ = 0, ip_map_off_ = 0;
     int64_t jv_base_[MAX_NV], hvv_pos_[MAX_NVV];
     // device state (created on first evaluation)
     bool dev_ready_ = false, staging_ready_ = false;

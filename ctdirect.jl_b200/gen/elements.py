@@ -121,6 +121,7 @@ class StepElement:
     inter: list = field(default_factory=list)        # [(symbol, expr)] intermediates (see Differ)
     inter_code: list = field(default_factory=list)   # C lines defining them in the reference's order
     u_node: list = field(default_factory=list)       # control used by the path constraints of the step
+    path_shift: bool = False    # implicit Euler: the element's path rows are those of the NEXT node (see build_step_element)
     rows_traced: list = field(default_factory=list)  # rows / cost before structural zeros are dropped
     cost_traced: sp.Expr = sp.Integer(0)
     structure: dict = None                           # detected structure (pattern_mode 'optimized')
@@ -214,9 +215,9 @@ def build_step_element(ocp: OCP, scheme: str, pattern_mode: str = "reference") -
             f = dyn(ti, xi, ui)
             cost = h * lag(ti, xi, ui)
         else:
-            if npc:
-                raise NotImplementedError("implicit Euler with path constraints: node i reads U_{i-1} "
-                                          "(euler.jl:66-69), which the step element does not hold")
+            if npc and pattern_mode == "reference":
+                raise NotImplementedError("implicit Euler with path constraints: node i reads U_{i-1} (euler.jl:66-69), "
+                                          "a dependency the reference's :manual pattern does not hold; use 'corrected'")
             f = dyn(tp, xn, ui)
             cost = h * lag(tp, xn, ui)
         rows = [xn[k] - (xi[k] + h * f[k]) for k in range(nx)]
@@ -272,7 +273,14 @@ def build_step_element(ocp: OCP, scheme: str, pattern_mode: str = "reference") -
         rows = state_rows + stage_rows
         cost = h * lsum
     E.inter, E.inter_code, E.u_node = inter, icode, list(u_node)
-    if npc:
+    # Implicit Euler: node i+1 reads the control of block i (euler.jl:66-69), i.e. the path constraints of node i+1
+    # depend on (x_{i+1}, U_i) -- the inputs of step i.  The element of step i therefore carries the path rows of the
+    # NEXT node: local rows EQS.. are global rows of the next step's block ("shifted" rows).  The path rows of node 1
+    # (x_1, U_1) are evaluated by the edge CTA with the final-path code, those of node N+1 by the final-path element.
+    E.path_shift = bool(npc) and scheme == "euler_implicit"
+    if E.path_shift:
+        rows += [sp.sympify(e) for e in ocp.path(tp, xn, u_node, v, p)]
+    elif npc:
         rows += [sp.sympify(e) for e in ocp.path(ti, xi, u_node, v, p)]
     assert len(rows) == L.cblock
     E.rows_traced = [sp.sympify(r) for r in rows]
@@ -324,12 +332,15 @@ def build_step_element(ocp: OCP, scheme: str, pattern_mode: str = "reference") -
         jv_stride = cnt[0]
     E.jv_stride = jv_stride or 0
 
+    def grow(i, r):  # 1-based global row of local row r of step i
+        return (i - 1 + (1 if (E.path_shift and r >= L.eqs_block) else 0)) * CB + r + 1
+
     for r in range(CB):
         for a in range(L.nz):
             expr = sp.simplify(D.d(rows[r], a)) if False else D.d(rows[r], a)
             offs = []
             for i in (PROBE_I, PROBE_I + 1):
-                pos = pat.find_pos(jr, jptr, (i - 1) * CB + r + 1, gcol(i, a))
+                pos = pat.find_pos(jr, jptr, grow(i, r), gcol(i, a))
                 if pos < 0:
                     offs.append(None)
                     continue
@@ -390,7 +401,8 @@ def build_step_element(ocp: OCP, scheme: str, pattern_mode: str = "reference") -
     assert hslots == list(range(E.h_block)), (scheme, hslots, E.h_block)
     if nv > 0:
         for kv in range(nv):
-            sl = sorted(e[2] for e in E.j_v if e[1] - L.n_own - L.n_next == kv)
+            # (shifted rows sit in the next step's chunk of the column: slot >= jv_stride)
+            sl = sorted(e[2] % E.jv_stride for e in E.j_v if e[1] - L.n_own - L.n_next == kv)
             assert sl == list(range(E.jv_stride)), (scheme, sl, E.jv_stride)
 
     # objective gradient of the running cost

@@ -169,7 +169,10 @@ def _cons_lines(ocp: OCP, E: el.StepElement):
                 e = f"CTD_ADD({e}, CTD_MUL(BB{j}, {kname(j, k)}))"
             out.append(f"s.template c<{k}>(CTD_SUB({xn[k]}, CTD_ADD({xi[k]}, CTD_MUL(hh, {e}))));")
     if npc:
-        g = ocp.path(sp.Symbol("ti"), [sp.Symbol(n) for n in xi], list(E.u_node), vs, E.p)
+        if E.path_shift:   # rows of the NEXT node: g(t_{i+1}, x_{i+1}, U_i, v)  (euler.jl:66-69)
+            g = ocp.path(sp.Symbol("tp"), [sp.Symbol(n) for n in xn], list(E.u_node), vs, E.p)
+        else:
+            g = ocp.path(sp.Symbol("ti"), [sp.Symbol(n) for n in xi], list(E.u_node), vs, E.p)
         lines, outs = cse_block(g, "c_pw")
         out += lines
         for r, o in enumerate(outs):
@@ -230,7 +233,7 @@ def emit_pair(ocp: OCP, scheme: str, pattern_mode: str = "reference") -> str:
     o.append(f"  static constexpr bool FREE_T0 = {b(ocp.free_t0)}, FREE_TF = {b(ocp.free_tf)}, LAGRANGE = {b(d.lagrange)}, "
              f"MAYER = {b(d.mayer)}, IS_MAX = {b(ocp.criterion == 'max')}, IRK = {b(L.irk)}, STAGEWISE = {b(L.stagewise)}, "
              f"FINAL_CONTROL = {b(L.final_control)}, SYNTHETIC = {b(ocp.synthetic)}, "
-             f"EULER_IMPLICIT = {b(scheme == 'euler_implicit')};\n")
+             f"EULER_IMPLICIT = {b(scheme == 'euler_implicit')}, PATH_SHIFT = {b(E.path_shift)};\n")
     tk = lambda spec: (0 if spec[0] == "const" else 1 if spec[0] == "var" else 2)
     o.append(f"  static constexpr int T0_KIND = {tk(ocp.t0)}, TF_KIND = {tk(ocp.tf)};  // 0 const, 1 v[idx], 2 p[idx]\n")
     o.append(f"  static constexpr int T0_IDX = {int(ocp.t0[1]) if ocp.t0[0] != 'const' else -1}, TF_IDX = {int(ocp.tf[1]) if ocp.tf[0] != 'const' else -1};\n")

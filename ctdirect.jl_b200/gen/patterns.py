@@ -129,7 +129,12 @@ def jacobian_pattern(L: Layout, pattern_mode: str = "reference"):
             T.block(dyn0, dyn1, vo + nx + 1, vo + B + nx)
             T.block(dyn0, dyn1, v0, v1)
             T.block(p0, p1, vo + 1, vo + nx)
-            T.block(p0, p1, vo + nx + 1, vo + nx + nu)
+            if L.scheme == "euler_implicit" and pattern_mode == "corrected" and i >= 2:
+                # node i of the implicit rule reads the control of block i-1 (euler.jl:66-69: u(]t_i, t_i+1]) = U_i,
+                # u(t_1) = U_1); the reference's :manual pattern lists block i (euler.jl:214-216)
+                T.block(p0, p1, vo - B + nx + 1, vo - B + nx + nu)
+            else:
+                T.block(p0, p1, vo + nx + 1, vo + nx + nu)
             T.block(p0, p1, v0, v1)
         elif L.scheme == "trapeze":
             p0, p1 = co + nx + 1, co + cb

@@ -234,7 +234,9 @@ struct Docp {
     static constexpr int eqs_block = ST::irk ? nx * (1 + s) : nx;           // irk.jl:144
     static constexpr int cblock = eqs_block + np;
     // local variables touched by one step (x_i, u_i[, k_i], x_{i+1}[, u_{i+1}], v)
-    static constexpr int NL_STEP = step_block + nx + (SCH == TRAPEZE ? nu : 0) + nv;
+    // (implicit Euler: the path rows of node i read the control of block i-1, euler.jl:66-69)
+    static constexpr bool prev_control = SCH == EULER_IMPLICIT && np > 0;
+    static constexpr int NL_STEP = step_block + nx + (SCH == TRAPEZE ? nu : 0) + nv + (prev_control ? nu : 0);
     static constexpr int NL_NODE = nx + control_block + nv;          // path / trapeze lagrange node
     static constexpr int NL_BC = 2 * nx + nv;                        // boundary + mayer
 
@@ -638,6 +640,7 @@ struct Docp {
         for (int i = 1; i <= N; ++i) {
             TraceAcc<NL_STEP> a;
             a.x = nullptr;
+            if (prev_control && i >= 2) a.add_range(control_off(i - 1), nu);
             a.add_range(state_off(i), step_block + nx + (SCH == TRAPEZE ? nu : 0));
             a.add_range(v_off(), nv);
             Tracer<NL_STEP> c[cblock > 0 ? cblock : 1];
@@ -721,7 +724,12 @@ struct Docp {
                 L.add_block(dyn_start, dyn_end, ui_start, xip1_end);
                 L.add_block(dyn_start, dyn_end, v_start, v_end);
                 L.add_block(path_start, path_end, xi_start, xi_end);
-                L.add_block(path_start, path_end, ui_start, ui_end);
+                if (SCH == EULER_IMPLICIT && pattern_mode == 1 && i >= 2)
+                    // node i of the implicit rule reads the control of block i-1 (euler.jl:66-69); the reference's
+                    // :manual pattern lists block i (euler.jl:214-216)
+                    L.add_block(path_start, path_end, ui_start - B, ui_end - B);
+                else
+                    L.add_block(path_start, path_end, ui_start, ui_end);
                 L.add_block(path_start, path_end, v_start, v_end);
             } else if constexpr (SCH == TRAPEZE) {
                 const int64_t path_start = c_offset + nx + 1, path_end = c_offset + cblock;
@@ -907,6 +915,7 @@ struct Docp {
         using T = HDual<NL_STEP>;
         SeedAcc<NL_STEP> a;
         a.x = xu;
+        if (prev_control && i >= 2) a.add_range(control_off(i - 1), nu);
         a.add_range(state_off(i), step_block + nx + (SCH == TRAPEZE ? nu : 0));
         a.add_range(v_off(), nv);
         T c[cblock > 0 ? cblock : 1];

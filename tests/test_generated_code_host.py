@@ -31,8 +31,11 @@ def _p(a):
     return a.ctypes.data_as(_dp)
 
 
-def _assemble(lib, m, x, y, sigma, sgrid):
-    """obj, grad, cons, jac, hess of oracle model m's problem from the host-compiled element code."""
+def _assemble(lib, m, x, y, sigma, sgrid, path_shift=False):
+    """obj, grad, cons, jac, hess of oracle model m's problem from the host-compiled element code.
+    `path_shift` (implicit Euler with path constraints): the local rows EQS.. of step i are the path rows of node
+    i+1 -- rows of the NEXT step's block (gen/elements.py); node 1 is evaluated with the final-path code on block 1,
+    node N+1 by the final-path element."""
     d = np.zeros(30, dtype=np.int32)
     lib.elem_dims(d.ctypes.data_as(C.POINTER(C.c_int)))
     (NZ, CB, NJO, NJN, NJV, NHO, NHN, NVV, NGO, NGN, NV, FPN, NP, NFPJ, NFPH, BCN, NB, NBCJ, NBCH, NBCG, NOWN, NNEXT,
@@ -77,22 +80,31 @@ def _assemble(lib, m, x, y, sigma, sgrid):
         if k is not None:
             hess[k] += val
 
+    def grow(i, r):   # 1-based global row of local row r of step i (None: no such row)
+        if path_shift and r >= EQS:
+            return i * CB + r + 1 if i < N else None
+        return (i - 1) * CB + r + 1
+
     obj = 0.0
     for i in range(1, N + 1):
         z = np.concatenate([x[(i - 1) * BLK:(i - 1) * BLK + NOWN + NNEXT], v])
         lam = y[(i - 1) * CB:i * CB].copy()
+        if path_shift:
+            lam[EQS:] = y[i * CB + EQS:(i + 1) * CB] if i < N else 0.0
         o = {k: np.zeros(max(n, 1)) for k, n in (("c", CB), ("jo", NJO), ("jn", NJN), ("jv", NJV), ("ho", NHO),
                                                  ("hn", NHN), ("hv", NVV), ("go", NGO), ("gn", NGN), ("gv", NV))}
         obj += lib.elem_step(_p(z), _p(targs(i)), _p(p), _p(lam), C.c_double(sigma), *[_p(o[k]) for k in
                              ("c", "jo", "jn", "jv", "ho", "hn", "hv", "go", "gn", "gv")])
-        cons[(i - 1) * CB:i * CB] = o["c"][:CB]
+        for r in range(CB):
+            if grow(i, r) is not None:
+                cons[grow(i, r) - 1] = o["c"][r]
         for tab, vals in ((JO, o["jo"]), (JN, o["jn"])):
             for n, (r, a, _) in enumerate(tab):
-                k = jpos.get(((i - 1) * CB + r + 1, gcol(i, a)))
+                k = jpos.get((grow(i, r), gcol(i, a)))
                 if k is not None:
                     jac[k] = vals[n]
         for n, (r, kv, _) in enumerate(JV):
-            k = jpos.get(((i - 1) * CB + r + 1, nvar - NV + kv + 1))
+            k = jpos.get((grow(i, r), nvar - NV + kv + 1))
             if k is not None:
                 jac[k] = o["jv"][n]
         for tab, vals in ((HO, o["ho"]), (HN, o["hn"])):
@@ -128,6 +140,20 @@ def _assemble(lib, m, x, y, sigma, sgrid):
                 jac[k] = j_[n]
         for n, (a, b, _) in enumerate(FPH):
             addh(fcol(a), fcol(b), h_[n])
+    if NP > 0 and path_shift:   # path rows of node 1: the final-path code on (U_1 block, x_1, v)
+        cb_ = FPN - NX - NV
+        z = np.concatenate([x[NX:NX + cb_], x[:NX], v])
+        icol = lambda a: nvar - NV + (a - (FPN - NV)) + 1 if a >= FPN - NV else (NX + a + 1 if a < cb_ else (a - cb_) + 1)
+        lam = y[EQS:EQS + NP].copy()
+        c_, j_, h_ = np.zeros(NP), np.zeros(max(NFPJ, 1)), np.zeros(max(NFPH, 1))
+        lib.elem_fpath(_p(z), _p(targs(1)), _p(p), _p(lam), _p(c_), _p(j_), _p(h_))
+        cons[EQS:EQS + NP] = c_
+        for n, (r, a, _) in enumerate(FPJ):
+            k = jpos.get((EQS + r + 1, icol(a)))
+            if k is not None:
+                jac[k] = j_[n]
+        for n, (a, b, _) in enumerate(FPH):
+            addh(icol(a), icol(b), h_[n])
     z = np.concatenate([x[:NX], x[N * BLK:N * BLK + NX], v])
     bcol = lambda a: a + 1 if a < NX else (N * BLK + (a - NX) + 1 if a < 2 * NX else nvar - NV + (a - 2 * NX) + 1)
     lam = y[ncon - NB:].copy() if NB else np.zeros(1)
@@ -156,7 +182,11 @@ CASES = [("goddard", "midpoint", "reference"), ("goddard", "midpoint", "optimize
          ("double_integrator_freet0tf", "midpoint", "reference"), ("double_integrator_freet0tf", "euler", "reference"),
          ("double_integrator_freet0tf", "euler_implicit", "reference"), ("double_integrator_freet0tf", "gauss_legendre_2", "reference"),
          ("double_integrator_freet0tf", "gauss_legendre_3", "reference"), ("beam", "trapeze", "reference"),
-         ("beam", "gauss_legendre_3", "reference"), ("beam", "euler_implicit", "reference")]
+         ("beam", "gauss_legendre_3", "reference"), ("beam", "euler_implicit", "reference"),
+         # implicit Euler WITH path constraints: node i reads the control of block i-1 (euler.jl:66-69); corrected pattern only
+         ("goddard_all", "euler_implicit", "corrected"),
+         # several controls per step (DirectShooting)
+         ("goddard_all", "midpoint_cs2", "optimized"), ("double_integrator_minenergy", "midpoint_cs10", "optimized")]
 
 
 if os.environ.get("CTD_HOST_ALL"):   # opt-in: every compiled (problem, scheme, pattern mode) triple, ~15 min on 8 cores
@@ -174,7 +204,7 @@ def test_host_compiled_elements_match_oracle(oracle_mod, tmp_path, problem, sche
                      "double_integrator_minenergy": [2.0], "vanderpol": [1.0, 1.0]}.get(problem, [])
         x, y = synthetic_point(m, seed=11 + N)
         sgrid = np.arange(N + 1) / N if grid is None else grid
-        obj, grad, cons, jac, hess = _assemble(lib, m, x, y, 0.7, sgrid)
+        obj, grad, cons, jac, hess = _assemble(lib, m, x, y, 0.7, sgrid, path_shift=(scheme == "euler_implicit" and m.np_ > 0))
         g_ref, j_ref, h_ref = m.derivs(x, y, 0.7)
         tag = f"{name}/N={N}"
         assert_close(cons, m.cons(x), scale=max(1.0, np.abs(x).max()), what=tag + " cons")
