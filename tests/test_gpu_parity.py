@@ -675,3 +675,52 @@ def test_library_call_counters(ctd):
     assert s["neval_cons"] == 4 and s["kernel_launches"] == d.launch_count >= 8 and s["host_call_seconds"] > 0
     d.reset_counters()
     assert d.counters() == dict.fromkeys(d.COUNTER_NAMES, 0)
+
+
+@pytest.mark.gpu
+def test_implicit_euler_with_path_constraints(ctd, oracle_mod):
+    """goddard_all / euler_implicit: node i reads the control of block i-1 (src/ode/euler.jl:66-69), so the step
+    elements carry the path rows of the NEXT node, node 1 is an extra job of the edge CTA and node N+1 the final-path
+    element.  Only the corrected pattern holds these dependencies (the reference's :manual pattern lists U_i,
+    euler.jl:214-216).  Values against the oracle at sizes around the tile boundaries, batches, the in-kernel
+    violation norm, solution unpacking."""
+    with pytest.raises(ctd.CtdError, match="not compiled in"):
+        ctd.DOCP("goddard_all", 10, "euler_implicit")                       # reference pattern: refused
+    lv = None
+    for N in (1, 2, 3, 4, 31, 32, 33, 34, 63, 64, 65, 1000):
+        o = oracle_mod.OracleModel("goddard_all", "euler_implicit", N, pattern_mode="corrected")
+        d = ctd.DOCP("goddard_all", N, "euler_implicit", pattern_mode="corrected")
+        x, y = synthetic_point(o, seed=300 + N)
+        _compare_all(ctd, o, d, x, y, 0.6, f"goddard_all/euler_implicit/corrected/N={N}")
+        # the Jacobian holds the dependency of node i's path rows on the control of block i-1
+        if N >= 3:
+            r, c = d.jacobian_structure()
+            B, CB = d.step_variables_block, d.step_constraints_block
+            rows_u1 = set(r[c == d.NLP_x + 1].tolist())                      # column of U_1
+            assert {d.NLP_x + q + 1 for q in range(d.path_cons)} <= rows_u1          # node 1 (u(t_1) = U_1)
+            assert {CB + d.NLP_x + q + 1 for q in range(d.path_cons)} <= rows_u1     # node 2
+            rows_u2 = set(r[c == B + d.NLP_x + 1].tolist())
+            assert not ({CB + d.NLP_x + q + 1 for q in range(d.path_cons)} & rows_u2)
+        obj, viol = d.norms(x)
+        lvar, uvar, lcon, ucon = d.bounds()
+        cref = o.cons(x)
+        v_ref = max(0.0, float(np.max(np.maximum(lcon - cref, cref - ucon))))
+        assert_close(viol[0], v_ref, scale=max(1.0, np.abs(x).max()), what=f"N={N} violation")
+        u_ref, u_got = o.unpack(x, y), d.unpack(x, y)
+        for k in u_got:
+            assert np.array_equal(u_got[k], u_ref[k]), (N, k)
+    B, N = 7, 100
+    d = ctd.DOCP("goddard_all", N, "euler_implicit", pattern_mode="corrected", batch=B)
+    o = oracle_mod.OracleModel("goddard_all", "euler_implicit", N, pattern_mode="corrected")
+    x, y = synthetic_point(d, seed=8, batch=B)
+    r = d.evaluate(ctd.CONS | ctd.JAC | ctd.HESS | ctd.GRAD | ctd.OBJ, x, y, 1.0)
+    obj, viol = d.norms(x)
+    lvar, uvar, lcon, ucon = d.bounds()
+    for b in range(B):
+        g, j, h = o.derivs(x[b], y[b], 1.0)
+        cref = o.cons(x[b])
+        assert_close(r["cons"][b], cref, scale=max(1.0, np.abs(x[b]).max()), what=f"shifted rows, instance {b} cons")
+        assert_close(r["jac"][b], j, scale=column_scale(d.jacobian_structure(), j, d.nvar), what=f"shifted rows, instance {b} jac")
+        assert_close(r["hess"][b], h, scale=hess_scale(o, x[b], y[b], 1.0, h), what=f"shifted rows, instance {b} hess")
+        assert_close(viol[b], max(0.0, float(np.max(np.maximum(lcon - cref, cref - ucon)))),
+                     scale=max(1.0, np.abs(x[b]).max()), what=f"shifted rows, instance {b} violation")
