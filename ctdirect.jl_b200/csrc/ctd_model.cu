@@ -192,8 +192,25 @@ void Model::build_detected_patterns() {
     H.reserve((size_t)N * f.s_step_h.n + 64);
     auto addH = [&](int64_t ga, int64_t gb) { H.emplace_back(std::min(ga, gb), std::max(ga, gb)); };   // (col, row), row >= col
     for (int64_t i = 1; i <= N; ++i) {
-        for (int n = 0; n < f.s_step_j.n; ++n) J.emplace_back(scol(i, f.s_step_j(n, 1)), (i - 1) * CB + f.s_step_j(n, 0) + 1);
+        for (int n = 0; n < f.s_step_j.n; ++n) {
+            const int r = f.s_step_j(n, 0);
+            if (f.path_shift && r >= f.eqs) {   // path rows of node i+1 (rows of the next step's block); node N+1: final-path element
+                if (i < N) J.emplace_back(scol(i, f.s_step_j(n, 1)), i * CB + r + 1);
+                continue;
+            }
+            J.emplace_back(scol(i, f.s_step_j(n, 1)), (i - 1) * CB + r + 1);
+        }
         for (int n = 0; n < f.s_step_h.n; ++n) addH(scol(i, f.s_step_h(n, 0)), scol(i, f.s_step_h(n, 1)));
+    }
+    if (f.path_shift) {   // path rows of node 1: the final-path structure on (U_1 block, x_1, v)
+        const int nl = f.fp_nloc - f.nv;
+        auto icol = [&](int a) -> int64_t {
+            if (a >= nl) return nvar_ - nv + (a - nl) + 1;
+            if (a < f.ctrl_blk) return f.nx + a + 1;
+            return (a - f.ctrl_blk) + 1;
+        };
+        for (int n = 0; n < f.s_fp_j.n; ++n) J.emplace_back(icol(f.s_fp_j(n, 1)), f.eqs + f.s_fp_j(n, 0) + 1);
+        for (int n = 0; n < f.s_fp_h.n; ++n) addH(icol(f.s_fp_h(n, 0)), icol(f.s_fp_h(n, 1)));
     }
     for (int n = 0; n < f.s_fp_j.n; ++n) J.emplace_back(fcol(f.s_fp_j(n, 1)), N * CB + f.s_fp_j(n, 0) + 1);
     for (int n = 0; n < f.s_fp_h.n; ++n) addH(fcol(f.s_fp_h(n, 0)), fcol(f.s_fp_h(n, 1)));

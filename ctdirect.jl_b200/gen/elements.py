@@ -215,7 +215,7 @@ def build_step_element(ocp: OCP, scheme: str, pattern_mode: str = "reference") -
             f = dyn(ti, xi, ui)
             cost = h * lag(ti, xi, ui)
         else:
-            if npc and pattern_mode == "reference":
+            if npc and pattern_mode == "reference":  # (corrected and optimized hold the dependency)
                 raise NotImplementedError("implicit Euler with path constraints: node i reads U_{i-1} (euler.jl:66-69), "
                                           "a dependency the reference's :manual pattern does not hold; use 'corrected'")
             f = dyn(tp, xn, ui)
@@ -516,7 +516,15 @@ def optimized_patterns_for(ocp: OCP, scheme: str, L, S):
     extra_J += [(L.ncon - d.nb + r + 1, _bc_gcol(L, a)) for (r, a) in S["bc_J"]]
     extra_H = [(_fpath_gcol(L, scheme, a), _fpath_gcol(L, scheme, b)) for (a, b) in S["fp_H"]]
     extra_H += [(_bc_gcol(L, a), _bc_gcol(L, b)) for (a, b) in S["bc_H"]]
-    return pat.optimized_patterns(L, S["step_J"], S["step_H"], extra_J, extra_H)
+    shift_from = None
+    if scheme == "euler_implicit" and d.np > 0:
+        # shifted path rows; node 1 is the final-path structure on (U_1 block, x_1, v)
+        shift_from = L.eqs_block
+        cbk, nl = L.control_block, L.control_block + d.nx
+        icol = lambda a: L.nvar - d.nv + (a - nl) + 1 if a >= nl else (d.nx + a + 1 if a < cbk else (a - cbk) + 1)
+        extra_J += [(L.eqs_block + r + 1, icol(a)) for (r, a) in S["fp_J"]]
+        extra_H += [(icol(a), icol(b)) for (a, b) in S["fp_H"]]
+    return pat.optimized_patterns(L, S["step_J"], S["step_H"], extra_J, extra_H, shift_from)
 
 
 @dataclass

@@ -241,7 +241,7 @@ def find_pos(rows, colptr, r, c):
     return -1
 
 
-def optimized_patterns(L: Layout, step_J, step_H, extra_J, extra_H):
+def optimized_patterns(L: Layout, step_J, step_H, extra_J, extra_H, shift_from=None):
     """`:optimized` (detected) patterns assembled from per-element structure: `step_J` = [(row r, local a)],
     `step_H` = [(local a, local b)] of one time step; `extra_*` = global 1-based (i, j) entries of the
     final-path and boundary(+Mayer) elements.  Returns the same CSC triples as the manual builders."""
@@ -251,9 +251,15 @@ def optimized_patterns(L: Layout, step_J, step_H, extra_J, extra_H):
     def gcol(i, a):
         return (i - 1) * B + a + 1 if a < nloc else L.nvar - d.nv + (a - nloc) + 1
 
+    # shift_from: local rows >= shift_from of step i are rows of the NEXT step's block (implicit Euler with path
+    # constraints, see gen/elements.py); those of step N do not exist (the final-path element holds node N+1)
     TJ, TH = _Triplets(), _Triplets()
     for i in range(1, N + 1):
         for (r, a) in step_J:
+            if shift_from is not None and r >= shift_from:
+                if i < N:
+                    TJ.one(i * cb + r + 1, gcol(i, a))
+                continue
             TJ.one((i - 1) * cb + r + 1, gcol(i, a))
         for (a, b) in step_H:
             TH.one(gcol(i, a), gcol(i, b))

@@ -184,7 +184,7 @@ CASES = [("goddard", "midpoint", "reference"), ("goddard", "midpoint", "optimize
          ("double_integrator_freet0tf", "gauss_legendre_3", "reference"), ("beam", "trapeze", "reference"),
          ("beam", "gauss_legendre_3", "reference"), ("beam", "euler_implicit", "reference"),
          # implicit Euler WITH path constraints: node i reads the control of block i-1 (euler.jl:66-69); corrected pattern only
-         ("goddard_all", "euler_implicit", "corrected"),
+         ("goddard_all", "euler_implicit", "corrected"), ("goddard_all", "euler_implicit", "optimized"),
          # several controls per step (DirectShooting)
          ("goddard_all", "midpoint_cs2", "optimized"), ("double_integrator_minenergy", "midpoint_cs10", "optimized")]
 

@@ -688,9 +688,15 @@ def test_implicit_euler_with_path_constraints(ctd, oracle_mod):
         ctd.DOCP("goddard_all", 10, "euler_implicit")                       # reference pattern: refused
     lv = None
     for N in (1, 2, 3, 4, 31, 32, 33, 34, 63, 64, 65, 1000):
+        # the detected pattern (the reference's default backend) holds the dependency by construction
+        od = oracle_mod.OracleModel("goddard_all", "euler_implicit", N, pattern_mode="optimized")
+        dd = ctd.DOCP("goddard_all", N, "euler_implicit", pattern_mode="optimized")
+        for a, b in zip(dd.jacobian_structure() + dd.hessian_structure(), od.jac_structure() + od.hess_structure()):
+            assert np.array_equal(a, b), N
+        x, y = synthetic_point(od, seed=300 + N)
+        _compare_all(ctd, od, dd, x, y, 0.6, f"goddard_all/euler_implicit/optimized/N={N}")
         o = oracle_mod.OracleModel("goddard_all", "euler_implicit", N, pattern_mode="corrected")
         d = ctd.DOCP("goddard_all", N, "euler_implicit", pattern_mode="corrected")
-        x, y = synthetic_point(o, seed=300 + N)
         _compare_all(ctd, o, d, x, y, 0.6, f"goddard_all/euler_implicit/corrected/N={N}")
         # the Jacobian holds the dependency of node i's path rows on the control of block i-1
         if N >= 3:
