@@ -42,11 +42,12 @@ def test_detected_pattern_counts_through_the_library(ctd):
     assert (d.nnzj, d.nnzh) == (4504, 5259)
     assert ctd.DOCP("goddard_all", 1000, "trapeze", pattern_mode="optimized").nnzh == 11011
     assert ctd.DOCP("goddard_all", 10000, "trapeze", pattern_mode="optimized").nnzh == 110011
-    # every problem has the detected pattern; a pair that is not compiled at all says so (node i of the implicit
-    # Euler rule reads U_{i-1}, which the step element does not hold: no goddard_all / euler_implicit)
+    # every problem has the detected pattern; a pair that is not compiled says so: with path constraints the implicit
+    # Euler rule reads U_{i-1} at node i, which the reference's :manual pattern does not hold (euler.jl:66-69,214-216)
     assert ctd.DOCP("bolza_freetf", 10, "midpoint", pattern_mode="optimized").nnzj > 0
+    assert ctd.DOCP("goddard_all", 10, "euler_implicit", pattern_mode="optimized").nnzj > 0
     with pytest.raises(ctd.CtdError, match="not compiled in"):
-        ctd.DOCP("goddard_all", 10, "euler_implicit", pattern_mode="optimized")
+        ctd.DOCP("goddard_all", 10, "euler_implicit", pattern_mode="reference")
 
 
 def test_large_grid_structure_is_csc_sorted(ctd, oracle_mod):
