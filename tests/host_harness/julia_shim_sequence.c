@@ -10,7 +10,11 @@
  * tests/test_julia_shim_sequence.py compares with the oracle (the two come from different kernels: same values within
  * rounding, checked here only coarsely).
  *
- *   julia_shim_sequence <problem> <scheme> <N> <pattern_mode> <x.bin> <y.bin> <out.bin>
+ * With a 9th argument (control_steps > 1) it is the DirectShooting discretizer (docp.time.control_steps goes into
+ * ctd_desc.control_steps).  At the end the library's own call counters (library_counters in the shim) must say what
+ * was called.
+ *
+ *   julia_shim_sequence <problem> <scheme> <N> <pattern_mode> <x.bin> <y.bin> <out.bin> [control_steps]
  */
 #include <math.h>
 #include <stdio.h>
@@ -49,7 +53,7 @@ static int close_enough(const double* a, const double* b, int64_t n) {   /* coar
 }
 
 int main(int argc, char** argv) {
-    if (argc != 8) {
+    if (argc != 8 && argc != 9) {
         fprintf(stderr, "usage: %s problem scheme N pattern_mode x.bin y.bin out.bin\n", argv[0]);
         return 1;
     }
@@ -68,6 +72,7 @@ int main(int argc, char** argv) {
     d.pattern_mode = atoi(argv[4]);
     d.batch = 1;
     d.device = 0;
+    d.control_steps = argc == 9 ? atoi(argv[8]) : 1;
     ctd_handle h = NULL;
     CHECK(ctd_create(&d, &h));
     int64_t nvar, ncon, nnzj, nnzh, info[16];
@@ -100,7 +105,12 @@ int main(int argc, char** argv) {
     }
     /* unpack_solution: time, state, control, variable, costate, path_dual, boundary_dual */
     const int64_t nx = info[0], nu = info[1], nv = info[2], np = info[3], nb = info[4];
-    double *tm = calloc((size_t)N + 1, 8), *st = calloc((size_t)(N + 1) * (nx ? nx : 1), 8), *ct = calloc((size_t)(N + 1) * (nu ? nu : 1), 8),
+    const int64_t ncs = ctd_control_steps(h);
+    if (ncs != (d.control_steps > 1 ? d.control_steps : 1)) {
+        fprintf(stderr, "ctd_control_steps says %lld\n", (long long)ncs);
+        return 6;
+    }
+    double *tm = calloc((size_t)N + 1, 8), *st = calloc((size_t)(N + 1) * (nx ? nx : 1), 8), *ct = calloc((size_t)(N * ncs + 1) * (nu ? nu : 1), 8),
            *vr = calloc((size_t)(nv ? nv : 1), 8), *cs = calloc((size_t)N * (nx ? nx : 1), 8), *pd = calloc((size_t)(N + 1) * (np ? np : 1), 8),
            *bd = calloc((size_t)(nb ? nb : 1), 8);
     ctd_solution sol;
@@ -108,6 +118,21 @@ int main(int argc, char** argv) {
     sol.time = tm; sol.state = st; sol.control = nu ? ct : NULL; sol.variable = nv ? vr : NULL; sol.costate = cs;
     sol.path_dual = np ? pd : NULL; sol.boundary_dual = nb ? bd : NULL;
     CHECK(ctd_unpack(h, x, y, &sol));
+    double* tc = calloc((size_t)(N * ncs + 1), 8);
+    CHECK(ctd_control_time(h, tm, tc));
+    if (tc[0] != tm[0] || tc[N * ncs] != tm[N] || tc[ncs] != tm[1]) {
+        fprintf(stderr, "ctd_control_time does not interpolate the time grid\n");
+        return 7;
+    }
+    /* the library's counters: obj, grad (= objective + gradient), cons, jac_coord, hess_coord, one fused call */
+    int64_t cnt[CTD_N_COUNTERS];
+    CHECK(ctd_counters(h, cnt));
+    if (cnt[CTD_NEVAL_OBJ] != 3 || cnt[CTD_NEVAL_GRAD] != 2 || cnt[CTD_NEVAL_CONS] != 2 || cnt[CTD_NEVAL_JAC] != 2 ||
+        cnt[CTD_NEVAL_HESS] != 2 || cnt[CTD_NCALL_EVAL] != 6 || cnt[CTD_NCALL_HOST] != 6) {
+        fprintf(stderr, "ctd_counters: %lld %lld %lld %lld %lld calls %lld host %lld\n", (long long)cnt[0], (long long)cnt[1],
+                (long long)cnt[2], (long long)cnt[3], (long long)cnt[4], (long long)cnt[5], (long long)cnt[6]);
+        return 8;
+    }
     FILE* o = fopen(argv[7], "wb");
     if (!o) return 5;
     int64_t hdr[8] = {nvar, ncon, nnzj, nnzh, info[13] /* max problem */, N, nx, nu};

@@ -63,14 +63,18 @@ def test_shim_call_sequence_on_gpu(ctd, oracle_mod, tmp_path, scheme):
     cases = [("goddard", 60, 0), ("double_integrator_freet0tf", 50, 0)]   # free tf / free t0 and tf: where fixed_grid is garbage
     if scheme in ("trapeze", "gauss_legendre_2", "gauss_legendre_3"):
         cases.append(("goddard", 60, 1))
+    if scheme == "midpoint":   # the DirectShooting discretizer: docp.time.control_steps = 2, detected pattern
+        cases.append(("goddard", 60, 2))
     for problem, N, mode in cases:
-        o = oracle_mod.OracleModel(problem, scheme, N, pattern_mode=("reference", "corrected")[mode])
+        extra = ["2"] if mode == 2 else []
+        o = oracle_mod.OracleModel(problem, "midpoint_cs2" if mode == 2 else scheme, N,
+                                   pattern_mode=("reference", "corrected", "optimized")[mode])
         x, y = synthetic_point(o, seed=5)
         if problem == "double_integrator_freet0tf":
             x[-2:] = (0.3, 2.1)
         fx, fy, fo = (str(tmp_path / n) for n in ("x.bin", "y.bin", "out.bin"))
         x.tofile(fx); y.tofile(fy)
-        r = subprocess.run([exe, problem, scheme, str(N), str(mode), fx, fy, fo], capture_output=True, text=True)
+        r = subprocess.run([exe, problem, scheme, str(N), str(mode), fx, fy, fo] + extra, capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
         raw = np.fromfile(fo, dtype=np.float64)
         hdr = raw[:8].view(np.int64)
