@@ -66,6 +66,13 @@ def build(force: bool = False, only=None, jobs: int | None = None, verbose: bool
     os.makedirs(OBJ, exist_ok=True)
     os.makedirs(LIB_DIR, exist_ok=True)
     common = max(os.path.getmtime(p) for p in _common_deps())
+    # A snapshot of the tree without the object cache (gpurun ships the library, not csrc/_build): the library on disk is
+    # used as it is when it is newer than every source, instead of recompiling ~270 translation units.
+    if not force and not only and os.path.exists(LIB) and not any(f.endswith(".o") for f in os.listdir(OBJ)):
+        newest = max([common] + [os.path.getmtime(s_) for s_ in _sources(None)] +
+                     [os.path.getmtime(s_[:-3] + ".cuh") for s_ in _sources(None) if os.path.exists(s_[:-3] + ".cuh")])
+        if os.path.getmtime(LIB) >= newest:
+            return LIB
     tasks = []
     objs = []
     for src in _sources(only):
