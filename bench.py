@@ -626,17 +626,13 @@ def leg_batched(cx, ctd):
             legs["two half-shards on two streams (no exchange at one GPU)"] = timed_two(lambda: (eA(), eB()))
             halves = (hA, hB)
         elif ok:
-            from ctdirect_b200.batch import PeerNormsPipeline, broadcast_unique_id
-            pA = PeerNormsPipeline(hA[0], rank, world, broadcast_unique_id(), depth=4, n_instances=(bl // 2) * world)
-            pB = PeerNormsPipeline(hB[0], rank, world, broadcast_unique_id(), depth=4, n_instances=(bl // 2) * world)
+            from ctdirect_b200.batch import SplitShardPipeline
+            split = SplitShardPipeline([hA[0], hB[0]], rank, world, depth=4)
 
             def two_step(serial):
-                pA.submit(ALL, hA[1], hA[2], hA[3], serial=serial)
-                pB.submit(ALL, hB[1], hB[2], hB[3], serial=serial)
+                split.submit(ALL, [hA[1], hB[1]], [hA[2], hB[2]], [hA[3], hB[3]], serial=serial)
 
-            def two_drain():
-                pA.drain()
-                pB.drain()
+            two_drain = split.drain
 
             legs["two half-shards per GPU on two streams, each with the fused peer-memory gather, then wait for all ranks"] = \
                 timed_two(lambda: two_step(True), two_drain)

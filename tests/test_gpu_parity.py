@@ -440,10 +440,28 @@ def _native_gather_worker(rank, world, port, q, kind="native", rounds=3):
         par[:, 3] = rng.uniform(1.0, 3.5, B)
         lo, hi = shard_range(B, world, rank)
         d = ctd.DOCP("goddard", N, "midpoint", params=par[lo:hi], batch=hi - lo, device=rank)
-        pipe = (PeerNormsPipeline if kind == "peer" else NativeNormsPipeline)(d, rank, world, broadcast_unique_id(), depth=2)
         dev = torch.device("cuda", rank)
         x_all = np.tile(d.initial_guess(), (B, 1)) * (1 + 1e-3 * rng.uniform(-1, 1, (B, d.nvar)))
         res = []
+        if kind == "split":   # the shard as two half-shards on two streams, each with its own fused gather
+            from ctdirect_b200.batch import SplitShardPipeline
+            mid = (lo + hi) // 2
+            parts = [ctd.DOCP("goddard", N, "midpoint", params=par[a:b], batch=b - a, device=rank, stream="own")
+                     for a, b in ((lo, mid), (mid, hi))]
+            split = SplitShardPipeline(parts, rank, world, depth=4)
+            for k in range(rounds):
+                xs = [torch.from_numpy(np.ascontiguousarray(x_all[a:b] * (1 + 1e-4 * k))).to(dev) for a, b in ((lo, mid), (mid, hi))]
+                torch.cuda.synchronize()
+                sl = split.submit(ctd.CONS | ctd.OBJ, xs)
+                gs = split.result(sl)
+                for p_ in parts:
+                    p_.synchronize()
+                # (world, 2, half) per part -> (world, 2, shard) in instance order
+                res.append(np.concatenate([g.cpu().numpy() for g in gs], axis=2))
+            split.drain()
+            q.put((rank, res))
+            return
+        pipe = (PeerNormsPipeline if kind == "peer" else NativeNormsPipeline)(d, rank, world, broadcast_unique_id(), depth=2)
         for k in range(rounds):
             xk = torch.from_numpy(np.ascontiguousarray(x_all[lo:hi] * (1 + 1e-4 * k))).to(dev)
             s = pipe.submit(ctd.CONS | ctd.OBJ, xk)
@@ -521,6 +539,41 @@ def test_peer_memory_gather_two_ranks(ctd):
         obj, viol = d.norms(np.ascontiguousarray(x_all * (1 + 1e-4 * k)))
         for rank in (0, 1):
             g = out[rank][k]                    # (world, 2, 4)
+            assert np.array_equal(g[:, 0, :].reshape(-1), obj), f"rank {rank} round {k}: objectives"
+            assert np.array_equal(g[:, 1, :].reshape(-1), viol), f"rank {rank} round {k}: violations"
+
+
+@pytest.mark.gpu
+def test_split_shard_pipeline_two_ranks(ctd):
+    """batch.SplitShardPipeline: every rank's shard as two half-shards on two streams, each with its own communicator
+    and fused peer-memory gather (the best 8-GPU schedule of bench.py).  Over 9 rounds on 4 slots the rows of both
+    halves of both ranks are bit-identical to a single-process evaluation of the whole batch."""
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    R = 9
+    procs = [mpc.Process(target=_native_gather_worker, args=(r, 2, port, q, "split", R)) for r in range(2)]
+    for p_ in procs:
+        p_.start()
+    out = dict(q.get(timeout=180) for _ in range(2))
+    for p_ in procs:
+        p_.join(timeout=60)
+        assert p_.exitcode == 0
+    B, N = 8, 120
+    rng = np.random.default_rng(3)
+    par = np.tile(np.array([310.0, 500.0, 2.0, 3.5]), (B, 1))
+    par[:, 3] = rng.uniform(1.0, 3.5, B)
+    d = ctd.DOCP("goddard", N, "midpoint", params=par, batch=B)
+    x_all = np.tile(d.initial_guess(), (B, 1)) * (1 + 1e-3 * rng.uniform(-1, 1, (B, d.nvar)))
+    for k in range(R):
+        obj, viol = d.norms(np.ascontiguousarray(x_all * (1 + 1e-4 * k)))
+        for rank in (0, 1):
+            g = out[rank][k]                    # (world, 2, 4): rank-major, each rank's two halves side by side
             assert np.array_equal(g[:, 0, :].reshape(-1), obj), f"rank {rank} round {k}: objectives"
             assert np.array_equal(g[:, 1, :].reshape(-1), viol), f"rank {rank} round {k}: violations"
 
