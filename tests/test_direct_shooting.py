@@ -155,6 +155,25 @@ def test_cuda_path_matches_oracle(ctd, oracle_mod, N):
 
 
 @pytest.mark.gpu
+def test_cuda_path_on_a_nonuniform_grid(ctd, oracle_mod):
+    """The C ABI takes a time grid together with control_steps (the reference's DirectShooting passes none; the
+    normalized grid of a DOCP built by hand may be anything increasing): h_i / control_steps sub-steps of every step."""
+    rng = np.random.default_rng(6)
+    grid = np.concatenate([[0.0], np.sort(rng.uniform(0.02, 0.98, 44)), [1.0]])
+    for problem, cs in (("goddard", 3), ("double_integrator_minenergy", 10), ("goddard_all", 2)):
+        o = oracle_mod.OracleModel(problem, f"midpoint_cs{cs}", 45, time_grid=grid, pattern_mode="optimized")
+        d = ctd.DOCP(problem, 45, "midpoint", time_grid=grid, control_steps=cs)
+        x, y = synthetic_point(o, seed=2)
+        r = d.nlp_model().eval_all(x, y, obj_weight=0.8)
+        g_ref, j_ref, h_ref = o.derivs(x, y, 0.8)
+        tag = f"{problem}/midpoint control_steps={cs}/non-uniform grid"
+        assert_close(r["cons"], o.cons(x), scale=max(1.0, float(np.abs(x).max())), what=tag + " cons")
+        assert_close(r["jac"], j_ref, scale=column_scale(d.jacobian_structure(), j_ref, d.nvar), what=tag + " jac")
+        assert_close(r["hess"], h_ref, scale=hess_scale(o, x, y, 0.8, h_ref), what=tag + " hess")
+        assert_close(r["obj"], o.obj(x), scale=1.0, what=tag + " obj")
+
+
+@pytest.mark.gpu
 def test_cuda_unpack_pack_and_batches(ctd, oracle_mod):
     import torch
     rng = np.random.default_rng(9)

@@ -768,6 +768,14 @@ def test_implicit_euler_with_path_constraints(ctd, oracle_mod):
         u_ref, u_got = o.unpack(x, y), d.unpack(x, y)
         for k in u_got:
             assert np.array_equal(u_got[k], u_ref[k]), (N, k)
+    # a non-uniform time grid (the step lengths enter the shifted rows through t_{i+1})
+    rng = np.random.default_rng(4)
+    grid = np.concatenate([[0.0], np.sort(rng.uniform(0.02, 0.98, 69)), [1.0]])
+    for mode in ("corrected", "optimized"):
+        o = oracle_mod.OracleModel("goddard_all", "euler_implicit", 70, time_grid=grid, pattern_mode=mode)
+        d = ctd.DOCP("goddard_all", 70, "euler_implicit", time_grid=grid, pattern_mode=mode)
+        x, y = synthetic_point(o, seed=12)
+        _compare_all(ctd, o, d, x, y, 1.3, f"goddard_all/euler_implicit/{mode}/non-uniform grid")
     B, N = 7, 100
     d = ctd.DOCP("goddard_all", N, "euler_implicit", pattern_mode="corrected", batch=B)
     o = oracle_mod.OracleModel("goddard_all", "euler_implicit", N, pattern_mode="corrected")
